@@ -1,0 +1,928 @@
+// nsg.cu — libnsg.so: C-ABI of include/nsg.h over the CUDA kernels in nsg_assemble.cuh,
+// nsg_linalg.cuh and nsg_precond.cuh (sm_100a, fp64).  One context = one GPU = one rank.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "nsg_assemble.cuh"
+#include "nsg_common.cuh"
+#include "nsg_linalg.cuh"
+
+namespace nsg {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+template <class T>
+int dev_alloc(T **p, int64_t n) {
+  *p = nullptr;
+  NSG_CUDA(cudaMalloc((void **)p, sizeof(T) * (size_t)std::max<int64_t>(n, 1)));
+  return NSG_OK;
+}
+template <class T>
+int upload(nsg_ctx *c, T **p, const T *h, int64_t n) {
+  NSG_TRY(dev_alloc(p, n));
+  if (n > 0) NSG_CUDA(cudaMemcpyAsync(*p, h, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += (int64_t)sizeof(T) * n;
+  return NSG_OK;
+}
+template <class T>
+void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+inline int grid_for(int64_t n, int threads, int cap = 148 * 16) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, cap));
+}
+inline int red_grid(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(((n >> 1) + RED_THREADS * 4 - 1) / (RED_THREADS * 4), RED_MAX_BLOCKS));
+}
+
+// -------------------------------------------------------------------------------------------------
+// reference-cell tables
+// -------------------------------------------------------------------------------------------------
+static void p2_eval(double x, double y, double psi[6], double dpsi[6][2]) {
+  const double l0 = 1 - x - y, l1 = x, l2 = y;
+  psi[0] = l0 * (2 * l0 - 1), psi[1] = l1 * (2 * l1 - 1), psi[2] = l2 * (2 * l2 - 1);
+  psi[3] = 4 * l0 * l1, psi[4] = 4 * l1 * l2, psi[5] = 4 * l2 * l0;
+  const double d[3][2] = {{-1, -1}, {1, 0}, {0, 1}};
+  for (int c = 0; c < 2; ++c) {
+    dpsi[0][c] = (4 * l0 - 1) * d[0][c];
+    dpsi[1][c] = (4 * l1 - 1) * d[1][c];
+    dpsi[2][c] = (4 * l2 - 1) * d[2][c];
+    dpsi[3][c] = 4 * (l0 * d[1][c] + l1 * d[0][c]);
+    dpsi[4][c] = 4 * (l1 * d[2][c] + l2 * d[1][c]);
+    dpsi[5][c] = 4 * (l2 * d[0][c] + l0 * d[2][c]);
+  }
+}
+static int upload_tables() {
+  FeTables t;
+  const double s = std::sqrt(15.0);
+  const double a = (6.0 - s) / 21.0, b = (6.0 + s) / 21.0;
+  const double wa = (155.0 - s) / 2400.0, wb = (155.0 + s) / 2400.0;
+  const double px[7] = {1.0 / 3.0, 1 - 2 * a, a, a, 1 - 2 * b, b, b};
+  const double py[7] = {1.0 / 3.0, a, 1 - 2 * a, a, b, 1 - 2 * b, b};
+  const double pw[7] = {9.0 / 80.0, wa, wa, wa, wb, wb, wb};
+  for (int q = 0; q < 7; ++q) {
+    t.w[q] = pw[q];
+    p2_eval(px[q], py[q], t.psi[q], t.dpsi[q]);
+    t.chi[q][0] = 1 - px[q] - py[q], t.chi[q][1] = px[q], t.chi[q][2] = py[q];
+  }
+  for (int k = 0; k < 6; ++k)
+    for (int l = 0; l < 6; ++l) {
+      double m = 0;
+      for (int q = 0; q < 7; ++q) m += t.w[q] * t.psi[q][k] * t.psi[q][l];
+      t.mhat[k][l] = m;
+    }
+  t.gl[0] = 0.5 - 0.5 * std::sqrt(0.6), t.gl[1] = 0.5, t.gl[2] = 0.5 + 0.5 * std::sqrt(0.6);
+  t.gw[0] = 5.0 / 18.0, t.gw[1] = 8.0 / 18.0, t.gw[2] = 5.0 / 18.0;
+  NSG_CUDA(cudaMemcpyToSymbol(c_fe, &t, sizeof t));
+  return NSG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// row-owner work lists (host, once)
+// -------------------------------------------------------------------------------------------------
+static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out) {
+  const int64_t T = c->n_cells, nu = c->n_own_u, nown = c->n_own;
+  const int64_t ng = kind == 0 ? nu / 2 : c->n_own_p;
+  const int nk = kind == 0 ? 6 : 3;
+  auto group_of = [&](int64_t cell, int k) -> int64_t {
+    const int32_t d = cd[15 * cell + (kind == 0 ? uidx(k) : 3 * k + 2)];
+    if (kind == 0) return d < nu ? d / 2 : -1;
+    return (d >= nu && d < nown) ? d - nu : -1;
+  };
+  std::vector<int64_t> gptr(ng + 1, 0);
+  for (int64_t cell = 0; cell < T; ++cell)
+    for (int k = 0; k < nk; ++k) {
+      const int64_t g = group_of(cell, k);
+      if (g >= 0) gptr[g + 1]++;
+    }
+  for (int64_t g = 0; g < ng; ++g) gptr[g + 1] += gptr[g];
+  const int64_t npairs = gptr[ng];
+  std::vector<int32_t> pcell(npairs);
+  std::vector<uint8_t> pk(npairs);
+  {
+    std::vector<int64_t> pos(gptr.begin(), gptr.end() - 1);
+    for (int64_t cell = 0; cell < T; ++cell)
+      for (int k = 0; k < nk; ++k) {
+        const int64_t g = group_of(cell, k);
+        if (g >= 0) {
+          pcell[pos[g]] = (int32_t)cell;
+          pk[pos[g]++] = (uint8_t)k;
+        }
+      }
+  }
+  const int64_t nchunks = (ng + NPC - 1) / NPC;
+  std::vector<int32_t> work_group(ng), chunk_iter_start(nchunks + 1, 0);
+  for (int64_t b = 0; b < nchunks; ++b) {
+    const int64_t g0 = b * NPC, g1 = std::min<int64_t>(g0 + NPC, ng);
+    int64_t mx = 0;
+    for (int64_t g = g0; g < g1; ++g) mx = std::max(mx, gptr[g + 1] - gptr[g]);
+    chunk_iter_start[b + 1] = chunk_iter_start[b] + (int32_t)mx + 1;
+  }
+  std::vector<int64_t> iter_ptr(chunk_iter_start[nchunks]);
+  std::vector<PairRec> recs(npairs);
+  int bad = 0;
+  int64_t max_stage = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_stage) reduction(+ : bad)
+  for (int64_t b = 0; b < nchunks; ++b) {
+    const int64_t g0 = b * NPC, g1 = std::min<int64_t>(g0 + NPC, ng);
+    const int n = (int)(g1 - g0);
+    int order[NPC];
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order, order + n, [&](int a, int bb) {
+      return gptr[g0 + a + 1] - gptr[g0 + a] > gptr[g0 + bb + 1] - gptr[g0 + bb];
+    });
+    for (int i = 0; i < n; ++i) work_group[g0 + i] = (int32_t)(g0 + order[i]);
+    const int niter = chunk_iter_start[b + 1] - chunk_iter_start[b] - 1;
+    int64_t w = gptr[g0];
+    for (int j = 0; j < niter; ++j) {
+      iter_ptr[chunk_iter_start[b] + j] = w;
+      for (int i = 0; i < n; ++i) {
+        const int64_t g = g0 + order[i];
+        if (gptr[g + 1] - gptr[g] <= j) break;
+        const int64_t src = gptr[g] + j;
+        PairRec r;
+        std::memset(&r, 0, sizeof r);
+        r.cell = pcell[src];
+        r.k = pk[src];
+        const int32_t *cdc = cd + 15 * (int64_t)r.cell;
+        const int64_t row = kind == 0 ? 2 * g : nu + g;
+        const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
+        if (re - rs >= 65535) bad++;
+        if (kind == 0 && c->h_rowptr[row + 2] - re != re - rs) bad++;
+        const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
+        for (int l = 0; l < 6; ++l) {
+          const int32_t tgt = cdc[uidx(l)];
+          const int32_t *p = std::lower_bound(cb, ce, tgt);
+          if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
+            bad++;
+            continue;
+          }
+          r.off[l] = (uint16_t)(p - cb);
+        }
+        if (kind == 0) {
+          for (int m = 0; m < 3; ++m) {
+            const int32_t tgt = cdc[3 * m + 2];
+            const int32_t *p = std::lower_bound(cb, ce, tgt);
+            if (p == ce || *p != tgt) {
+              bad++;
+              continue;
+            }
+            r.off[6 + m] = (uint16_t)(p - cb);
+          }
+        } else {
+          const int32_t *mb = c->h_pm_col.data() + c->h_pm_rowptr[row], *me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+          for (int m = 0; m < 3; ++m) {
+            const int32_t tgt = cdc[3 * m + 2];
+            const int32_t *p = std::lower_bound(mb, me, tgt);
+            if (p == me || *p != tgt) {
+              bad++;
+              continue;
+            }
+            r.off[6 + m] = (uint16_t)(p - mb);
+          }
+        }
+        recs[w++] = r;
+      }
+    }
+    iter_ptr[chunk_iter_start[b] + niter] = w;
+    int64_t stage;
+    if (kind == 0)
+      stage = c->h_rowptr[2 * g1] - c->h_rowptr[2 * g0];
+    else
+      stage = (c->h_rowptr[nu + g1] - c->h_rowptr[nu + g0]) + (c->h_pm_rowptr[nu + g1] - c->h_pm_rowptr[nu + g0]);
+    max_stage = std::max(max_stage, stage);
+  }
+  if (bad) return fail(NSG_ERR_ARG, "cell_dofs do not match the sparsity pattern (or a row has >= 65535 entries)");
+  out->n_groups = ng;
+  out->n_chunks = nchunks;
+  out->n_pairs = npairs;
+  out->max_stage = max_stage;
+  NSG_TRY(upload(c, &out->work_group, work_group.data(), ng));
+  NSG_TRY(upload(c, &out->chunk_iter_start, chunk_iter_start.data(), nchunks + 1));
+  NSG_TRY(upload(c, &out->iter_ptr, iter_ptr.data(), (int64_t)iter_ptr.size()));
+  NSG_TRY(upload(c, &out->recs, recs.data(), npairs));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));  // host vectors die here
+  return NSG_OK;
+}
+
+static void free_worklist(WorkList &w) {
+  dev_free(w.work_group);
+  dev_free(w.chunk_iter_start);
+  dev_free(w.iter_ptr);
+  dev_free(w.recs);
+}
+
+// chunks of consecutive rows with <= SPMV_CAP non-zeros and <= SPMV_THREADS rows
+static void make_spmv_chunks(const int64_t *rowptr, int64_t n, std::vector<int32_t> &chunks) {
+  chunks.clear();
+  chunks.push_back(0);
+  int64_t r = 0;
+  while (r < n) {
+    int64_t e = r + 1;
+    while (e < n && e - r < SPMV_THREADS && rowptr[e + 1] - rowptr[r] <= SPMV_CAP) ++e;
+    chunks.push_back((int32_t)e);
+    r = e;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// communication helpers
+// -------------------------------------------------------------------------------------------------
+static int halo_exchange(nsg_ctx *c, double *vec) {
+  if (c->n_ranks <= 1 || c->n_neighbors == 0) return NSG_OK;
+  if (c->n_send > 0) {
+    k_gather<<<grid_for(c->n_send, 256, 1 << 20), 256, 0, c->stream>>>(c->n_send, c->send_idx, vec, c->send_buf);
+    NSG_LAUNCH_CHECK(c);
+  }
+  NSG_NCCL(ncclGroupStart());
+  for (int k = 0; k < c->n_neighbors; ++k) {
+    const int64_t ns = c->send_ptr[k + 1] - c->send_ptr[k], nr = c->recv_ptr[k + 1] - c->recv_ptr[k];
+    if (ns > 0) NSG_NCCL(ncclSend(c->send_buf + c->send_ptr[k], (size_t)ns, ncclDouble, c->neighbors[k], c->comm, c->stream));
+    if (nr > 0) NSG_NCCL(ncclRecv(c->recv_buf + c->recv_ptr[k], (size_t)nr, ncclDouble, c->neighbors[k], c->comm, c->stream));
+  }
+  NSG_NCCL(ncclGroupEnd());
+  if (c->n_recv > 0) {
+    k_scatter<<<grid_for(c->n_recv, 256, 1 << 20), 256, 0, c->stream>>>(c->n_recv, c->recv_idx, c->recv_buf, vec);
+    NSG_LAUNCH_CHECK(c);
+  }
+  return NSG_OK;
+}
+static int allreduce_scalar(nsg_ctx *c, double *d) {
+  if (c->n_ranks <= 1) return NSG_OK;
+  NSG_NCCL(ncclAllReduce(d, d, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  return NSG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// vector-op wrappers (global over ranks)
+// -------------------------------------------------------------------------------------------------
+static int dev_dot(nsg_ctx *c, int64_t n, const double *a, const double *b, double *out, const int32_t *state) {
+  k_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, a, b, c->partials, c->ticket, out, state);
+  NSG_LAUNCH_CHECK(c);
+  return allreduce_scalar(c, out);
+}
+static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr, double sign, const double *V,
+                           const double *W, double *out, const int32_t *state) {
+  k_add_and_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, vv, aptr, sign, V, W, c->partials, c->ticket, out, state);
+  NSG_LAUNCH_CHECK(c);
+  return allreduce_scalar(c, out);
+}
+static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
+  NSG_TRY(halo_exchange(c, x_with_ghosts));
+  k_spmv_stream<<<(unsigned)c->spmv_n_chunks, SPMV_THREADS, 0, c->stream>>>(c->spmv_chunk_rows, c->rowptr, c->col, c->vals,
+                                                                            x_with_ghosts, y, state);
+  NSG_LAUNCH_CHECK(c);
+  return NSG_OK;
+}
+
+static AsmParams asm_params(const nsg_ctx *c) {
+  AsmParams P;
+  P.nu = c->prm.nu, P.rho = c->prm.rho, P.p_out = c->prm.p_out;
+  P.dt_inv = c->prm.use_mass ? 1.0 / c->prm.deltat : 0.0;
+  P.f0 = c->prm.forcing[0], P.f1 = c->prm.forcing[1];
+  P.use_mass = c->prm.use_mass, P.stokes = c->prm.stokes, P.neumann_id = c->prm.neumann_id;
+  return P;
+}
+
+static int launch_assembly(nsg_ctx *c) {
+  const AsmParams P = asm_params(c);
+  if (c->wl_u.n_chunks > 0) {
+    k_assemble_u<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
+        c->wl_u, c->rowptr, c->vals, c->R, c->geom, c->cell_dofs, c->sol, c->sol_old, P);
+    NSG_LAUNCH_CHECK(c);
+  }
+  if (c->wl_p.n_chunks > 0) {
+    k_assemble_p<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
+        c->wl_p, c->n_own_u, c->rowptr, c->vals, c->pm_rowptr, c->pm_vals, c->R, c->geom, P);
+    NSG_LAUNCH_CHECK(c);
+  }
+  if (c->n_bnodes > 0) {
+    k_neumann<<<grid_for(c->n_bnodes, 128, 1 << 20), 128, 0, c->stream>>>(c->n_bnodes, c->bnode_dof, c->bnode_ptr, c->bnode_face,
+                                                                        c->bnode_pos, c->bface_cell, c->bface_face, c->bface_tag,
+                                                                        c->cell_vertices, c->xy, c->R, P);
+    NSG_LAUNCH_CHECK(c);
+  }
+  return NSG_OK;
+}
+
+static int ensure_pinned(nsg_ctx *c, int64_t n) {
+  if (c->h_pinned_cap >= n) return NSG_OK;
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->h_pinned = nullptr;
+  NSG_CUDA(cudaMallocHost((void **)&c->h_pinned, sizeof(double) * (size_t)n));
+  c->h_pinned_cap = n;
+  return NSG_OK;
+}
+
+// host (pageable or pinned) -> device vector of owned length, through the pinned staging buffer
+static int put_vec(nsg_ctx *c, double *dev, const double *host, int64_t n) {
+  NSG_TRY(ensure_pinned(c, n));
+  std::memcpy(c->h_pinned, host, sizeof(double) * (size_t)n);
+  NSG_CUDA(cudaMemcpyAsync(dev, c->h_pinned, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->h2d += 8 * n;
+  return NSG_OK;
+}
+static int get_vec(nsg_ctx *c, const double *dev, double *host, int64_t n) {
+  NSG_TRY(ensure_pinned(c, n));
+  NSG_CUDA(cudaMemcpyAsync(c->h_pinned, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(host, c->h_pinned, sizeof(double) * (size_t)n);
+  c->d2h += 8 * n;
+  return NSG_OK;
+}
+
+}  // namespace nsg
+
+#include "nsg_precond.cuh"
+
+using namespace nsg;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *nsg_last_error(void) { return g_err.c_str(); }
+
+void nsg_params_default(nsg_params *p) {
+  if (!p) return;
+  p->nu = 0.001, p->rho = 1.0, p->p_out = 10.0;  // hpp:703-709
+  p->deltat = 0.05;                              // main.cpp:13
+  p->forcing[0] = 0.0, p->forcing[1] = -0.0;     // hpp:438: g = 0
+  p->neumann_id = 10;                            // cpp:320
+  p->use_mass = 1, p->stokes = 0, p->reserved = 0;
+}
+
+int nsg_create(int device, nsg_ctx **out) {
+  if (!out) return fail(NSG_ERR_ARG, "null out pointer");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(NSG_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(NSG_ERR_ARG, "device ordinal out of range");
+  NSG_CUDA(cudaSetDevice(device));
+  auto *c = new nsg_ctx;
+  c->device = device;
+  nsg_params_default(&c->prm);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(NSG_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  c->stream = c->own_stream;
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  int rc = upload_tables();
+  if (rc == NSG_OK) rc = dev_alloc(&c->partials, RED_MAX_BLOCKS);
+  if (rc == NSG_OK) rc = dev_alloc(&c->ticket, 4);
+  if (rc == NSG_OK) rc = dev_alloc(&c->scal, 64);
+  if (rc == NSG_OK) rc = dev_alloc(&c->ctl, 1);
+  if (rc == NSG_OK && cudaMallocHost((void **)&c->h_ctl, sizeof(GmresCtl)) != cudaSuccess) rc = fail(NSG_ERR_CUDA, "cudaMallocHost failed");
+  if (rc == NSG_OK) {
+    cudaMemset(c->ticket, 0, 16);
+    cudaMemset(c->scal, 0, 64 * 8);
+    cudaMemset(c->ctl, 0, sizeof(GmresCtl));
+  }
+  if (rc != NSG_OK) {
+    nsg_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return NSG_OK;
+}
+
+void nsg_destroy(nsg_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->comm) ncclCommDestroy(c->comm);
+  dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
+  dev_free(c->spmv_chunk_rows), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  free_worklist(c->wl_u), free_worklist(c->wl_p);
+  dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
+  dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
+  dev_free(c->sol), dev_free(c->sol_old), dev_free(c->delta), dev_free(c->R), dev_free(c->basis), dev_free(c->work);
+  dev_free(c->partials), dev_free(c->ticket), dev_free(c->scal), dev_free(c->ctl), dev_free(c->hist);
+  dev_free(c->dir_dofs), dev_free(c->dir_vals), dev_free(c->send_idx), dev_free(c->recv_idx), dev_free(c->send_buf), dev_free(c->recv_buf);
+  free_blocks(c);
+  if (c->h_ctl) cudaFreeHost(c->h_ctl);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int nsg_set_stream(nsg_ctx *c, void *s) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return NSG_OK;
+}
+
+int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p,
+                    const int64_t *jac_rowptr, const int32_t *jac_col, const int64_t *pm_rowptr, const int32_t *pm_col) {
+  if (!c || !jac_rowptr || !jac_col || !pm_rowptr || !pm_col) return fail(NSG_ERR_ARG, "null argument");
+  if (n_own_u < 0 || n_own_p < 0 || (n_own_u & 1)) return fail(NSG_ERR_ARG, "n_own_u must be even and sizes non-negative");
+  if (c->have_pattern) return fail(NSG_ERR_STATE, "pattern already set (the CSR is fixed for the life of the context)");
+  NSG_CUDA(cudaSetDevice(c->device));
+  c->n_own_u = n_own_u, c->n_own_p = n_own_p, c->n_own = n_own_u + n_own_p;
+  c->n_ghost_u = n_ghost_u, c->n_ghost_p = n_ghost_p;
+  c->n_loc = c->n_own + n_ghost_u + n_ghost_p;
+  if (c->n_loc >= (int64_t)INT32_MAX) return fail(NSG_ERR_ARG, "local DoF count exceeds 32-bit column indices");
+  c->stride = (c->n_loc + 31) / 32 * 32;
+  const int64_t n = c->n_own;
+  c->nnz = jac_rowptr[n], c->pm_nnz = pm_rowptr[n];
+  for (int64_t i = 0; i < n; ++i)
+    if (jac_rowptr[i + 1] < jac_rowptr[i] || pm_rowptr[i + 1] < pm_rowptr[i]) return fail(NSG_ERR_ARG, "row pointers not monotone");
+  c->h_rowptr.assign(jac_rowptr, jac_rowptr + n + 1);
+  c->h_col.assign(jac_col, jac_col + c->nnz);
+  c->h_pm_rowptr.assign(pm_rowptr, pm_rowptr + n + 1);
+  c->h_pm_col.assign(pm_col, pm_col + c->pm_nnz);
+  NSG_TRY(upload(c, &c->rowptr, jac_rowptr, n + 1));
+  NSG_TRY(upload(c, &c->col, jac_col, c->nnz));
+  NSG_TRY(upload(c, &c->pm_rowptr, pm_rowptr, n + 1));
+  NSG_TRY(upload(c, &c->pm_col, pm_col, c->pm_nnz));
+  NSG_TRY(dev_alloc(&c->vals, c->nnz));
+  NSG_TRY(dev_alloc(&c->pm_vals, c->pm_nnz));
+  NSG_CUDA(cudaMemsetAsync(c->vals, 0, 8 * (size_t)std::max<int64_t>(c->nnz, 1), c->stream));
+  NSG_CUDA(cudaMemsetAsync(c->pm_vals, 0, 8 * (size_t)std::max<int64_t>(c->pm_nnz, 1), c->stream));
+  std::vector<int32_t> chunks;
+  make_spmv_chunks(jac_rowptr, n, chunks);
+  c->spmv_n_chunks = (int64_t)chunks.size() - 1;
+  NSG_TRY(upload(c, &c->spmv_chunk_rows, chunks.data(), (int64_t)chunks.size()));
+  for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
+    NSG_TRY(dev_alloc(v, c->stride));
+    NSG_CUDA(cudaMemsetAsync(*v, 0, 8 * (size_t)c->stride, c->stream));
+  }
+  NSG_TRY(dev_alloc(&c->work, 8 * c->stride));
+  NSG_CUDA(cudaMemsetAsync(c->work, 0, 8 * 8 * (size_t)c->stride, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_pattern = true;
+  return NSG_OK;
+}
+
+int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *xy, const int32_t *cell_vertices,
+                 const int32_t *cell_dofs, int64_t n_bfaces, const int32_t *bface_cell, const int32_t *bface_face,
+                 const int32_t *bface_tag) {
+  if (!c || !xy || !cell_vertices || !cell_dofs) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern must be called before nsg_set_mesh");
+  if (c->have_mesh) return fail(NSG_ERR_STATE, "mesh already set");
+  if (n_bfaces > 0 && (!bface_cell || !bface_face || !bface_tag)) return fail(NSG_ERR_ARG, "null boundary-face arrays");
+  NSG_CUDA(cudaSetDevice(c->device));
+  for (int64_t i = 0; i < 15 * n_cells; ++i)
+    if (cell_dofs[i] < 0 || cell_dofs[i] >= c->n_loc) return fail(NSG_ERR_ARG, "cell_dofs entry out of range");
+  for (int64_t i = 0; i < 3 * n_cells; ++i)
+    if (cell_vertices[i] < 0 || cell_vertices[i] >= n_vertices) return fail(NSG_ERR_ARG, "cell_vertices entry out of range");
+  c->n_cells = n_cells, c->n_vertices = n_vertices, c->n_bfaces = n_bfaces;
+  NSG_TRY(upload(c, &c->xy, xy, 2 * n_vertices));
+  NSG_TRY(upload(c, &c->cell_vertices, cell_vertices, 3 * n_cells));
+  NSG_TRY(upload(c, &c->cell_dofs, cell_dofs, 15 * n_cells));
+  NSG_TRY(upload(c, &c->bface_cell, bface_cell, n_bfaces));
+  NSG_TRY(upload(c, &c->bface_face, bface_face, n_bfaces));
+  NSG_TRY(upload(c, &c->bface_tag, bface_tag, n_bfaces));
+  NSG_TRY(dev_alloc(&c->geom, 5 * n_cells));
+  if (n_cells > 0) {
+    k_cell_geometry<<<grid_for(n_cells, 256, 1 << 30), 256, 0, c->stream>>>(n_cells, c->xy, c->cell_vertices, c->geom);
+    NSG_LAUNCH_CHECK(c);
+  }
+  NSG_TRY(build_worklist(c, 0, cell_dofs, &c->wl_u));
+  NSG_TRY(build_worklist(c, 1, cell_dofs, &c->wl_p));
+  const size_t smem_u = 8 * (size_t)c->wl_u.max_stage, smem_p = 8 * (size_t)c->wl_p.max_stage;
+  if (smem_u > 200 * 1024 || smem_p > 200 * 1024)
+    return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  // Neumann: owned boundary P2 nodes -> (face, position on the face)
+  {
+    struct Ent {
+      int32_t dof, face, pos;
+    };
+    std::vector<Ent> ents;
+    for (int64_t i = 0; i < n_bfaces; ++i) {
+      const int64_t cell = bface_cell[i];
+      const int f = bface_face[i];
+      if (cell < 0 || cell >= n_cells || f < 0 || f > 2) return fail(NSG_ERR_ARG, "boundary face out of range");
+      const int ks[3] = {f, (f + 1) % 3, 3 + f};
+      for (int pos = 0; pos < 3; ++pos) {
+        const int32_t d = cell_dofs[15 * cell + uidx(ks[pos])];
+        if (d < c->n_own_u) ents.push_back({d, (int32_t)i, pos});
+      }
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.dof < b.dof; });
+    std::vector<int32_t> ndof, nptr{0}, nface, npos;
+    for (size_t i = 0; i < ents.size(); ++i) {
+      if (i == 0 || ents[i].dof != ents[i - 1].dof) {
+        if (i) nptr.push_back((int32_t)i);
+        ndof.push_back(ents[i].dof);
+      }
+      nface.push_back(ents[i].face);
+      npos.push_back(ents[i].pos);
+    }
+    nptr.push_back((int32_t)ents.size());
+    c->n_bnodes = (int64_t)ndof.size();
+    NSG_TRY(upload(c, &c->bnode_dof, ndof.data(), (int64_t)ndof.size()));
+    NSG_TRY(upload(c, &c->bnode_ptr, nptr.data(), (int64_t)nptr.size()));
+    NSG_TRY(upload(c, &c->bnode_face, nface.data(), (int64_t)nface.size()));
+    NSG_TRY(upload(c, &c->bnode_pos, npos.data(), (int64_t)npos.size()));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  NSG_TRY(build_blocks(c));  // sub-matrix views + level schedules of the block preconditioners
+  c->h_col.clear(), c->h_col.shrink_to_fit();
+  c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
+  c->have_mesh = true;
+  return NSG_OK;
+}
+
+int nsg_set_halo(nsg_ctx *c, int32_t n_neighbors, const int32_t *neighbors, const int64_t *send_ptr, const int32_t *send_idx,
+                 const int64_t *recv_ptr, const int32_t *recv_idx) {
+  if (!c || n_neighbors < 0) return fail(NSG_ERR_ARG, "bad argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern first");
+  c->n_neighbors = n_neighbors;
+  if (n_neighbors == 0) return NSG_OK;
+  if (!neighbors || !send_ptr || !send_idx || !recv_ptr || !recv_idx) return fail(NSG_ERR_ARG, "null argument");
+  c->neighbors.assign(neighbors, neighbors + n_neighbors);
+  c->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+  c->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+  c->n_send = send_ptr[n_neighbors], c->n_recv = recv_ptr[n_neighbors];
+  for (int64_t i = 0; i < c->n_send; ++i)
+    if (send_idx[i] < 0 || send_idx[i] >= c->n_own) return fail(NSG_ERR_ARG, "send index is not an owned DoF");
+  for (int64_t i = 0; i < c->n_recv; ++i)
+    if (recv_idx[i] < c->n_own || recv_idx[i] >= c->n_loc) return fail(NSG_ERR_ARG, "recv index is not a ghost DoF");
+  NSG_TRY(upload(c, &c->send_idx, send_idx, c->n_send));
+  NSG_TRY(upload(c, &c->recv_idx, recv_idx, c->n_recv));
+  NSG_TRY(dev_alloc(&c->send_buf, c->n_send));
+  NSG_TRY(dev_alloc(&c->recv_buf, c->n_recv));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  return NSG_OK;
+}
+
+int nsg_comm_unique_id(void *out128) {
+  if (!out128) return fail(NSG_ERR_ARG, "null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NSG_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof id);
+  return NSG_OK;
+}
+
+int nsg_comm_init(nsg_ctx *c, int rank, int n_ranks, const void *unique_id128) {
+  if (!c || !unique_id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(NSG_ERR_ARG, "bad argument");
+  NSG_CUDA(cudaSetDevice(c->device));
+  c->rank = rank, c->n_ranks = n_ranks;
+  if (n_ranks == 1) return NSG_OK;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id128, sizeof id);
+  NSG_NCCL(ncclCommInitRank(&c->comm, n_ranks, id, rank));
+  return NSG_OK;
+}
+
+int nsg_set_params(nsg_ctx *c, const nsg_params *p) {
+  if (!c || !p) return fail(NSG_ERR_ARG, "null argument");
+  if (!(p->nu > 0) || (p->use_mass && !(p->deltat > 0))) return fail(NSG_ERR_ARG, "nu and deltat must be positive");
+  c->prm = *p;
+  return NSG_OK;
+}
+
+int nsg_assemble(nsg_ctx *c) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_pattern and nsg_set_mesh must precede nsg_assemble");
+  NSG_CUDA(cudaSetDevice(c->device));
+  NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
+  NSG_TRY(launch_assembly(c));
+  NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
+  NSG_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->phase_ms[0] = ms;
+  c->blocks_stale = true;
+  return NSG_OK;
+}
+
+int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double *values, int32_t into_solution) {
+  if (!c || n < 0 || (n > 0 && (!dofs || !values))) return fail(NSG_ERR_ARG, "bad argument");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  if (n == 0) return NSG_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if (dofs[i] < 0 || dofs[i] >= c->n_own) return fail(NSG_ERR_ARG, "Dirichlet dof is not a locally owned row");
+  if (c->dir_cap < n) {
+    dev_free(c->dir_dofs), dev_free(c->dir_vals);
+    NSG_TRY(dev_alloc(&c->dir_dofs, n));
+    NSG_TRY(dev_alloc(&c->dir_vals, n));
+    c->dir_cap = n;
+  }
+  NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->dir_dofs, dofs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->dir_vals, values, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += 12 * n;
+  k_first_nonzero_diag<<<1, 32, 0, c->stream>>>(c->n_own_u, c->n_own, c->rowptr, c->col, c->vals, c->scal + 8);
+  NSG_LAUNCH_CHECK(c);
+  double *x = into_solution ? c->sol : c->delta;
+  k_apply_dirichlet<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(n, c->dir_dofs, c->dir_vals, c->n_own_u, c->rowptr, c->col,
+                                                                             c->vals, x, c->R, c->scal + 8);
+  NSG_LAUNCH_CHECK(c);
+  NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
+  NSG_CUDA(cudaEventSynchronize(c->ev1));  // dofs/values are caller-owned: the copies must have completed
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->phase_ms[1] = ms;
+  c->blocks_stale = true;
+  return NSG_OK;
+}
+
+int nsg_residual_norm(nsg_ctx *c, double *out) {
+  if (!c || !out) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  NSG_TRY(dev_dot(c, c->n_own, c->R, c->R, c->scal, nullptr));
+  double v = 0;
+  NSG_CUDA(cudaMemcpyAsync(&v, c->scal, 8, cudaMemcpyDeviceToHost, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h += 8;
+  *out = std::sqrt(v);
+  return NSG_OK;
+}
+
+__global__ void k_gmres_init(GmresCtl *c, double rel_tol, int max_steps, int n_tmp, int hist_cap) {
+  c->tol = rel_tol * sqrt(c->nrm2);
+  c->state = 0;
+  c->accumulated = 0;
+  c->dim = 0;
+  c->max_steps = max_steps;
+  c->n_tmp = n_tmp;
+  c->hist_cap = hist_cap;
+}
+
+static int read_ctl_header(nsg_ctx *c) {
+  NSG_CUDA(cudaMemcpyAsync(c->h_ctl, c->ctl, GM_HEADER_BYTES, cudaMemcpyDeviceToHost, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h += GM_HEADER_BYTES;
+  return NSG_OK;
+}
+
+int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32_t n_tmp, int32_t target, int32_t *its_out,
+              double *res_out) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  if (n_tmp < 3 || n_tmp > GM_MAX_TMP) return fail(NSG_ERR_ARG, "n_tmp_vectors must be in [3,64]");
+  if (precond < 0 || precond > 2 || max_it < 0) return fail(NSG_ERR_ARG, "bad precond / max_it");
+  NSG_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n_own, S = c->stride;
+  if (c->basis_n_tmp < n_tmp) {
+    dev_free(c->basis);
+    NSG_TRY(dev_alloc(&c->basis, (int64_t)n_tmp * S));
+    c->basis_n_tmp = n_tmp;
+  }
+  const int64_t hist_cap = std::min<int64_t>(max_it, 1 << 22);
+  if (c->hist_cap < hist_cap) {
+    dev_free(c->hist);
+    NSG_TRY(dev_alloc(&c->hist, hist_cap));
+    c->hist_cap = hist_cap;
+  }
+  NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
+  // temporaries start zeroed (a fresh TmpVectors pool); they are recycled across restarts
+  NSG_CUDA(cudaMemsetAsync(c->basis, 0, 8 * (size_t)n_tmp * (size_t)S, c->stream));
+  if (precond != NSG_PRECOND_IDENTITY) NSG_TRY(precond_initialize(c));
+  double *x = target ? c->sol : c->delta;
+  double *b = c->R;
+  GmresCtl *ctl = c->ctl;
+  const int32_t *state = &ctl->state;
+  auto V = [&](int i) { return c->basis + (int64_t)i * S; };
+  double *p = V(n_tmp - 1);
+  const int m = n_tmp - 2;
+  // SolverControl(max_it, rel_tol * ||R||)
+  NSG_TRY(dev_dot(c, n, b, b, &ctl->nrm2, nullptr));
+  k_gmres_init<<<1, 1, 0, c->stream>>>(ctl, rel_tol, max_it, n_tmp, (int)hist_cap);
+  NSG_LAUNCH_CHECK(c);
+  bool re_orth = false;
+  int rc_inner = NSG_OK;
+  const int vgrid = grid_for(n, 256);
+  while (true) {
+    // p = b - A x ; v0 = P^-1 p
+    NSG_TRY(dev_spmv(c, x, p, nullptr));
+    k_sadd<<<vgrid, 256, 0, c->stream>>>(n, p, -1.0, 1.0, b);
+    NSG_LAUNCH_CHECK(c);
+    if (precond == NSG_PRECOND_IDENTITY)
+      NSG_CUDA(cudaMemcpyAsync(V(0), p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    else if ((rc_inner = precond_vmult(c, precond, V(0), p)) != NSG_OK)
+      break;
+    NSG_TRY(dev_dot(c, n, V(0), V(0), &ctl->nrm2, nullptr));
+    k_gmres_cycle_start<<<1, 1, 0, c->stream>>>(ctl);
+    NSG_LAUNCH_CHECK(c);
+    k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, V(0), &ctl->inv_s, state);
+    NSG_LAUNCH_CHECK(c);
+    if (precond != NSG_PRECOND_IDENTITY) {  // the inner solves are host-driven: stop launching once decided
+      NSG_TRY(read_ctl_header(c));
+      if (c->h_ctl->state != 0) break;
+    }
+    bool decided = false;
+    for (int inner = 0; inner < m; ++inner) {
+      double *vv = V(inner + 1);
+      const int dim = inner + 1;
+      if (precond == NSG_PRECOND_IDENTITY) {
+        NSG_TRY(dev_spmv(c, V(inner), vv, state));
+      } else {
+        NSG_TRY(dev_spmv(c, V(inner), p, state));
+        if ((rc_inner = precond_vmult(c, precond, vv, p)) != NSG_OK) break;
+      }
+      const bool consider = !re_orth && (inner % 5 == 4);
+      if (consider) NSG_TRY(dev_dot(c, n, vv, vv, &ctl->norm_start2, state));
+      NSG_TRY(dev_dot(c, n, vv, V(0), &ctl->h[0], state));
+      for (int i = 1; i < dim; ++i) NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h[i - 1], -1.0, V(i - 1), V(i), &ctl->h[i], state));
+      NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h[dim - 1], -1.0, V(dim - 1), vv, &ctl->nrm2, state));
+      bool reorth_now = re_orth;
+      if (consider || precond != NSG_PRECOND_IDENTITY) {
+        NSG_TRY(read_ctl_header(c));
+        if (c->h_ctl->state != 0) {
+          decided = true;
+          break;
+        }
+        if (consider) {
+          const double nv = std::sqrt(c->h_ctl->nrm2), ns = std::sqrt(c->h_ctl->norm_start2);
+          if (!(nv > 10. * ns * std::sqrt(std::numeric_limits<double>::epsilon()))) re_orth = reorth_now = true;
+        }
+      }
+      if (reorth_now) {
+        NSG_TRY(dev_dot(c, n, vv, V(0), &ctl->h2[0], state));
+        for (int i = 1; i < dim; ++i) NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h2[i - 1], -1.0, V(i - 1), V(i), &ctl->h2[i], state));
+        NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h2[dim - 1], -1.0, V(dim - 1), vv, &ctl->nrm2, state));
+      }
+      k_gmres_step<<<1, 1, 0, c->stream>>>(ctl, inner, reorth_now ? 1 : 0, c->hist);
+      NSG_LAUNCH_CHECK(c);
+      k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, vv, &ctl->inv_s, state);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (rc_inner != NSG_OK) break;
+    (void)decided;
+    // x += sum_i y_i v_i with y from the back-substitution of the rotated Hessenberg matrix
+    k_gmres_backsolve<<<1, 1, 0, c->stream>>>(ctl);
+    NSG_LAUNCH_CHECK(c);
+    k_multi_axpy<<<vgrid, 256, 0, c->stream>>>(n, x, c->basis, S, ctl->y, &ctl->dim);
+    NSG_LAUNCH_CHECK(c);
+    NSG_TRY(read_ctl_header(c));
+    if (c->h_ctl->state != 0) break;
+  }
+  if (rc_inner != NSG_OK) return rc_inner;
+  NSG_TRY(read_ctl_header(c));
+  const int st = c->h_ctl->state & 0xff;
+  const int its = c->h_ctl->accumulated;
+  if (its_out) *its_out = its;
+  if (res_out) *res_out = c->h_ctl->rho;
+  c->h_hist.resize(std::min<int64_t>(its, c->hist_cap));
+  if (!c->h_hist.empty()) {
+    NSG_CUDA(cudaMemcpyAsync(c->h_hist.data(), c->hist, 8 * c->h_hist.size(), cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += 8 * (int64_t)c->h_hist.size();
+  }
+  // solution = solution_owned (cpp:587 / 556): ghost import
+  NSG_TRY(halo_exchange(c, c->sol));
+  NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
+  NSG_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->phase_ms[2] = ms;
+  if (st != 1) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "GMRES did not converge: %d steps, last residual %.6e", its, c->h_ctl->rho);
+    return fail(NSG_ERR_NO_CONVERGENCE, buf);
+  }
+  return NSG_OK;
+}
+
+int64_t nsg_gmres_history(nsg_ctx *c, double *out, int64_t cap) {
+  if (!c) return 0;
+  const int64_t n = std::min<int64_t>(cap, (int64_t)c->h_hist.size());
+  if (out) std::copy(c->h_hist.begin(), c->h_hist.begin() + n, out);
+  return (int64_t)c->h_hist.size();
+}
+
+int nsg_update_solution(nsg_ctx *c) {
+  if (!c || !c->have_pattern) return fail(NSG_ERR_STATE, "context not set up");
+  NSG_CUDA(cudaSetDevice(c->device));
+  k_sadd<<<grid_for(c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->sol, 1.0, 1.0, c->delta);
+  NSG_LAUNCH_CHECK(c);
+  return halo_exchange(c, c->sol);
+}
+
+int nsg_push_time_level(nsg_ctx *c) {
+  if (!c || !c->have_pattern) return fail(NSG_ERR_STATE, "context not set up");
+  NSG_CUDA(cudaSetDevice(c->device));
+  NSG_CUDA(cudaMemcpyAsync(c->sol_old, c->sol, 8 * (size_t)c->n_loc, cudaMemcpyDeviceToDevice, c->stream));
+  return NSG_OK;
+}
+
+static int set_owned(nsg_ctx *c, double *dev, const double *host, bool ghosts) {
+  if (!c || !host) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  NSG_TRY(put_vec(c, dev, host, c->n_own));
+  if (ghosts) {
+    NSG_TRY(halo_exchange(c, dev));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return NSG_OK;
+}
+static int get_owned(nsg_ctx *c, const double *dev, double *host, int64_t n) {
+  if (!c || !host) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  return get_vec(c, dev, host, n);
+}
+int nsg_set_solution(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->sol : nullptr, h, true); }
+int nsg_set_solution_old(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->sol_old : nullptr, h, true); }
+int nsg_set_delta(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->delta : nullptr, h, false); }
+int nsg_get_solution(nsg_ctx *c, double *h) { return get_owned(c, c ? c->sol : nullptr, h, c ? c->n_own : 0); }
+int nsg_get_delta(nsg_ctx *c, double *h) { return get_owned(c, c ? c->delta : nullptr, h, c ? c->n_own : 0); }
+int nsg_get_residual(nsg_ctx *c, double *h) { return get_owned(c, c ? c->R : nullptr, h, c ? c->n_own : 0); }
+int nsg_get_matrix_values(nsg_ctx *c, double *h) { return get_owned(c, c ? c->vals : nullptr, h, c ? c->nnz : 0); }
+int nsg_get_pm_values(nsg_ctx *c, double *h) { return get_owned(c, c ? c->pm_vals : nullptr, h, c ? c->pm_nnz : 0); }
+
+int nsg_spmv(nsg_ctx *c, const double *x, double *y) {
+  if (!c || !x || !y) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_pattern) return fail(NSG_ERR_STATE, "nsg_set_pattern first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  double *dx = c->work, *dy = c->work + c->stride;
+  NSG_TRY(put_vec(c, dx, x, c->n_own));
+  NSG_TRY(dev_spmv(c, dx, dy, nullptr));
+  return get_vec(c, dy, y, c->n_own);
+}
+
+int nsg_precond_apply(nsg_ctx *c, int32_t precond, const double *x, double *y) {
+  if (!c || !x || !y) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  double *dx = c->work, *dy = c->work + c->stride;
+  NSG_TRY(put_vec(c, dx, x, c->n_own));
+  NSG_CUDA(cudaMemsetAsync(dy, 0, 8 * (size_t)c->stride, c->stream));
+  if (precond == NSG_PRECOND_IDENTITY)
+    NSG_CUDA(cudaMemcpyAsync(dy, dx, 8 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
+  else {
+    NSG_TRY(precond_initialize(c));
+    NSG_TRY(precond_vmult(c, precond, dy, dx));
+  }
+  return get_vec(c, dy, y, c->n_own);
+}
+
+int nsg_ilu_apply(nsg_ctx *c, int32_t which, const double *x, double *y) {
+  if (!c || !x || !y || which < 0 || which > 1) return fail(NSG_ERR_ARG, "bad argument");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  CsrBlock &B = which == 0 ? c->blkA : c->blkM;
+  double *dx = c->work, *dy = c->work + c->stride;
+  NSG_TRY(put_vec(c, dx, x, B.n));
+  NSG_TRY(precond_initialize(c));
+  NSG_TRY(ilu_apply(c, B, dy, dx));
+  return get_vec(c, dy, y, B.n);
+}
+
+int nsg_time_kernel(nsg_ctx *c, int32_t what, int32_t reps, double *ms_per_launch) {
+  if (!c || !ms_per_launch || reps < 1) return fail(NSG_ERR_ARG, "bad argument");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n_own;
+  double *a = c->work + 2 * c->stride, *b = c->work + 3 * c->stride, *w = c->work + 4 * c->stride;
+  NSG_CUDA(cudaMemsetAsync(c->scal, 0, 8, c->stream));
+  NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
+  for (int r = 0; r < reps; ++r) {
+    switch (what) {
+      case 0: NSG_TRY(launch_assembly(c)); break;
+      case 1: NSG_TRY(dev_spmv(c, c->delta, a, nullptr)); break;
+      case 2: NSG_TRY(dev_add_and_dot(c, n, a, c->scal, 1.0, b, w, c->scal + 1, nullptr)); break;
+      case 3: NSG_TRY(dev_dot(c, n, a, b, c->scal + 1, nullptr)); break;
+      case 4: NSG_TRY(halo_exchange(c, c->delta)); break;
+      default: return fail(NSG_ERR_ARG, "unknown kernel id");
+    }
+  }
+  NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
+  NSG_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  *ms_per_launch = (double)ms / reps;
+  if (what == 0) c->blocks_stale = true;
+  return NSG_OK;
+}
+
+int nsg_get_counters(nsg_ctx *c, int64_t *launches, int64_t *h2d, int64_t *d2h) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  if (launches) *launches = c->launches;
+  if (h2d) *h2d = c->h2d;
+  if (d2h) *d2h = c->d2h;
+  return NSG_OK;
+}
+
+int nsg_get_phase_ms(nsg_ctx *c, double *out3) {
+  if (!c || !out3) return fail(NSG_ERR_ARG, "null argument");
+  for (int i = 0; i < 3; ++i) out3[i] = c->phase_ms[i];
+  return NSG_OK;
+}
+
+}  // extern "C"

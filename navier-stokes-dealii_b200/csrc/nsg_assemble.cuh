@@ -1,0 +1,379 @@
+// nsg_assemble.cuh — K1/K2/K3: owner-computes assembly of the Jacobian, pressure mass matrix and
+// residual (reference: src/NavierStokesSolver.cpp:203-347), Neumann faces (cpp:315-336) and
+// Dirichlet rows (cpp:349-377).
+//
+// Scheme ("row-owner"): every matrix row has exactly one owner thread.  A velocity P2 node owns
+// rows (2n, 2n+1); a pressure vertex owns its Jacobian row and its pressure-mass row.  The owner
+// walks the cells of its patch in ascending cell order (the order the reference's cell loop adds
+// them), integrates only ITS rows of each 15x15 local matrix with the 7-point rule and adds them
+// into a shared-memory image of the chunk's CSR rows.  The chunk image is then streamed to HBM
+// once, fully coalesced: every Jacobian entry is written exactly once per assembly, there are no
+// atomics, no zero-fill pass and the summation order is fixed.
+#pragma once
+#include "nsg_common.cuh"
+
+namespace nsg {
+
+constexpr int NPC = 128;  // row owners (threads) per CTA
+
+// Reference-cell tables: QGaussSimplex<2>(3) (7 points, degree 5) and FE_SimplexP(2)/(1) values.
+struct FeTables {
+  double w[7];
+  double psi[7][6];
+  double dpsi[7][6][2];
+  double chi[7][3];
+  double mhat[6][6];  // sum_q w_q psi_k psi_l  (reference mass matrix of the same rule)
+  double gl[3], gw[3];  // QGaussSimplex<1>(3) on [0,1]
+};
+__constant__ FeTables c_fe;
+
+struct AsmParams {
+  double nu, rho, p_out, dt_inv, f0, f1;
+  int32_t use_mass, stokes, neumann_id;
+};
+
+// local scalar P2 index k -> position of its x-velocity dof in the 15-dof FESystem order
+__host__ __device__ inline int uidx(int k) { return k < 3 ? 3 * k : 9 + 2 * (k - 3); }
+
+__global__ void k_cell_geometry(int64_t T, const double *__restrict__ xy, const int32_t *__restrict__ cv,
+                                double *__restrict__ geom) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  const int32_t v0 = cv[3 * c], v1 = cv[3 * c + 1], v2 = cv[3 * c + 2];
+  const double x0 = xy[2 * v0], y0 = xy[2 * v0 + 1];
+  const double J00 = xy[2 * v1] - x0, J01 = xy[2 * v2] - x0;
+  const double J10 = xy[2 * v1 + 1] - y0, J11 = xy[2 * v2 + 1] - y0;
+  const double det = J00 * J11 - J01 * J10;
+  geom[5 * c + 0] = J11 / det;   // J^-T
+  geom[5 * c + 1] = -J10 / det;
+  geom[5 * c + 2] = -J01 / det;
+  geom[5 * c + 3] = J00 / det;
+  geom[5 * c + 4] = fabs(det);
+}
+
+// ---- velocity rows: A (both Frechet terms), B^T, residual --------------------------------------
+__global__ void __launch_bounds__(NPC, 3)
+k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
+             double *__restrict__ R, const double *__restrict__ geom, const int32_t *__restrict__ cell_dofs,
+             const double *__restrict__ sol, const double *__restrict__ sol_old, const AsmParams P) {
+  extern __shared__ double s_vals[];
+  __shared__ double s_w[7], s_psi[7][6], s_dpsi[7][6][2], s_chi[7][3];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const int64_t g0 = b * NPC, g1 = min(g0 + (int64_t)NPC, wl.n_groups);
+  const int64_t rs = rowptr[2 * g0], re = rowptr[2 * g1];
+  const int cnt = (int)(re - rs);
+  for (int i = t; i < cnt; i += NPC) s_vals[i] = 0.0;
+  if (t < 7) s_w[t] = c_fe.w[t];
+  if (t < 42) (&s_psi[0][0])[t] = (&c_fe.psi[0][0])[t];
+  if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
+  if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
+  __syncthreads();
+
+  const bool have = g0 + t < g1;
+  const int64_t node = have ? wl.work_group[g0 + t] : 0;
+  const int64_t r0 = rowptr[2 * node];
+  const int len = (int)(rowptr[2 * node + 1] - r0);
+  double *row0 = s_vals + (r0 - rs), *row1 = row0 + len;
+  double res0 = 0.0, res1 = 0.0;
+
+  const int it0 = wl.chunk_iter_start[b], it1 = wl.chunk_iter_start[b + 1] - 1;  // last entry is the sentinel
+  const double nurho = P.nu * P.rho;
+  for (int it = it0; it < it1; ++it) {
+    const int64_t base = wl.iter_ptr[it];
+    const int nact = (int)(wl.iter_ptr[it + 1] - base);
+    if (t >= nact) continue;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + base + t);
+    const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+    const int64_t c = (int)ra.x;
+    const int k = (int)ra.y;
+    const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
+                 a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
+    const int32_t *cd = cell_dofs + 15 * c;
+    double u[6][2], pr[3];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const int32_t d0 = __ldg(cd + uidx(l));
+      u[l][0] = sol[d0];
+      u[l][1] = sol[d0 + 1];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
+
+    double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) A00[l] = A01[l] = A10[l] = A11[l] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) B0[m] = B1[m] = 0.0;
+
+#pragma unroll 1
+    for (int q = 0; q < 7; ++q) {
+      const double wq = adet * s_w[q];
+      double g[6][2];
+      double U0 = 0, U1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+        g[l][0] = a00 * dx + a01 * dy;
+        g[l][1] = a10 * dx + a11 * dy;
+      }
+      if (!P.stokes) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          const double pl = s_psi[q][l];
+          U0 += u[l][0] * pl;
+          U1 += u[l][1] * pl;
+          G00 += u[l][0] * g[l][0];
+          G01 += u[l][0] * g[l][1];
+          G10 += u[l][1] * g[l][0];
+          G11 += u[l][1] * g[l][1];
+        }
+      }
+      const double pk = s_psi[q][k];
+      const double gkx = a00 * s_dpsi[q][k][0] + a01 * s_dpsi[q][k][1];
+      const double gky = a10 * s_dpsi[q][k][0] + a11 * s_dpsi[q][k][1];
+      const double wpk = wq * pk;
+      const double rw = P.rho * wpk;
+      const double mk = P.use_mass ? wpk * P.dt_inv : 0.0;
+      const double vgx = nurho * wq * gkx, vgy = nurho * wq * gky;
+      // A[(a,k),(b,l)] += w [ d_ab (psi_k psi_l/dt + nu rho g_k.g_l) + rho G_ab psi_k psi_l + rho U_b (g_l)_a psi_k ]
+      const double d00 = mk + rw * G00, d01 = rw * G01, d10 = rw * G10, d11 = mk + rw * G11;
+      const double c0 = rw * U0, c1 = rw * U1;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double pl = s_psi[q][l], glx = g[l][0], gly = g[l][1];
+        const double visc = vgx * glx + vgy * gly;
+        A00[l] += visc + d00 * pl + c0 * glx;
+        A01[l] += d01 * pl + c1 * glx;
+        A10[l] += d10 * pl + c0 * gly;
+        A11[l] += visc + d11 * pl + c1 * gly;
+      }
+      // B^T[(a,k),m] -= w (g_k)_a chi_m   (cpp:272-274)
+      const double bx = -wq * gkx, by = -wq * gky;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const double cm = s_chi[q][m];
+        B0[m] += bx * cm;
+        B1[m] += by * cm;
+      }
+      // residual (cpp:287-311), time-derivative term added after the loop
+      if (!P.stokes) {
+        const double Pq = pr[0] * s_chi[q][0] + pr[1] * s_chi[q][1] + pr[2] * s_chi[q][2];
+        res0 += wq * (-nurho * (G00 * gkx + G01 * gky) - P.rho * (U0 * G00 + U1 * G10) * pk + Pq * gkx);
+        res1 += wq * (-nurho * (G10 * gkx + G11 * gky) - P.rho * (U0 * G01 + U1 * G11) * pk + Pq * gky);
+      }
+      res0 += wpk * P.f0;
+      res1 += wpk * P.f1;
+    }
+    if (!P.stokes && P.use_mass) {
+      // -rho (u - u_old)/dt psi_k integrated with the same 7-point rule = -rho/dt |detJ| sum_l mhat[k][l] (u_l - uold_l)
+      double t0 = 0, t1 = 0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const int32_t d0 = __ldg(cd + uidx(l));
+        const double mh = c_fe.mhat[k][l];
+        t0 += mh * (u[l][0] - sol_old[d0]);
+        t1 += mh * (u[l][1] - sol_old[d0 + 1]);
+      }
+      const double f = -P.rho * P.dt_inv * adet;
+      res0 += f * t0;
+      res1 += f * t1;
+    }
+    // scatter into the owner's private rows of the chunk image
+    const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+      row0[o] += A00[l];
+      row0[o + 1] += A01[l];
+      row1[o] += A10[l];
+      row1[o + 1] += A11[l];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const int l = 6 + m;
+      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+      row0[o] += B0[m];
+      row1[o] += B1[m];
+    }
+  }
+  if (have) {
+    R[2 * node] = res0;
+    R[2 * node + 1] = res1;
+  }
+  __syncthreads();
+  for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
+}
+
+// ---- pressure rows: B, the structurally present zero p-p block, pressure mass -------------------
+__global__ void __launch_bounds__(NPC, 3)
+k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
+             const int64_t *__restrict__ pm_rowptr, double *__restrict__ pm_vals, double *__restrict__ R,
+             const double *__restrict__ geom, const AsmParams P) {
+  extern __shared__ double s_vals[];
+  __shared__ double s_w[7], s_dpsi[7][6][2], s_chi[7][3];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const int64_t g0 = b * NPC, g1 = min(g0 + (int64_t)NPC, wl.n_groups);
+  const int64_t rs = rowptr[n_own_u + g0], re = rowptr[n_own_u + g1];
+  const int64_t ms = pm_rowptr[n_own_u + g0], me = pm_rowptr[n_own_u + g1];
+  const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
+  double *s_pm = s_vals + cnt;
+  for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
+  if (t < 7) s_w[t] = c_fe.w[t];
+  if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
+  if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
+  __syncthreads();
+  const bool have = g0 + t < g1;
+  const int64_t prow = n_own_u + (have ? wl.work_group[g0 + t] : 0);
+  double *row = s_vals + (rowptr[prow] - rs);
+  double *mrow = s_pm + (pm_rowptr[prow] - ms);
+  const double inv_nu = 1.0 / P.nu;
+  const int it0 = wl.chunk_iter_start[b], it1 = wl.chunk_iter_start[b + 1] - 1;
+  for (int it = it0; it < it1; ++it) {
+    const int64_t base = wl.iter_ptr[it];
+    const int nact = (int)(wl.iter_ptr[it + 1] - base);
+    if (t >= nact) continue;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + base + t);
+    const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+    const int64_t c = (int)ra.x;
+    const int m = (int)ra.y;
+    const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
+                 a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
+    double Bx[6], By[6], M[3];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) Bx[l] = By[l] = 0.0;
+    M[0] = M[1] = M[2] = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 7; ++q) {
+      const double wq = adet * s_w[q];
+      const double cm = s_chi[q][m];
+      const double wc = -wq * cm;
+      // B[m,(b,l)] -= w (g_l)_b chi_m   (cpp:277-279)
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+        Bx[l] += wc * (a00 * dx + a01 * dy);
+        By[l] += wc * (a10 * dx + a11 * dy);
+      }
+      // Mp[m,n] += w chi_m chi_n / nu   (cpp:282-284)
+#pragma unroll
+      for (int n = 0; n < 3; ++n) M[n] += cm * s_chi[q][n] * inv_nu * wq;
+    }
+    const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+      row[o] += Bx[l];
+      row[o + 1] += By[l];
+    }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int l = 6 + n;
+      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+      mrow[o] += M[n];
+    }
+  }
+  if (have) R[prow] = 0.0;  // no statement of the reference tests the pressure space
+  __syncthreads();
+  for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
+  for (int i = t; i < mcnt; i += NPC) __stcs(pm_vals + ms + i, s_pm[i]);
+}
+
+// ---- K2: Neumann faces (cpp:315-336), one thread per boundary P2 node, faces in list order ------
+__global__ void k_neumann(int64_t n_bnodes, const int32_t *__restrict__ bnode_dof, const int32_t *__restrict__ bnode_ptr,
+                          const int32_t *__restrict__ bnode_face, const int32_t *__restrict__ bnode_pos,
+                          const int32_t *__restrict__ bface_cell, const int32_t *__restrict__ bface_face,
+                          const int32_t *__restrict__ bface_tag, const int32_t *__restrict__ cv,
+                          const double *__restrict__ xy, double *__restrict__ R, const AsmParams P) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_bnodes) return;
+  double r0 = 0, r1 = 0;
+  bool any = false;
+  for (int32_t e = bnode_ptr[i]; e < bnode_ptr[i + 1]; ++e) {
+    const int32_t bf = bnode_face[e];
+    if (bface_tag[bf] != P.neumann_id) continue;
+    any = true;
+    const int64_t c = bface_cell[bf];
+    const int f = bface_face[bf];
+    const int32_t va = cv[3 * c + f], vb = cv[3 * c + (f + 1) % 3], vc = cv[3 * c + (f + 2) % 3];
+    const double ex = xy[2 * vb] - xy[2 * va], ey = xy[2 * vb + 1] - xy[2 * va + 1];
+    const double L = sqrt(ex * ex + ey * ey);
+    // outward normal: pointing away from the opposite vertex
+    double nx = ey / L, ny = -ex / L;
+    if (nx * (xy[2 * vc] - xy[2 * va]) + ny * (xy[2 * vc + 1] - xy[2 * va + 1]) > 0) nx = -nx, ny = -ny;
+    const int pos = bnode_pos[e];  // 0: first vertex of the face, 1: second vertex, 2: midpoint
+    double acc = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double s = c_fe.gl[q];
+      const double ps = pos == 0 ? (1 - s) * (1 - 2 * s) : (pos == 1 ? s * (2 * s - 1) : 4 * s * (1 - s));
+      acc += ps * (L * c_fe.gw[q]);
+    }
+    r0 += -P.p_out * nx * acc;
+    r1 += -P.p_out * ny * acc;
+  }
+  if (any) {
+    const int32_t d = bnode_dof[i];
+    R[d] += r0;
+    R[d + 1] += r1;
+  }
+}
+
+// ---- K3: MatrixTools::apply_boundary_values, Trilinos block version (cpp:375-376) ---
+// first non-zero diagonal entry of each diagonal block in the local range
+__global__ void k_first_nonzero_diag(int64_t n_own_u, int64_t n_own, const int64_t *__restrict__ rowptr,
+                                     const int32_t *__restrict__ col, const double *__restrict__ vals,
+                                     double *__restrict__ out2) {
+  const int blk = threadIdx.x;
+  if (blk > 1) return;
+  const int64_t r0 = blk == 0 ? 0 : n_own_u, r1 = blk == 0 ? n_own_u : n_own;
+  double d = 1.0;
+  for (int64_t i = r0; i < r1; ++i) {
+    double v = 0;
+    for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
+      if (col[p] == i) v = vals[p];
+    if (v != 0) {
+      d = fabs(v);
+      break;
+    }
+  }
+  out2[blk] = d;
+}
+
+// one warp per constrained row: clear the row in every block, keep a non-zero diagonal (else the
+// block's first non-zero diagonal), set the solution entry and rhs_i = g_i * diag_i
+__global__ void k_apply_dirichlet(int64_t n, const int32_t *__restrict__ dofs, const double *__restrict__ g,
+                                  int64_t n_own_u, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                  double *__restrict__ vals, double *__restrict__ x, double *__restrict__ R,
+                                  const double *__restrict__ first_nz) {
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int64_t i = dofs[w];
+  double diag = 0;
+  int64_t pd = -1;
+  for (int64_t p = rowptr[i] + lane; p < rowptr[i + 1]; p += 32) {
+    if (col[p] == i) {
+      pd = p;
+      diag = vals[p];
+    } else
+      vals[p] = 0.0;
+  }
+  const unsigned has = __ballot_sync(0xffffffffu, pd >= 0);
+  if (has) {
+    const int src = __ffs(has) - 1;
+    diag = __shfl_sync(0xffffffffu, diag, src);
+    pd = __shfl_sync(0xffffffffu, pd, src);
+  }
+  if (lane == 0) {
+    if (pd >= 0 && diag == 0.0) {
+      diag = first_nz[i < n_own_u ? 0 : 1];
+      vals[pd] = diag;
+    }
+    x[i] = g[w];
+    R[i] = g[w] * diag;
+  }
+}
+
+}  // namespace nsg

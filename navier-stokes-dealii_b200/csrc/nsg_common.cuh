@@ -1,0 +1,157 @@
+// nsg_common.cuh — context, error handling and small helpers shared by the libnsg.so sources.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nsg.h"
+
+namespace nsg {
+
+extern thread_local std::string g_err;
+int fail(int code, const std::string &msg);
+
+#define NSG_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::nsg::fail(NSG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+#define NSG_NCCL(expr)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r__ = (expr);                                                                  \
+    if (r__ != ncclSuccess)                                                                     \
+      return ::nsg::fail(NSG_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(r__));    \
+  } while (0)
+#define NSG_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != NSG_OK) return rc__; \
+  } while (0)
+#define NSG_LAUNCH_CHECK(ctx)  \
+  do {                         \
+    (ctx)->launches++;         \
+    NSG_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// One (row-owner, cell) work item of the assembly: `k` is the local scalar index of the owner's
+// node in the cell (P2 index 0..5 for a velocity node, P1 index 0..2 for a pressure row);
+// off[0..5] = offset inside the owner's Jacobian row of the column pair (2m,2m+1) of the cell's
+// six P2 nodes; off[6..8] = offset of the cell's three pressure columns (in the Jacobian row for a
+// velocity owner, in the pressure-mass row for a pressure owner).
+struct __align__(16) PairRec {
+  int32_t cell;
+  int32_t k;
+  uint16_t off[12];
+};
+static_assert(sizeof(PairRec) == 32, "PairRec must be 32 bytes");
+
+// Row-owner work lists: `n_groups` owners in chunks of NPC; inside a chunk threads are sorted by
+// patch size (descending) so iteration j is served by a prefix of the threads.
+struct WorkList {
+  int64_t n_groups = 0, n_chunks = 0, n_pairs = 0;
+  int32_t *work_group = nullptr;      // [n_groups] owner handled by thread t of its chunk
+  int32_t *chunk_iter_start = nullptr;  // [n_chunks+1] index into iter_ptr
+  int64_t *iter_ptr = nullptr;        // record offsets per (chunk, iteration), +1 sentinel per chunk
+  PairRec *recs = nullptr;            // [n_pairs]
+  int64_t max_stage = 0;              // max number of staged matrix entries of a chunk
+};
+
+// deal.II SolverGMRES bookkeeping kept on the device
+constexpr int GM_MAX_TMP = 64;
+struct GmresCtl {
+  // header (first 64 bytes are mirrored to the host at the synchronisation points)
+  double tol, rho, nrm2, norm_start2, inv_s;
+  int32_t state;  // 0 iterate, 1 success, 2 failure; | 0x100 when decided inside a cycle
+  int32_t accumulated, dim, max_steps, n_tmp, hist_cap;
+  double gamma[GM_MAX_TMP], ci[GM_MAX_TMP], si[GM_MAX_TMP], h[GM_MAX_TMP], h2[GM_MAX_TMP], y[GM_MAX_TMP];
+  double H[GM_MAX_TMP * GM_MAX_TMP];
+};
+constexpr size_t GM_HEADER_BYTES = 64;
+
+struct CsrBlock {  // a sub-matrix held separately (A, Mp, B of the block preconditioners)
+  int64_t n = 0, nnz = 0;
+  int64_t *rowptr = nullptr;
+  int32_t *col = nullptr;
+  double *val = nullptr;
+  int64_t *src = nullptr;   // position of each entry in the parent CSR (for the value refresh)
+  int64_t *diag = nullptr;  // position of the diagonal in each row
+  // level schedule of the lower / upper triangular solves and of the ILU(0) elimination
+  int32_t n_levels = 0;
+  int32_t *level_ptr = nullptr;   // [n_levels+1]
+  int32_t *level_rows = nullptr;  // [n] rows sorted by level
+  std::vector<int32_t> h_level_ptr;
+  double *fval = nullptr;  // ILU(0) factors on the same pattern
+  double *dinv = nullptr;
+  int32_t *chunk_rows = nullptr;
+  int64_t n_chunks = 0;
+};
+
+}  // namespace nsg
+
+struct nsg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  // sizes
+  int64_t n_own_u = 0, n_own_p = 0, n_own = 0, n_ghost_u = 0, n_ghost_p = 0, n_loc = 0, stride = 0;
+  int64_t nnz = 0, pm_nnz = 0;
+  int64_t n_cells = 0, n_vertices = 0, n_bfaces = 0;
+  bool have_pattern = false, have_mesh = false;
+  nsg_params prm{};
+  // host copies of the patterns kept until nsg_set_mesh has built the work lists
+  std::vector<int64_t> h_rowptr, h_pm_rowptr;
+  std::vector<int32_t> h_col, h_pm_col;
+  // device CSR
+  int64_t *rowptr = nullptr, *pm_rowptr = nullptr;
+  int32_t *col = nullptr, *pm_col = nullptr;
+  double *vals = nullptr, *pm_vals = nullptr;
+  int32_t *spmv_chunk_rows = nullptr;
+  int64_t spmv_n_chunks = 0;
+  // mesh
+  double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|
+  double *xy = nullptr;
+  int32_t *cell_vertices = nullptr, *cell_dofs = nullptr;
+  nsg::WorkList wl_u, wl_p;
+  // Neumann: boundary nodes -> faces
+  int64_t n_bnodes = 0;
+  int32_t *bnode_dof = nullptr, *bnode_ptr = nullptr, *bnode_face = nullptr, *bnode_pos = nullptr;
+  int32_t *bface_cell = nullptr, *bface_face = nullptr, *bface_tag = nullptr;
+  // vectors (stride doubles each; ghosts at [n_own, n_loc))
+  double *sol = nullptr, *sol_old = nullptr, *delta = nullptr, *R = nullptr;
+  double *basis = nullptr;  // n_tmp * stride
+  int32_t basis_n_tmp = 0;
+  double *work = nullptr;   // scratch vectors for the preconditioners (8 * stride)
+  // reductions / control
+  double *partials = nullptr;
+  unsigned int *ticket = nullptr;
+  double *scal = nullptr;  // misc device scalars
+  nsg::GmresCtl *ctl = nullptr, *h_ctl = nullptr;  // device / pinned host mirror
+  double *hist = nullptr;
+  int64_t hist_cap = 0;
+  std::vector<double> h_hist;
+  // Dirichlet scratch
+  int32_t *dir_dofs = nullptr;
+  double *dir_vals = nullptr;
+  int64_t dir_cap = 0;
+  // halo
+  int32_t n_neighbors = 0;
+  std::vector<int32_t> neighbors;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  int32_t *send_idx = nullptr, *recv_idx = nullptr;
+  double *send_buf = nullptr, *recv_buf = nullptr;
+  int64_t n_send = 0, n_recv = 0;
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  // block preconditioner state
+  nsg::CsrBlock blkA, blkM, blkB;
+  bool have_blocks = false, blocks_stale = true;
+  // staging + counters
+  double *h_pinned = nullptr;
+  int64_t h_pinned_cap = 0;
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  double phase_ms[3] = {0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};

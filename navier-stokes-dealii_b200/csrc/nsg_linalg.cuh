@@ -1,0 +1,264 @@
+// nsg_linalg.cuh — K4 SpMV on the fixed CSR and K5 Krylov vector kernels (fp64, HBM-bound).
+//
+// SpMV ("CSR-stream"): a CTA owns a chunk of consecutive rows whose non-zeros (<= SPMV_CAP) form
+// one contiguous slice of vals/col; the slice is streamed with perfectly coalesced loads, the
+// products val*x[col] are parked in shared memory and each row is then summed in CSR order by one
+// thread — the same order a CPU CSR loop uses, so the result is run-to-run deterministic.
+// Replaces jacobian_matrix.vmult inside SolverGMRES (src/NavierStokesSolver.cpp:583) and
+// B->vmult (src/NavierStokesSolver.hpp:608).
+//
+// Reductions: two-stage and deterministic — fixed grid for a given n, per-CTA partials, the last
+// CTA to finish (ticket) sums the partials in index order; the scalar stays on the device.
+#pragma once
+#include "nsg_common.cuh"
+
+namespace nsg {
+
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_CAP = 4096;  // non-zeros per chunk (32 KB of products)
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
+
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_stream(const int32_t *__restrict__ chunk_rows, const int64_t *__restrict__ rowptr,
+              const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x,
+              double *__restrict__ y, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  __shared__ double s_prod[SPMV_CAP];
+  __shared__ int64_t s_rp[SPMV_THREADS + 1];
+  const int t = threadIdx.x;
+  const int32_t r0 = chunk_rows[blockIdx.x], r1 = chunk_rows[blockIdx.x + 1];
+  const int nrows = r1 - r0;
+  const int64_t s = rowptr[r0], e = rowptr[r1];
+  const int cnt = (int)(e - s);
+  if (cnt <= SPMV_CAP) {
+    // phase 1: stream the slice
+    const double *v = vals + s;
+    const int32_t *c = col + s;
+#pragma unroll 4
+    for (int i = t; i < cnt; i += SPMV_THREADS) s_prod[i] = __ldcs(v + i) * __ldg(x + __ldcs(c + i));
+    for (int i = t; i <= nrows; i += SPMV_THREADS) s_rp[i] = rowptr[r0 + i] - s;
+    __syncthreads();
+    // phase 2: one thread per row, CSR order
+    for (int r = t; r < nrows; r += SPMV_THREADS) {
+      double acc = 0.0;
+      const int pe = (int)s_rp[r + 1];
+      for (int p = (int)s_rp[r]; p < pe; ++p) acc += s_prod[p];
+      y[r0 + r] = acc;
+    }
+  } else {
+    // a single row longer than the chunk capacity: one row per chunk by construction
+    double acc = 0.0;
+    for (int64_t p = s + t; p < e; p += SPMV_THREADS) acc += vals[p] * x[col[p]];
+    s_prod[t] = acc;
+    __syncthreads();
+    if (t == 0) {
+      double a = 0.0;
+      for (int i = 0; i < SPMV_THREADS; ++i) a += s_prod[i];
+      y[r0] = a;
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block partial -> partials[], last block sums partials in index order -> *out
+__device__ __forceinline__ void finish_reduce(double v, double *__restrict__ partials, unsigned int *ticket,
+                                              double *__restrict__ out) {
+  __shared__ double s_w[RED_THREADS / 32];
+  __shared__ bool s_last;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  v = warp_sum(v);
+  if (lane == 0) s_w[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = lane < RED_THREADS / 32 ? s_w[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) {
+      partials[blockIdx.x] = v;
+      __threadfence();
+      const unsigned int k = atomicAdd(ticket, 1u);
+      s_last = (k == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double a = 0.0;
+    for (int i = t; i < (int)gridDim.x; i += RED_THREADS) a += __ldcg(partials + i);
+    a = warp_sum(a);
+    __syncthreads();
+    if (lane == 0) s_w[wid] = a;
+    __syncthreads();
+    if (wid == 0) {
+      a = lane < RED_THREADS / 32 ? s_w[lane] : 0.0;
+      a = warp_sum(a);
+      if (lane == 0) {
+        *out = a;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+
+// out = a . b
+__global__ void __launch_bounds__(RED_THREADS)
+k_dot(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *partials, unsigned int *ticket,
+      double *out, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  double acc = 0.0;
+  const int64_t n2 = n >> 1;
+  const double2 *a2 = reinterpret_cast<const double2 *>(a), *b2 = reinterpret_cast<const double2 *>(b);
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * RED_THREADS) {
+    const double2 x = a2[i], y = b2[i];
+    acc += x.x * y.x;
+    acc += x.y * y.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc += a[n - 1] * b[n - 1];
+  finish_reduce(acc, partials, ticket, out);
+}
+
+// vv += (sign * *aptr) * V ; out = vv . W   (W may alias vv)  — Vector::add_and_dot of the MGS sweep
+__global__ void __launch_bounds__(RED_THREADS)
+k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const double *__restrict__ V, const double *W,
+              double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const double a = sign * (*aptr);
+  const bool self = (W == vv);
+  double acc = 0.0;
+  const int64_t n2 = n >> 1;
+  double2 *v2 = reinterpret_cast<double2 *>(vv);
+  const double2 *V2 = reinterpret_cast<const double2 *>(V), *W2 = reinterpret_cast<const double2 *>(W);
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * RED_THREADS) {
+    double2 x = v2[i];
+    const double2 y = V2[i];
+    x.x += a * y.x;
+    x.y += a * y.y;
+    v2[i] = x;
+    const double2 w = self ? x : W2[i];
+    acc += x.x * w.x;
+    acc += x.y * w.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double x = vv[n - 1] + a * V[n - 1];
+    vv[n - 1] = x;
+    acc += x * (self ? x : W[n - 1]);
+  }
+  finish_reduce(acc, partials, ticket, out);
+}
+
+// v *= *sptr (skipped when the factor is not finite: lucky breakdown s == 0)
+__global__ void k_scale_dev(int64_t n, double *__restrict__ v, const double *__restrict__ sptr,
+                            const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const double s = *sptr;
+  if (!isfinite(s)) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] *= s;
+}
+
+// y = alpha * y + beta * x
+__global__ void k_sadd(int64_t n, double *__restrict__ y, double alpha, double beta, const double *__restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = alpha * y[i] + beta * x[i];
+}
+// y += (sign * *aptr) * x
+__global__ void k_axpy_dev(int64_t n, double *__restrict__ y, const double *__restrict__ aptr, double sign,
+                           const double *__restrict__ x) {
+  const double a = sign * (*aptr);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+// y = (sign * *aptr) * y - x   (CG: d.sadd(beta, -1, h)) / y = (sign * *aptr) * x  when init
+__global__ void k_sadd_dev(int64_t n, double *__restrict__ y, const double *__restrict__ aptr, double beta,
+                           const double *__restrict__ x) {
+  const double a = *aptr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * y[i] + beta * x[i];
+}
+
+// x += sum_{i<dim} y_i v_i, sequential in i per entry (x.add(h(i), tmp_vectors[i]) at the cycle end)
+__global__ void k_multi_axpy(int64_t n, double *__restrict__ x, const double *__restrict__ basis, int64_t stride,
+                             const double *__restrict__ y, const int32_t *__restrict__ dimptr) {
+  const int dim = *dimptr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double a = x[i];
+    for (int k = 0; k < dim; ++k) a += y[k] * __ldcs(basis + k * stride + i);
+    x[i] = a;
+  }
+}
+
+// halo pack / unpack (K8)
+__global__ void k_gather(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                         double *__restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_scatter(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                          double *__restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[i];
+}
+
+// ---- GMRES scalar bookkeeping on the device (single thread) ------------------------------------
+__device__ inline int32_t gm_check(const GmresCtl *c, int step, double val) {
+  if (val <= c->tol) return 1;
+  if (step >= c->max_steps || isnan(val)) return 2;
+  return 0;
+}
+// cycle start: rho = ||v0||, check, gamma(0) = rho, 1/rho for the scaling kernel
+__global__ void k_gmres_cycle_start(GmresCtl *c) {
+  if (c->state != 0) return;
+  const double rho = sqrt(c->nrm2);
+  c->rho = rho;
+  c->dim = 0;
+  c->state = gm_check(c, c->accumulated, rho);
+  c->gamma[0] = rho;
+  c->inv_s = 1.0 / rho;
+  for (int i = 0; i < GM_MAX_TMP; ++i) c->h[i] = 0.0;
+}
+// after the orthogonalisation of inner step `inner`: h(inner+1) = s, Givens, residual estimate
+__global__ void k_gmres_step(GmresCtl *c, int inner, int reorth, double *hist) {
+  if (c->state != 0) return;
+  const int ld = GM_MAX_TMP;
+  c->accumulated += 1;
+  const int dim = inner + 1;
+  c->dim = dim;
+  if (reorth)
+    for (int i = 0; i < dim; ++i) c->h[i] += c->h2[i];
+  const double s = sqrt(c->nrm2);
+  c->h[inner + 1] = s;
+  c->inv_s = (s != 0.0) ? 1.0 / s : nan("");
+  for (int i = 0; i < inner; ++i) {
+    const double sn = c->si[i], cs = c->ci[i], dummy = c->h[i];
+    c->h[i] = cs * dummy + sn * c->h[i + 1];
+    c->h[i + 1] = -sn * dummy + cs * c->h[i + 1];
+  }
+  const double r = 1. / sqrt(c->h[inner] * c->h[inner] + c->h[inner + 1] * c->h[inner + 1]);
+  c->si[inner] = c->h[inner + 1] * r;
+  c->ci[inner] = c->h[inner] * r;
+  c->h[inner] = c->ci[inner] * c->h[inner] + c->si[inner] * c->h[inner + 1];
+  c->gamma[inner + 1] = -c->si[inner] * c->gamma[inner];
+  c->gamma[inner] *= c->ci[inner];
+  for (int i = 0; i < dim; ++i) c->H[i * ld + inner] = c->h[i];
+  const double rho = fabs(c->gamma[dim]);
+  c->rho = rho;
+  if (c->accumulated - 1 < c->hist_cap) hist[c->accumulated - 1] = rho;
+  c->state = gm_check(c, c->accumulated, rho);
+  if (c->state != 0) c->state |= 0x100;  // finished inside this cycle: the update below must still run
+}
+// H1.backward(h, gamma)
+__global__ void k_gmres_backsolve(GmresCtl *c) {
+  const int ld = GM_MAX_TMP;
+  const int dim = c->dim;
+  for (int i = dim - 1; i >= 0; --i) {
+    double s = c->gamma[i];
+    for (int j = i + 1; j < dim; ++j) s -= c->y[j] * c->H[i * ld + j];
+    c->y[i] = s / c->H[i * ld + i];
+  }
+}
+
+}  // namespace nsg
