@@ -8,13 +8,13 @@ CXX      := /usr/bin/g++
 CXXFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=c++17 -fPIC -Wall -Wextra
 NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wall
 
-all: $(PKG)/libnst.so $(PKG)/libnsg.so oracle/libns_oracle.so $(PKG)/host/ns_app
+all: $(PKG)/libnst.so $(PKG)/libnsg.so oracle/libns_oracle.so
 
 $(PKG)/libnst.so: $(PKG)/csrc/nst.cpp include/nst.h
 	$(CXX) $(CXXFLAGS) -shared -o $@ $<
 
 $(PKG)/libnsg.so: $(PKG)/csrc/nsg.cu $(wildcard $(PKG)/csrc/*.cuh) include/nsg.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $< -lnccl -lgomp
+	$(NVCC) $(NVFLAGS) -shared -o $@ $< -lgomp -ldl
 
 oracle/libns_oracle.so: oracle/ns_oracle.cpp
 	$(CXX) $(CXXFLAGS) -shared -o $@ $<

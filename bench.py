@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — one Newton step of the hot path (assemble_system + solve_system) on a synthetic
+uniformly refined cylinder mesh, N GPUs of one node (one process per GPU).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                      # the CPU oracle port on the host cores
+
+A "step" = zero-free owner-computes assembly of J, Mp, R (+ Neumann) + Dirichlet rows + ||R|| +
+GMRES(28, identity) capped at --gmres-its steps (the synthetic state does not converge with an
+unpreconditioned GMRES, exactly like the CPU oracle; the cap makes the step deterministic).
+metric = BASELINE.json's "Jacobian assembly MDoF/s" (value) with "GMRES time per Newton step"
+reported beside it in the same JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MESHES = {  # name -> (file, surface entity, geometric tags?, Dirichlet calls, neumann id, inlet)
+    "cmy": ("cylinder_cmy.msh", -1, False, [{11: True}, {11: True, 12: False, 13: False}], 10,
+            dict(u_m=1.5, H=0.41, y0=0.0)),
+    "mesh2d": ("cylinder_mesh2d.msh", 5, True, [{0: True}, {2: False, 3: False}], 1, dict(u_m=1.5, H=4.1, y0=-2.0)),
+}
+
+
+def analytic_state(xy, n_u):
+    sol = np.zeros(len(xy))
+    sol[0:n_u:2] = np.sin(np.pi * xy[0:n_u:2, 0]) * np.cos(np.pi * xy[0:n_u:2, 1])
+    sol[1:n_u:2] = -np.cos(np.pi * xy[1:n_u:2, 0]) * np.sin(np.pi * xy[1:n_u:2, 1])
+    sol[n_u:] = xy[n_u:, 0] * xy[n_u:, 1]
+    return sol
+
+
+def build_problem(pkg, mesh, levels, world, rank):
+    fn, ent, geo, calls, neumann, inlet = MESHES[mesh]
+    m = pkg.Mesh.read_msh(os.path.join(ROOT, "tests", "golden", fn), ent)
+    if geo:
+        m.tag_boundary_box(0, 1, 2, 3)
+    if levels:
+        m = m.refine(levels)
+    cp = m.partition_rcb(world) if world > 1 else None
+    d = pkg.Dofs(m, world, cp)
+    part = pkg.Part(d, rank)
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
+    ld, lv = part.localize_dirichlet(gd, gv)
+    xy = d.support_points()
+    sol = analytic_state(xy, d.n_u)[part.l2g[: part.n_own]]
+    return m, d, part, (ld, lv), neumann, sol
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(self.rows[0][2]) if self.rows and len(self.rows[0]) >= 9 else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_assembly(pkg, mesh, level, workers):
+    """Oracle (CPU port of the reference loops) assembling `workers` independent replicas of the
+    level-`level` mesh, one per process: the perfect-scaling upper bound of `mpirun -np workers`."""
+    if workers == 1:
+        r = _oracle_worker((mesh, level))
+        return r[0], r[1], r[2], r[3]
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_oracle_worker, [(mesh, level)] * workers)
+    n = res[0][0]
+    t_asm = max(r[1] for r in res)
+    t_it = max(r[2] for r in res)
+    return n, t_asm, t_it, res[0][3]
+
+
+def _oracle_worker(args):
+    mesh, level = args
+    pkg = importlib.import_module("navier-stokes-dealii_b200")
+    from oracle.oracle import Oracle
+    m, d, part, (ld, lv), neumann, sol = build_problem(pkg, mesh, level, 1, 0)
+    o = Oracle(part)
+    o.set_params(neumann_id=neumann)
+    o.set_solution(sol)
+    o.set_solution_old(0.9 * sol)
+    t0 = time.perf_counter()
+    o.assemble()
+    o.apply_dirichlet(ld, lv)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    its, res, rc = o.solve(0, 1e-2, 28, 30, 0)
+    t_solve = time.perf_counter() - t0
+    return d.n, t_asm, t_solve / max(its, 1), m.n_cells
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = the oracle port (deal.II/Trilinos/MPI are not in
+    this image), all host cores, bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ["OMP_NUM_THREADS"] = "1"   # one core per replica
+    pkg = importlib.import_module("navier-stokes-dealii_b200")
+    workers = os.cpu_count() or 1
+    level = args.cpu_level
+    vals, its = [], []
+    for s in range(args.warmup + args.steps):
+        n, t_asm, t_it, cells = cpu_baseline_assembly(pkg, args.mesh, level, workers)
+        if s >= args.warmup:
+            vals.append(workers * n / t_asm / 1e6)
+            its.append(t_it / workers)
+    v = float(np.mean(vals))
+    sample = (f"{workers} independent replicas (one per core, perfect-scaling bound of mpirun -np {workers}) of the "
+              f"{args.mesh} mesh refined {level}x ({cells} cells, {n} DoFs each); assembly + Dirichlet timed")
+    line = {"impl": "reference", "metric": "jacobian_assembly_mdofs", "value": v, "unit": "MDoF/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(1e3 * n * workers / (v * 1e6)),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, None),
+            "gmres_ms_per_iteration_per_replica_dof": None,
+            "cpu_baseline": {"value": v, "unit": "MDoF/s", "cores": workers, "kind": "port", "sample": sample,
+                             "gmres_s_per_iteration_at_sample_size": float(np.mean(its)) * workers},
+            "e2e": {"value": v, "unit": "MDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, d):
+    cfg = {"workload": f"synthetic uniformly refined cylinder mesh: {MESHES[args.mesh][0]} red-refined {args.levels}x, "
+                       "P2-P1, state u=(sin(pi x)cos(pi y), -cos(pi x)sin(pi y)), p=xy, u_old=0.9u",
+           "mesh": args.mesh, "levels": args.levels, "gmres_its_cap": args.gmres_its,
+           "preconditioner": "identity (reference cpp:570)", "l2": "inputs larger than L2 (no flush needed)",
+           "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, NCCL halo + allreduce"}
+    if d is not None:
+        cfg.update({"cells": int(d.mesh.n_cells), "dofs": int(d.n)})
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mesh", default="cmy", choices=list(MESHES))
+    ap.add_argument("--levels", type=int, default=5)
+    ap.add_argument("--gmres-its", type=int, default=56)
+    ap.add_argument("--cpu-level", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("navier-stokes-dealii_b200")
+
+    t_setup = time.perf_counter()
+    m, d, part, (ld, lv), neumann, sol = build_problem(pkg, args.mesh, args.levels, world, rank)
+    dev = pkg.DeviceProblem(part, local)
+    if world > 1:
+        uid = [pkg.DeviceProblem.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dev.comm_init(rank, world, uid[0])
+    dev.set_params(neumann_id=neumann)
+    dev.set_solution(sol)
+    dev.set_solution_old(0.9 * sol)
+    t_setup = time.perf_counter() - t_setup
+    N = d.n
+    zero = np.zeros(part.n_own)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        dev.assemble()
+        dev.apply_dirichlet(ld, lv)
+        r = dev.residual_norm()
+        its, res, rc = dev.solve(0, 1e-2, args.gmres_its, 30, 0, check=False)
+        if rc not in (0, -3):
+            raise RuntimeError(f"nsg_solve failed: {rc}")
+        ph = dev.phase_ms()
+        return r, its, ph
+
+    def step_e2e(host_sol):
+        t0 = time.perf_counter()
+        dev.set_solution(host_sol)                 # H2D: the step's input iterate
+        dev.assemble()
+        dev.apply_dirichlet(ld, lv)
+        r = dev.residual_norm()                    # D2H: the step's result (assembly metric)
+        t_asm = time.perf_counter() - t0
+        its, res, rc = dev.solve(0, 1e-2, args.gmres_its, 30, 0, check=False)
+        delta = dev.get_delta()                    # D2H: the Newton increment
+        return t_asm, time.perf_counter() - t0, delta
+
+    for _ in range(args.warmup):
+        dev.set_delta(zero)
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c0 = dev.counters()
+    asm_ms, dir_ms, sol_ms, its_seen = [], [], [], []
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        dev.set_delta(zero)
+        r, its, ph = step()
+        asm_ms.append(ph["assemble"]), dir_ms.append(ph["dirichlet"]), sol_ms.append(ph["solve"])
+        its_seen.append(its)
+    ev1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    c1 = dev.counters()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # device-timed phases: max over ranks
+    local_t = torch.tensor([np.mean(asm_ms) + np.mean(dir_ms), np.mean(sol_ms), wall_ms / args.steps],
+                           dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(local_t, op=dist.ReduceOp.MAX)
+    t_asm_ms, t_sol_ms, t_step_ms = (float(x) for x in local_t.cpu())
+    value = N / (t_asm_ms * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (SpMV: G launches per step) + the other two hot kernels
+    hbm, hbm_src = peaks()
+    reps = 10
+    n_rows, nnz, n_cols = part.n_own, part.nnz_jac, part.n_loc
+    spmv_ms = dev.time_kernel(1, reps)
+    spmv_bytes = 12 * nnz + 8 * n_cols + 8 * n_rows + 8 * (n_rows + 1)
+    aad_ms = dev.time_kernel(2, reps)
+    asm_k_ms = dev.time_kernel(0, reps)
+    asm_bytes = (8 * nnz + 8 * part.nnz_pm + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
+    rl = {"bound": "hbm", "kernel": "k_spmv_stream", "achieved": spmv_bytes / spmv_ms / 1e6, "peak": hbm, "unit": "GB/s",
+          "frac": spmv_bytes / spmv_ms / 1e6 / hbm, "traffic": None, "peak_source": hbm_src,
+          "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms}
+    rl_other = {
+        "k_add_and_dot": {"bound": "hbm", "achieved": 32 * n_rows / aad_ms / 1e6, "peak": hbm, "unit": "GB/s",
+                          "frac": 32 * n_rows / aad_ms / 1e6 / hbm, "ms_per_launch": aad_ms},
+        "assembly(k_assemble_u+k_assemble_p+k_neumann)": {
+            "bound": "hbm", "achieved": asm_bytes / asm_k_ms / 1e6, "peak": hbm, "unit": "GB/s",
+            "frac": asm_bytes / asm_k_ms / 1e6 / hbm, "ms_per_launch": asm_k_ms, "algorithmic_bytes_per_launch": asm_bytes,
+            "mdofs": part.n_own / asm_k_ms / 1e3}}
+
+    # end-to-end through the public API with host buffers
+    e2e_asm, e2e_step = [], []
+    host_sol = sol.copy()
+    for _ in range(2):
+        step_e2e(host_sol)
+    barrier()
+    for _ in range(max(2, args.steps // 2)):
+        dev.set_delta(zero)
+        a, s, _ = step_e2e(host_sol)
+        e2e_asm.append(a), e2e_step.append(s)
+    barrier()
+    e2e_t = torch.tensor([np.mean(e2e_asm), np.mean(e2e_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_asm_s, e2e_step_s = (float(x) for x in e2e_t.cpu())
+
+    if rank == 0:
+        line = {"metric": "jacobian_assembly_mdofs", "value": value, "unit": "MDoF/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, d),
+                "assembly_ms": t_asm_ms, "gmres_ms_per_newton_step": t_sol_ms, "gmres_its": int(its_seen[-1]),
+                "gmres_ms_per_iteration": t_sol_ms / max(1, its_seen[-1]), "setup_s": t_setup,
+                "gpu_launches": int(c1["launches"] - c0["launches"]), "clocks": clocks, "roofline": rl,
+                "roofline_other": rl_other,
+                "e2e": {"value": N / e2e_asm_s / 1e6, "unit": "MDoF/s",
+                        "h2d_bytes_per_step": int(8 * part.n_own + 12 * len(ld)), "d2h_bytes_per_step": int(8 + 8 * part.n_own),
+                        "newton_step_ms": 1e3 * e2e_step_s,
+                        "what": "set_solution(host) + assemble + Dirichlet + residual norm to host; newton_step_ms adds "
+                                "GMRES and get_delta(host)"}}
+        if not args.no_cpu_baseline and world == 1:
+            workers = 1
+            n_s, t_a, t_it, cells = cpu_baseline_assembly(pkg, args.mesh, args.cpu_level + 1, workers)
+            line["cpu_baseline"] = {"value": n_s / t_a / 1e6, "unit": "MDoF/s", "cores": workers, "kind": "port",
+                                    "sample": f"oracle (scalar C++ port of cpp:178-378) on the {args.mesh} mesh refined "
+                                              f"{args.cpu_level + 1}x: {cells} cells, {n_s} DoFs, one assembly + Dirichlet",
+                                    "gmres_s_per_iteration_at_sample_size": t_it}
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

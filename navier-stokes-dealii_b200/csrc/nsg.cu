@@ -243,13 +243,13 @@ static int halo_exchange(nsg_ctx *c, double *vec) {
     k_gather<<<grid_for(c->n_send, 256, 1 << 20), 256, 0, c->stream>>>(c->n_send, c->send_idx, vec, c->send_buf);
     NSG_LAUNCH_CHECK(c);
   }
-  NSG_NCCL(ncclGroupStart());
+  NSG_NCCL(nccl_api().GroupStart());
   for (int k = 0; k < c->n_neighbors; ++k) {
     const int64_t ns = c->send_ptr[k + 1] - c->send_ptr[k], nr = c->recv_ptr[k + 1] - c->recv_ptr[k];
-    if (ns > 0) NSG_NCCL(ncclSend(c->send_buf + c->send_ptr[k], (size_t)ns, ncclDouble, c->neighbors[k], c->comm, c->stream));
-    if (nr > 0) NSG_NCCL(ncclRecv(c->recv_buf + c->recv_ptr[k], (size_t)nr, ncclDouble, c->neighbors[k], c->comm, c->stream));
+    if (ns > 0) NSG_NCCL(nccl_api().Send(c->send_buf + c->send_ptr[k], (size_t)ns, ncclDouble, c->neighbors[k], c->comm, c->stream));
+    if (nr > 0) NSG_NCCL(nccl_api().Recv(c->recv_buf + c->recv_ptr[k], (size_t)nr, ncclDouble, c->neighbors[k], c->comm, c->stream));
   }
-  NSG_NCCL(ncclGroupEnd());
+  NSG_NCCL(nccl_api().GroupEnd());
   if (c->n_recv > 0) {
     k_scatter<<<grid_for(c->n_recv, 256, 1 << 20), 256, 0, c->stream>>>(c->n_recv, c->recv_idx, c->recv_buf, vec);
     NSG_LAUNCH_CHECK(c);
@@ -258,7 +258,7 @@ static int halo_exchange(nsg_ctx *c, double *vec) {
 }
 static int allreduce_scalar(nsg_ctx *c, double *d) {
   if (c->n_ranks <= 1) return NSG_OK;
-  NSG_NCCL(ncclAllReduce(d, d, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  NSG_NCCL(nccl_api().AllReduce(d, d, 1, ncclDouble, ncclSum, c->comm, c->stream));
   return NSG_OK;
 }
 
@@ -404,7 +404,7 @@ void nsg_destroy(nsg_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->spmv_chunk_rows), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p);
@@ -569,8 +569,9 @@ int nsg_set_halo(nsg_ctx *c, int32_t n_neighbors, const int32_t *neighbors, cons
 int nsg_comm_unique_id(void *out128) {
   if (!out128) return fail(NSG_ERR_ARG, "null argument");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!nccl_api().handle) return fail(NSG_ERR_NCCL, nccl_api().error);
   ncclUniqueId id;
-  NSG_NCCL(ncclGetUniqueId(&id));
+  NSG_NCCL(nccl_api().GetUniqueId(&id));
   std::memcpy(out128, &id, sizeof id);
   return NSG_OK;
 }
@@ -580,9 +581,10 @@ int nsg_comm_init(nsg_ctx *c, int rank, int n_ranks, const void *unique_id128) {
   NSG_CUDA(cudaSetDevice(c->device));
   c->rank = rank, c->n_ranks = n_ranks;
   if (n_ranks == 1) return NSG_OK;
+  if (!nccl_api().handle) return fail(NSG_ERR_NCCL, nccl_api().error);
   ncclUniqueId id;
   std::memcpy(&id, unique_id128, sizeof id);
-  NSG_NCCL(ncclCommInitRank(&c->comm, n_ranks, id, rank));
+  NSG_NCCL(nccl_api().CommInitRank(&c->comm, n_ranks, id, rank));
   return NSG_OK;
 }
 

@@ -1,7 +1,7 @@
 // nsg_common.cuh — context, error handling and small helpers shared by the libnsg.so sources.
 #pragma once
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include "nsg_nccl.cuh"
 #include <stdint.h>
 
 #include <string>
@@ -24,7 +24,7 @@ int fail(int code, const std::string &msg);
   do {                                                                                          \
     ncclResult_t r__ = (expr);                                                                  \
     if (r__ != ncclSuccess)                                                                     \
-      return ::nsg::fail(NSG_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(r__));    \
+      return ::nsg::fail(NSG_ERR_NCCL, std::string(#expr) + ": " + ::nsg::nccl_api().GetErrorString(r__)); \
   } while (0)
 #define NSG_TRY(expr)          \
   do {                         \

@@ -19,6 +19,7 @@ sol = np.zeros(d.n)
 sol[:d.n_u:2] = np.sin(np.pi*xy[:d.n_u:2,0])*np.cos(np.pi*xy[:d.n_u:2,1])
 sol[1:d.n_u:2] = -np.cos(np.pi*xy[1:d.n_u:2,0])*np.sin(np.pi*xy[1:d.n_u:2,1])
 sol[d.n_u:] = xy[d.n_u:,0]*xy[d.n_u:,1]
+sol *= 0.02
 old = 0.9*sol
 for obj in (dev, o):
     obj.set_solution(sol); obj.set_solution_old(old); obj.assemble()

@@ -1,0 +1,228 @@
+"""-m gpu: the CUDA path (through the C-ABI, libnsg.so) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): assembled entries and residuals 1e-12 (relative to the
+largest entry of the row — entries are sums of cancelling cell contributions), GMRES / Newton
+iterates and residual histories 1e-8 relative.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import analytic_state, mesh_path, row_scaled_err
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "cmy": ("cylinder_cmy.msh", -1, [{11: True}, {11: True, 12: False, 13: False}], 10, dict(u_m=1.5, H=0.41)),
+    "mesh2d": ("cylinder_mesh2d.msh", 5, None, 1, dict(u_m=1.5, H=4.1, y0=-2.0)),
+    "square": ("square_h0.05.msh", -1, [{0: True}, {2: False, 3: False}], 1, dict(u_m=1.5, H=1.0)),
+}
+
+
+def build(pkg, case, levels=0):
+    name, ent, calls, neumann, inlet = CASES[case]
+    m = pkg.Mesh.read_msh(mesh_path(name), ent)
+    if case == "mesh2d":      # untagged and clockwise in the file: geometric ids
+        m.tag_boundary_box(0, 1, 2, 3)
+        calls = [{0: True}, {2: False, 3: False}]
+    if levels:
+        m = m.refine(levels)
+    d = pkg.Dofs(m)
+    part = pkg.Part(d, 0)
+    return m, d, part, calls, neumann, inlet
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("mode", ["newton", "steady", "stokes"])
+def test_assembly_parity(pkg, case, mode):
+    m, d, part, calls, neumann, inlet = build(pkg, case)
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    kw = dict(nu=0.001, rho=1.3, p_out=10.0, deltat=0.05, forcing=(0.0, -0.7), neumann_id=neumann,
+              use_mass=0 if mode == "steady" else 1, stokes=1 if mode == "stokes" else 0)
+    dev.set_params(**kw)
+    o.set_params(**kw)
+    sol, old = analytic_state(d), analytic_state(d, 0.9)
+    for obj in (dev, o):
+        obj.set_solution(sol)
+        obj.set_solution_old(old)
+        obj.assemble()
+    assert row_scaled_err(dev.get_matrix_values(), o.get_matrix_values(), part.jac_rowptr) <= 1e-12
+    assert row_scaled_err(dev.get_pm_values(), o.get_pm_values(), part.pm_rowptr) <= 1e-12
+    Rd, Ro = dev.get_residual(), o.get_residual()
+    assert np.abs(Rd - Ro).max() <= 1e-12 * np.abs(Ro).max()
+    assert (Rd[d.n_u:] == 0).all()
+    # Dirichlet rows (non-zero inlet data so that rhs_i = g_i * diag_i is exercised)
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
+    ld, lv = part.localize_dirichlet(gd, gv)
+    assert np.array_equal(ld, gd)
+    dev.apply_dirichlet(ld, lv, into_solution=(mode == "stokes"))
+    o.apply_dirichlet(gd, gv, into_solution=(mode == "stokes"))
+    assert row_scaled_err(dev.get_matrix_values(), o.get_matrix_values(), part.jac_rowptr) <= 1e-12
+    Rd, Ro = dev.get_residual(), o.get_residual()
+    assert np.abs(Rd - Ro).max() <= 1e-12 * np.abs(Ro).max()
+    assert abs(dev.residual_norm() - o.residual_norm()) <= 1e-12 * o.residual_norm()
+    x = dev.get_solution() if mode == "stokes" else dev.get_delta()
+    assert np.array_equal(x[gd], gv)
+    dev.close()
+
+
+def test_exact_cell_on_device(pkg, golden):
+    """The sympy known-answer vector straight against the CUDA kernels (one cell)."""
+    import os
+    g = np.load(os.path.join(golden, "exact_cell.npz"))
+    f = int(g["neumann_face"])
+    m = pkg.Mesh.from_arrays(g["vertices"], np.array([[0, 1, 2]], np.int32), np.array([[f, (f + 1) % 3]], np.int32),
+                             np.array([10], np.int32))
+    d = pkg.Dofs(m)
+    part = pkg.Part(d, 0)
+    cd = d.cell_dofs[0]
+    dev = pkg.DeviceProblem(part, 0)
+    dev.set_params(nu=float(g["nu"]), rho=float(g["rho"]), p_out=float(g["p_out"]), deltat=float(g["deltat"]),
+                   forcing=tuple(g["forcing"]), neumann_id=10)
+    sol, old = np.zeros(15), np.zeros(15)
+    sol[cd], old[cd] = g["sol"], g["old"]
+    dev.set_solution(sol)
+    dev.set_solution_old(old)
+    dev.assemble()
+    J = sp.csr_matrix((dev.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(15, 15)).toarray()
+    assert np.abs(J[np.ix_(cd, cd)] - g["A"]).max() <= 1e-13 * np.abs(g["A"]).max()
+    exact = g["R"] + g["N"]
+    assert np.abs(dev.get_residual()[cd] - exact).max() <= 1e-13 * np.abs(exact).max()
+    dev.close()
+
+
+def test_spmv_parity_and_linearity(pkg):
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy", levels=1)
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    for obj in (dev, o):
+        obj.set_params()
+        obj.set_solution(analytic_state(d, 0.3))
+        obj.assemble()
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(d.n), rng.standard_normal(d.n)
+    ax, ay = dev.spmv(x), dev.spmv(y)
+    ref = o.spmv(x)
+    assert np.abs(ax - ref).max() <= 1e-13 * np.abs(ref).max()
+    J = sp.csr_matrix((dev.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(d.n, d.n))
+    assert np.abs(ax - J @ x).max() <= 1e-13 * np.abs(ref).max()
+    lin = dev.spmv(2.0 * x - 0.5 * y)
+    assert np.abs(lin - (2.0 * ax - 0.5 * ay)).max() <= 1e-12 * np.abs(lin).max()
+    assert np.array_equal(dev.spmv(x), ax)        # run-to-run deterministic
+    dev.close()
+
+
+def newton_trajectory(obj, part_or_none, gd, gv, n_steps, n, precond=0):
+    """The reference's time loop (cpp:658-678) + solve_newton (cpp:590-627) on either backend."""
+    hist = []
+    obj.set_solution(np.zeros(n))
+    for step in range(n_steps):
+        obj.push_time_level()
+        it, r = 0, 1e300
+        while it < 1000 and r > 1e-2:
+            obj.assemble()
+            obj.apply_dirichlet(gd, gv)
+            r = obj.residual_norm()
+            its = None
+            if r > 1e-2:
+                its, res, rc = obj.solve(precond, 1e-2, 100000, 30, 0)
+                assert rc == 0
+                obj.update_solution()
+            hist.append((step, it, r, its))
+            it += 1
+    return hist, obj.get_solution()
+
+
+def test_reference_run_cmy(pkg):
+    """Config 1 on the mesh the reference opens (cpp:15) with its shipped parameters: 2 time steps of
+    Newton + GMRES(28, identity). Residual history, GMRES step counts and iterates vs the oracle."""
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy")
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=0.0, **inlet))
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    dev.set_params()
+    o.set_params()
+    hd, sd = newton_trajectory(dev, part, gd, gv, 2, d.n)
+    ho, so = newton_trajectory(o, None, gd, gv, 2, d.n)
+    assert [(a, b, c2) for a, b, _, c2 in hd] == [(a, b, c2) for a, b, _, c2 in ho]
+    for (_, _, rd, _), (_, _, ro, _) in zip(hd, ho):
+        assert abs(rd - ro) <= 1e-8 * max(ro, 1e-2)
+    assert np.abs(sd - so).max() <= 1e-8 * np.abs(so).max()
+    # the shipped set-up converges towards u = 0, p = 10
+    assert np.abs(sd[d.n_u:] - 10).max() < 0.5
+    dev.close()
+
+
+def test_gmres_history_parity_live_inlet(pkg):
+    """Non-trivial data: inlet switched on (time factor 1), small convecting state, restarts exercised."""
+    m, d, part, calls, neumann, inlet = build(pkg, "square")
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    for obj in (dev, o):
+        obj.set_params(nu=0.01, neumann_id=neumann)
+        obj.set_solution(analytic_state(d, 0.05))
+        obj.set_solution_old(analytic_state(d, 0.045))
+        obj.assemble()
+        obj.apply_dirichlet(gd, gv)
+    rd = dev.solve(0, 1e-6, 100000, 30, 0)
+    ro = o.solve(0, 1e-6, 100000, 30, 0)
+    assert rd[0] == ro[0] and rd[0] > 28 and rd[2] == ro[2] == 0
+    h1, h2 = dev.gmres_history(), o.gmres_history()
+    assert len(h1) == len(h2) == rd[0]
+    assert np.abs(h1 / h2 - 1).max() <= 1e-8
+    xd, xo = dev.get_delta(), o.get_delta()
+    assert np.abs(xd - xo).max() <= 1e-8 * np.abs(xo).max()
+    # size-independent property: the accepted increment satisfies the stopping test for real
+    J = sp.csr_matrix((dev.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(d.n, d.n))
+    b = dev.get_residual()
+    assert np.linalg.norm(J @ xd - b) <= 1.5e-6 * np.linalg.norm(b)
+    dev.close()
+
+
+def test_no_convergence_is_reported(pkg):
+    m, d, part, calls, neumann, inlet = build(pkg, "square")
+    dev = pkg.DeviceProblem(part, 0)
+    dev.set_params(nu=0.01, neumann_id=neumann)
+    dev.set_solution(analytic_state(d, 0.05))
+    dev.assemble()
+    its, res, rc = dev.solve(0, 1e-12, 40, 30, 0, check=False)
+    assert rc == -3 and its == 40
+    with pytest.raises(Exception, match="did not converge"):
+        dev.solve(0, 1e-12, 5, 30, 0)
+    dev.close()
+
+
+def test_full_size_properties(pkg):
+    """At a refined size the oracle would be slow for: properties that need no oracle.
+    (a) fixed point: R(u=0,p=10) = 0; (b) assembly is deterministic; (c) row sums of the Stokes
+    viscous block vanish; (d) the pressure mass matrix sums to area/nu."""
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy", levels=3)     # 412 672 cells, 1.87 M DoFs
+    dev = pkg.DeviceProblem(part, 0)
+    dev.set_params()
+    sol = np.zeros(d.n)
+    sol[d.n_u:] = 10.0
+    dev.set_solution(sol)
+    dev.set_solution_old(sol)
+    dev.assemble()
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=0.0, **inlet))
+    dev.apply_dirichlet(gd, gv)
+    assert dev.residual_norm() < 1e-11
+    dev.set_solution(analytic_state(d))
+    dev.assemble()
+    v1, r1 = dev.get_matrix_values(), dev.get_residual()
+    dev.assemble()
+    assert np.array_equal(v1, dev.get_matrix_values()) and np.array_equal(r1, dev.get_residual())
+    area = 7 * 4 - np.pi * 0.25
+    pm = dev.get_pm_values().sum() * 0.001
+    assert abs(pm - area) < 2e-3 * area      # polygonal approximation of the disc (no boundary snapping)
+    dev.set_params(stokes=1)
+    dev.assemble()
+    ones = np.zeros(d.n)
+    ones[0:d.n_u:2] = 1.0
+    y = dev.spmv(ones)
+    scale = np.abs(dev.get_matrix_values()).max()
+    assert np.abs(y[:d.n_u]).max() <= 1e-11 * scale
+    dev.close()

@@ -1,0 +1,176 @@
+"""Host topology (libnst.so) against the independent structural facts of SURVEY §8d."""
+import numpy as np
+import pytest
+
+from conftest import MESH_FACTS, mesh_path
+
+
+@pytest.mark.parametrize("key", list(MESH_FACTS))
+def test_counts_match_survey(pkg, key):
+    name, ent = key
+    f = MESH_FACTS[key]
+    m = pkg.Mesh.read_msh(mesh_path(name), ent)
+    assert (m.n_vertices, m.n_cells, m.n_edges) == (f["V"], f["T"], f["E"])
+    # Euler characteristic of a planar domain with h holes: V - E + T = 1 - h
+    holes = 1 if "cylinder" in name else 0
+    assert m.n_vertices - m.n_edges + m.n_cells == 1 - holes
+    d = pkg.Dofs(m)
+    assert (d.n_u, d.n_p) == (f["n_u"], f["n_p"])
+    assert d.n_u == 2 * (m.n_vertices + m.n_edges) and d.n_p == m.n_vertices
+    if f["nnz"]:
+        for kind in range(3):
+            rp, col = d.sparsity(kind)
+            assert rp[-1] == f["nnz"][kind] == len(col)
+
+
+def test_overlapping_entities_rejected(pkg):
+    # mesh2d.msh as a whole has edges shared by 3 triangles
+    with pytest.raises(Exception, match="more than two cells"):
+        pkg.Mesh.read_msh(mesh_path("cylinder_mesh2d.msh"), -1)
+
+
+def test_missing_file_and_bad_args(pkg):
+    with pytest.raises(Exception, match="cannot open"):
+        pkg.Mesh.read_msh("/nonexistent.msh")
+
+
+def test_orientation_fixed(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("cylinder_mesh2d.msh"), 5)
+    assert m.n_inverted == 288  # all clockwise in the file
+    xy, c = m.xy, m.cells
+    a, b, cc = xy[c[:, 0]], xy[c[:, 1]], xy[c[:, 2]]
+    det = (b[:, 0] - a[:, 0]) * (cc[:, 1] - a[:, 1]) - (cc[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    assert (det > 0).all()
+
+
+def test_boundary_ids_cmy(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("cylinder_cmy.msh"))
+    _, _, tag = m.boundary_faces()
+    counts = {int(t): int((tag == t).sum()) for t in np.unique(tag)}
+    assert counts == {10: 40, 11: 40, 12: 140, 13: 32}
+
+
+def test_dof_numbering_first_visit(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("square_h0.1.msh"))
+    d = pkg.Dofs(m)
+    cd = d.cell_dofs
+    # replay distribute_dofs + component_wise in pure Python
+    node_of, p_of, nn, npp = {}, {}, 0, 0
+    cells, ce = m.cells, m.cell_edges
+    for c in range(m.n_cells):
+        for k in range(3):
+            v = ("v", int(cells[c, k]))
+            if v not in node_of:
+                node_of[v] = nn
+                nn += 1
+                p_of[v] = npp
+                npp += 1
+        for k in range(3):
+            e = ("e", int(ce[c, k]))
+            if e not in node_of:
+                node_of[e] = nn
+                nn += 1
+    n_u = 2 * nn
+    for c in range(m.n_cells):
+        exp = []
+        for k in range(3):
+            v = ("v", int(cells[c, k]))
+            exp += [2 * node_of[v], 2 * node_of[v] + 1, n_u + p_of[v]]
+        for k in range(3):
+            e = ("e", int(ce[c, k]))
+            exp += [2 * node_of[e], 2 * node_of[e] + 1]
+        assert list(cd[c]) == exp
+
+
+def test_sparsity_is_all_cell_pairs(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("square_h0.1.msh"))
+    d = pkg.Dofs(m)
+    cd = d.cell_dofs
+    n_u = d.n_u
+    sets = [[set() for _ in range(d.n)] for _ in range(3)]
+    for c in range(m.n_cells):
+        for i in cd[c]:
+            for j in cd[c]:
+                pp = i >= n_u and j >= n_u
+                sets[0][i].add(j)
+                if not pp:
+                    sets[1][i].add(j)
+                else:
+                    sets[2][i].add(j)
+    for kind in range(3):
+        rp, col = d.sparsity(kind)
+        for i in range(d.n):
+            assert list(col[rp[i]:rp[i + 1]]) == sorted(sets[kind][i])
+
+
+def test_refinement(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("cylinder_cmy.msh"))
+    r = m.refine(2)
+    assert r.n_cells == 16 * m.n_cells
+    assert r.n_vertices - r.n_edges + r.n_cells == 0
+    assert r.n_boundary_edges == 4 * m.n_boundary_edges
+    _, _, t0 = m.boundary_faces()
+    _, _, t2 = r.boundary_faces()
+    for t in np.unique(t0):
+        assert (t2 == t).sum() == 4 * (t0 == t).sum()
+    # area is preserved and children keep the orientation
+    def area(mm):
+        xy, c = mm.xy, mm.cells
+        a, b, cc = xy[c[:, 0]], xy[c[:, 1]], xy[c[:, 2]]
+        return 0.5 * ((b[:, 0] - a[:, 0]) * (cc[:, 1] - a[:, 1]) - (cc[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+    assert (area(r) > 0).all()
+    np.testing.assert_allclose(area(r).sum(), area(m).sum(), rtol=1e-13)
+
+
+def test_dirichlet_list(pkg):
+    m = pkg.Mesh.read_msh(mesh_path("cylinder_cmy.msh"))
+    d = pkg.Dofs(m)
+    inlet = dict(u_m=1.5, H=0.41, time_factor=1.0)
+    gd, gv = d.dirichlet_values([{11: True}, {11: True, 12: False, 13: False}], inlet)
+    assert len(gd) == 850 and (np.diff(gd) > 0).all() and gd.max() < d.n_u
+    xy = d.support_points()
+    on_inlet = np.isclose(xy[gd, 0], 5.0)
+    ux = (gd % 2 == 0)
+    y = xy[gd, 1]
+    exp = np.where(on_inlet & ux, 4 * 1.5 * y * (0.41 - y) / 0.41 ** 2, 0.0)
+    # corners shared by the inlet and a wall take whichever face is visited last; everything else is exact
+    interior = ~(on_inlet & (np.isclose(np.abs(y), 2.0)))
+    np.testing.assert_allclose(gv[interior], exp[interior], rtol=0, atol=1e-14)
+    # frozen time: all values are zero
+    _, gv0 = d.dirichlet_values([{11: True}, {11: True, 12: False, 13: False}], dict(u_m=1.5, H=0.41, time_factor=0.0))
+    assert (gv0 == 0).all()
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_partition_and_local_problems(pkg, n_parts):
+    m = pkg.Mesh.read_msh(mesh_path("cylinder_cmy.msh"))
+    cp = m.partition_rcb(n_parts)
+    sizes = np.bincount(cp, minlength=n_parts)
+    assert sizes.min() > 0 and sizes.max() - sizes.min() <= n_parts
+    d1 = pkg.Dofs(m)
+    d = pkg.Dofs(m, n_parts, cp)
+    assert (d.n_u, d.n_p) == (d1.n_u, d1.n_p)
+    assert np.array_equal(np.unique(d.cell_dofs), np.arange(d.n))
+    rp, col = d.sparsity(0)
+    parts = [pkg.Part(d, r) for r in range(n_parts)]
+    owned = np.concatenate([p.l2g[:p.n_own] for p in parts])
+    assert sorted(owned.tolist()) == list(range(d.n))          # every DoF owned exactly once
+    assert sum(p.n_owned_cells for p in parts) == m.n_cells
+    for p in parts:
+        # block-wise, part-major numbering: owned ranges are contiguous per block
+        assert (np.diff(p.l2g[:p.n_own_u]) == 1).all() and (np.diff(p.l2g[p.n_own_u:p.n_own]) == 1).all()
+        # the local pattern is the global pattern of the owned rows, in local column ids
+        for i in np.random.default_rng(p.rank).integers(0, p.n_own, 50):
+            g = p.l2g[i]
+            loc = p.l2g[p.jac_col[p.jac_rowptr[i]:p.jac_rowptr[i + 1]]]
+            assert sorted(loc.tolist()) == col[rp[g]:rp[g + 1]].tolist()
+            assert (np.diff(p.jac_col[p.jac_rowptr[i]:p.jac_rowptr[i + 1]]) > 0).all()
+    # halo plans are mutually consistent: what r sends to k is what k expects from r, same order
+    for p in parts:
+        for a, k in enumerate(p.neighbors):
+            q = parts[k]
+            b = list(q.neighbors).index(p.rank)
+            sent = p.l2g[p.send_idx[p.send_ptr[a]:p.send_ptr[a + 1]]]
+            recv = q.l2g[q.recv_idx[q.recv_ptr[b]:q.recv_ptr[b + 1]]]
+            assert sent.tolist() == recv.tolist() and len(sent) > 0
+        assert p.n_recv == p.n_ghost_u + p.n_ghost_p
