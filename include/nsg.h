@@ -144,6 +144,10 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
  * Neumann, no Dirichlet), 1 = SpMV J*delta, 2 = add_and_dot, 3 = dot, 4 = one halo exchange. */
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
+/* Tuning knobs that do not change what is computed (only the summation order inside a row):
+ * key 0 = SpMV kernel variant: 0 "CSR-stream" (default), 1 "CSR-vector, 8 lanes per row". */
+int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
+
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */
 int nsg_get_counters(nsg_ctx *ctx, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

@@ -148,6 +148,7 @@ _NSG_SIGS = {
     "nsg_precond_apply": (C.c_int, [vp, i32, f64p, f64p]),
     "nsg_ilu_apply": (C.c_int, [vp, i32, f64p, f64p]),
     "nsg_time_kernel": (C.c_int, [vp, i32, i32, C.POINTER(C.c_double)]),
+    "nsg_set_tuning": (C.c_int, [vp, i32, i32]),
     "nsg_get_counters": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "nsg_get_phase_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
 }

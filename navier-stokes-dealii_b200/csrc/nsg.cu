@@ -278,8 +278,12 @@ static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr
 }
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
   NSG_TRY(halo_exchange(c, x_with_ghosts));
-  k_spmv_stream<<<(unsigned)c->spmv_n_chunks, SPMV_THREADS, 0, c->stream>>>(c->spmv_chunk_rows, c->rowptr, c->col, c->vals,
-                                                                            x_with_ghosts, y, state);
+  if (c->spmv_variant == 1)
+    k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
+        c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  else
+    k_spmv_stream<<<(unsigned)c->spmv_n_chunks, SPMV_THREADS, 0, c->stream>>>(c->spmv_chunk_rows, c->rowptr, c->col, c->vals,
+                                                                              x_with_ghosts, y, state);
   NSG_LAUNCH_CHECK(c);
   return NSG_OK;
 }
@@ -406,7 +410,7 @@ void nsg_destroy(nsg_ctx *c) {
   cudaDeviceSynchronize();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
-  dev_free(c->spmv_chunk_rows), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
@@ -456,6 +460,12 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   NSG_TRY(dev_alloc(&c->pm_vals, c->pm_nnz));
   NSG_CUDA(cudaMemsetAsync(c->vals, 0, 8 * (size_t)std::max<int64_t>(c->nnz, 1), c->stream));
   NSG_CUDA(cudaMemsetAsync(c->pm_vals, 0, 8 * (size_t)std::max<int64_t>(c->pm_nnz, 1), c->stream));
+  NSG_TRY(dev_alloc(&c->diag_pos, n));
+  NSG_TRY(dev_alloc(&c->first_idx, 2));
+  if (n > 0) {
+    k_diag_pos<<<grid_for(n, 256, 1 << 30), 256, 0, c->stream>>>(n, c->rowptr, c->col, c->diag_pos);
+    NSG_LAUNCH_CHECK(c);
+  }
   std::vector<int32_t> chunks;
   make_spmv_chunks(jac_rowptr, n, chunks);
   c->spmv_n_chunks = (int64_t)chunks.size() - 1;
@@ -627,11 +637,24 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
   NSG_CUDA(cudaMemcpyAsync(c->dir_dofs, dofs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   NSG_CUDA(cudaMemcpyAsync(c->dir_vals, values, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   c->h2d += 12 * n;
-  k_first_nonzero_diag<<<1, 32, 0, c->stream>>>(c->n_own_u, c->n_own, c->rowptr, c->col, c->vals, c->scal + 8);
-  NSG_LAUNCH_CHECK(c);
+  // d_b = |first non-zero diagonal entry of block (b,b) in the local range|, only for blocks that
+  // have constrained rows (the per-block apply_boundary_values returns early otherwise)
+  bool has_blk[2] = {false, false};
+  for (int64_t i = 0; i < n; ++i) has_blk[dofs[i] < c->n_own_u ? 0 : 1] = true;
+  NSG_CUDA(cudaMemsetAsync(c->first_idx, 0xff, 16, c->stream));
+  for (int b = 0; b < 2; ++b) {
+    if (!has_blk[b]) continue;
+    const int64_t r0 = b == 0 ? 0 : c->n_own_u, r1 = b == 0 ? c->n_own_u : c->n_own;
+    if (r1 > r0) {
+      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, 1 << 30), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
+      NSG_LAUNCH_CHECK(c);
+    }
+    k_first_nonzero_diag_value<<<1, 1, 0, c->stream>>>(c->diag_pos, c->vals, c->first_idx + b, c->scal + 8 + b);
+    NSG_LAUNCH_CHECK(c);
+  }
   double *x = into_solution ? c->sol : c->delta;
-  k_apply_dirichlet<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(n, c->dir_dofs, c->dir_vals, c->n_own_u, c->rowptr, c->col,
-                                                                             c->vals, x, c->R, c->scal + 8);
+  k_apply_dirichlet<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(n, c->dir_dofs, c->dir_vals, c->n_own_u, c->rowptr,
+                                                                             c->diag_pos, c->vals, x, c->R, c->scal + 8);
   NSG_LAUNCH_CHECK(c);
   NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
   NSG_CUDA(cudaEventSynchronize(c->ev1));  // dofs/values are caller-owned: the copies must have completed
@@ -911,6 +934,17 @@ int nsg_time_kernel(nsg_ctx *c, int32_t what, int32_t reps, double *ms_per_launc
   *ms_per_launch = (double)ms / reps;
   if (what == 0) c->blocks_stale = true;
   return NSG_OK;
+}
+
+int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  switch (key) {
+    case 0:
+      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "spmv variant must be 0 (stream) or 1 (vector8)");
+      c->spmv_variant = value;
+      return NSG_OK;
+    default: return fail(NSG_ERR_ARG, "unknown tuning key");
+  }
 }
 
 int nsg_get_counters(nsg_ctx *c, int64_t *launches, int64_t *h2d, int64_t *d2h) {

@@ -134,7 +134,7 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
       const double gky = a10 * s_dpsi[q][k][0] + a11 * s_dpsi[q][k][1];
       const double wpk = wq * pk;
       const double rw = P.rho * wpk;
-      const double mk = P.use_mass ? wpk * P.dt_inv : 0.0;
+      const double mk = (P.use_mass && !P.stokes) ? wpk * P.dt_inv : 0.0;
       const double vgx = nurho * wq * gkx, vgy = nurho * wq * gky;
       // A[(a,k),(b,l)] += w [ d_ab (psi_k psi_l/dt + nu rho g_k.g_l) + rho G_ab psi_k psi_l + rho U_b (g_l)_a psi_k ]
       const double d00 = mk + rw * G00, d01 = rw * G01, d10 = rw * G10, d11 = mk + rw * G11;
@@ -321,52 +321,53 @@ __global__ void k_neumann(int64_t n_bnodes, const int32_t *__restrict__ bnode_do
 }
 
 // ---- K3: MatrixTools::apply_boundary_values, Trilinos block version (cpp:375-376) ---
-// first non-zero diagonal entry of each diagonal block in the local range
-__global__ void k_first_nonzero_diag(int64_t n_own_u, int64_t n_own, const int64_t *__restrict__ rowptr,
-                                     const int32_t *__restrict__ col, const double *__restrict__ vals,
-                                     double *__restrict__ out2) {
-  const int blk = threadIdx.x;
-  if (blk > 1) return;
-  const int64_t r0 = blk == 0 ? 0 : n_own_u, r1 = blk == 0 ? n_own_u : n_own;
-  double d = 1.0;
-  for (int64_t i = r0; i < r1; ++i) {
-    double v = 0;
-    for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
-      if (col[p] == i) v = vals[p];
-    if (v != 0) {
-      d = fabs(v);
+// position of the diagonal entry of every row (-1 if structurally absent), computed once
+__global__ void k_diag_pos(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                           int64_t *__restrict__ diag_pos) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t lo = rowptr[i], hi = rowptr[i + 1], pd = -1;
+  while (lo < hi) {  // columns ascend
+    const int64_t mid = (lo + hi) >> 1;
+    const int32_t cm = col[mid];
+    if (cm == i) {
+      pd = mid;
       break;
     }
+    if (cm < i) lo = mid + 1; else hi = mid;
   }
-  out2[blk] = d;
+  diag_pos[i] = pd;
+}
+// first non-zero diagonal entry of a diagonal block in the local range [r0,r1): index by atomicMin
+// (the minimum is unique, so the result does not depend on the execution order), value afterwards
+__global__ void k_first_nonzero_diag_index(int64_t r0, int64_t r1, const int64_t *__restrict__ diag_pos,
+                                           const double *__restrict__ vals, unsigned long long *first_idx) {
+  const int64_t i = r0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= r1 || (unsigned long long)i >= *first_idx) return;
+  const int64_t p = diag_pos[i];
+  if (p >= 0 && vals[p] != 0.0) atomicMin(first_idx, (unsigned long long)i);
+}
+__global__ void k_first_nonzero_diag_value(const int64_t *__restrict__ diag_pos, const double *__restrict__ vals,
+                                           const unsigned long long *first_idx, double *out) {
+  const unsigned long long i = *first_idx;
+  *out = (i == ~0ull) ? 1.0 : fabs(vals[diag_pos[i]]);
 }
 
 // one warp per constrained row: clear the row in every block, keep a non-zero diagonal (else the
 // block's first non-zero diagonal), set the solution entry and rhs_i = g_i * diag_i
 __global__ void k_apply_dirichlet(int64_t n, const int32_t *__restrict__ dofs, const double *__restrict__ g,
-                                  int64_t n_own_u, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                  int64_t n_own_u, const int64_t *__restrict__ rowptr, const int64_t *__restrict__ diag_pos,
                                   double *__restrict__ vals, double *__restrict__ x, double *__restrict__ R,
                                   const double *__restrict__ first_nz) {
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const int64_t i = dofs[w];
-  double diag = 0;
-  int64_t pd = -1;
-  for (int64_t p = rowptr[i] + lane; p < rowptr[i + 1]; p += 32) {
-    if (col[p] == i) {
-      pd = p;
-      diag = vals[p];
-    } else
-      vals[p] = 0.0;
-  }
-  const unsigned has = __ballot_sync(0xffffffffu, pd >= 0);
-  if (has) {
-    const int src = __ffs(has) - 1;
-    diag = __shfl_sync(0xffffffffu, diag, src);
-    pd = __shfl_sync(0xffffffffu, pd, src);
-  }
+  const int64_t pd = diag_pos[i];
+  for (int64_t p = rowptr[i] + lane; p < rowptr[i + 1]; p += 32)
+    if (p != pd) vals[p] = 0.0;
   if (lane == 0) {
+    double diag = pd >= 0 ? vals[pd] : 0.0;
     if (pd >= 0 && diag == 0.0) {
       diag = first_nz[i < n_own_u ? 0 : 1];
       vals[pd] = diag;

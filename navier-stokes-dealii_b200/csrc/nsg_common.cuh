@@ -109,6 +109,9 @@ struct nsg_ctx {
   int32_t *col = nullptr, *pm_col = nullptr;
   double *vals = nullptr, *pm_vals = nullptr;
   int32_t *spmv_chunk_rows = nullptr;
+  int64_t *diag_pos = nullptr;
+  unsigned long long *first_idx = nullptr;
+  int spmv_variant = 0;
   int64_t spmv_n_chunks = 0;
   // mesh
   double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|

@@ -39,12 +39,19 @@ k_spmv_stream(const int32_t *__restrict__ chunk_rows, const int64_t *__restrict_
     for (int i = t; i < cnt; i += SPMV_THREADS) s_prod[i] = __ldcs(v + i) * __ldg(x + __ldcs(c + i));
     for (int i = t; i <= nrows; i += SPMV_THREADS) s_rp[i] = rowptr[r0 + i] - s;
     __syncthreads();
-    // phase 2: one thread per row, CSR order
-    for (int r = t; r < nrows; r += SPMV_THREADS) {
+    // phase 2: 8 lanes per row over consecutive products (bank-conflict free), fixed shuffle tree
+    const int sub = t >> 3, l8 = t & 7;
+    for (int rb = 0; rb < nrows; rb += SPMV_THREADS / 8) {
+      const int r = rb + sub;
       double acc = 0.0;
-      const int pe = (int)s_rp[r + 1];
-      for (int p = (int)s_rp[r]; p < pe; ++p) acc += s_prod[p];
-      y[r0 + r] = acc;
+      if (r < nrows) {
+        const int pe = (int)s_rp[r + 1];
+        for (int p = (int)s_rp[r] + l8; p < pe; p += 8) acc += s_prod[p];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (r < nrows && l8 == 0) y[r0 + r] = acc;
     }
   } else {
     // a single row longer than the chunk capacity: one row per chunk by construction
@@ -58,6 +65,26 @@ k_spmv_stream(const int32_t *__restrict__ chunk_rows, const int64_t *__restrict_
       y[r0] = a;
     }
   }
+}
+
+// variant 1 ("CSR-vector"): 8 lanes per row straight from global memory, no staging
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_vec8(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+            const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int64_t row = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  const int l8 = threadIdx.x & 7;
+  double acc = 0.0;
+  if (row < n_rows) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+#pragma unroll 4
+    for (int64_t p = s + l8; p < e; p += 8) acc += __ldcs(vals + p) * __ldg(x + __ldcs(col + p));
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (row < n_rows && l8 == 0) y[row] = acc;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -143,6 +143,9 @@ class DeviceProblem:
         nsg_check(self._L.nsg_time_kernel(self._h, what, reps, C.byref(ms)))
         return ms.value
 
+    def set_tuning(self, key, value):
+        nsg_check(self._L.nsg_set_tuning(self._h, int(key), int(value)))
+
     def counters(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         nsg_check(self._L.nsg_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
