@@ -145,7 +145,8 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
 /* Tuning knobs that do not change what is computed (only the summation order inside a row):
- * key 0 = SpMV kernel variant: 0 "CSR-stream" (default), 1 "CSR-vector, 8 lanes per row". */
+ * key 0 = SpMV kernel variant: 0 "CSR-stream", 1 "CSR-vector, 8 lanes per row", 2 "paired CSR"
+ * (pair-compressed column index; default when the pattern has the P2 node-pair structure). */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

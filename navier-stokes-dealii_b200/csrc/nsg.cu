@@ -119,105 +119,114 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
         }
       }
   }
-  const int64_t nchunks = (ng + NPC - 1) / NPC;
-  std::vector<int32_t> work_group(ng), chunk_iter_start(nchunks + 1, 0);
-  for (int64_t b = 0; b < nchunks; ++b) {
-    const int64_t g0 = b * NPC, g1 = std::min<int64_t>(g0 + NPC, ng);
-    int64_t mx = 0;
-    for (int64_t g = g0; g < g1; ++g) mx = std::max(mx, gptr[g + 1] - gptr[g]);
-    chunk_iter_start[b + 1] = chunk_iter_start[b] + (int32_t)mx + 1;
+  // chunks: consecutive owners while the slots fit one CTA
+  auto nslots = [&](int64_t g) { return (int)((gptr[g + 1] - gptr[g] + ASM_PPT - 1) / ASM_PPT); };
+  std::vector<ChunkInfo> chunks;
+  {
+    int64_t g = 0, rec = 0;
+    while (g < ng) {
+      ChunkInfo ci{};
+      ci.g0 = (int32_t)g;
+      int nt = 0, mx = 0;
+      while (g < ng && g - ci.g0 < 255) {
+        const int ns = std::max(nslots(g), 1);
+        if (ns > NPC) return fail(NSG_ERR_ARG, "a vertex has too many incident cells for one CTA");
+        if (nt + ns > NPC) break;
+        nt += ns;
+        mx = std::max(mx, ns);
+        ++g;
+      }
+      ci.g1 = (int32_t)g;
+      ci.n_threads = nt;
+      ci.max_slots = mx;
+      ci.rec_base = rec;
+      rec += (int64_t)nt * ASM_PPT;
+      chunks.push_back(ci);
+    }
   }
-  std::vector<int64_t> iter_ptr(chunk_iter_start[nchunks]);
-  std::vector<PairRec> recs(npairs);
+  const int64_t nchunks = (int64_t)chunks.size();
+  const int64_t nrecs = nchunks ? chunks.back().rec_base + (int64_t)chunks.back().n_threads * ASM_PPT : 0;
+  std::vector<uint16_t> tdesc((size_t)nchunks * NPC, 0);
+  std::vector<PairRec> recs(nrecs);
   int bad = 0;
   int64_t max_stage = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_stage) reduction(+ : bad)
   for (int64_t b = 0; b < nchunks; ++b) {
-    const int64_t g0 = b * NPC, g1 = std::min<int64_t>(g0 + NPC, ng);
-    const int n = (int)(g1 - g0);
-    int order[NPC];
-    for (int i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order, order + n, [&](int a, int bb) {
-      return gptr[g0 + a + 1] - gptr[g0 + a] > gptr[g0 + bb + 1] - gptr[g0 + bb];
-    });
-    for (int i = 0; i < n; ++i) work_group[g0 + i] = (int32_t)(g0 + order[i]);
-    const int niter = chunk_iter_start[b + 1] - chunk_iter_start[b] - 1;
-    int64_t w = gptr[g0];
-    for (int j = 0; j < niter; ++j) {
-      iter_ptr[chunk_iter_start[b] + j] = w;
-      for (int i = 0; i < n; ++i) {
-        const int64_t g = g0 + order[i];
-        if (gptr[g + 1] - gptr[g] <= j) break;
-        const int64_t src = gptr[g] + j;
-        PairRec r;
-        std::memset(&r, 0, sizeof r);
-        r.cell = pcell[src];
-        r.k = pk[src];
-        const int32_t *cdc = cd + 15 * (int64_t)r.cell;
-        const int64_t row = kind == 0 ? 2 * g : nu + g;
-        const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
-        if (re - rs >= 65535) bad++;
-        if (kind == 0 && c->h_rowptr[row + 2] - re != re - rs) bad++;
-        const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
-        for (int l = 0; l < 6; ++l) {
-          const int32_t tgt = cdc[uidx(l)];
-          const int32_t *p = std::lower_bound(cb, ce, tgt);
-          if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
-            bad++;
-            continue;
-          }
-          r.off[l] = (uint16_t)(p - cb);
-        }
-        if (kind == 0) {
-          for (int m = 0; m < 3; ++m) {
-            const int32_t tgt = cdc[3 * m + 2];
-            const int32_t *p = std::lower_bound(cb, ce, tgt);
-            if (p == ce || *p != tgt) {
-              bad++;
-              continue;
+    const ChunkInfo &ci = chunks[b];
+    // thread order: all slot-0 threads (one per owner), then slot 1, ...
+    int t = 0;
+    for (int r = 0; r < ci.max_slots; ++r)
+      for (int64_t g = ci.g0; g < ci.g1; ++g) {
+        const int ns = std::max(nslots(g), 1);
+        if (r >= ns) continue;
+        tdesc[b * NPC + t] = (uint16_t)((g - ci.g0) | (r << 8));
+        for (int j = 0; j < ASM_PPT; ++j) {
+          PairRec rcd;
+          std::memset(&rcd, 0, sizeof rcd);
+          rcd.cell = -1;
+          const int64_t pi = r + (int64_t)j * ns;
+          if (pi < gptr[g + 1] - gptr[g]) {
+            const int64_t src = gptr[g] + pi;
+            rcd.cell = pcell[src];
+            rcd.k = pk[src];
+            const int32_t *cdc = cd + 15 * (int64_t)rcd.cell;
+            const int64_t row = kind == 0 ? 2 * g : nu + g;
+            const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
+            if (re - rs >= 65535) bad++;
+            if (kind == 0 && c->h_rowptr[row + 2] - re != re - rs) bad++;
+            const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
+            for (int l = 0; l < 6; ++l) {
+              const int32_t tgt = cdc[uidx(l)];
+              const int32_t *p = std::lower_bound(cb, ce, tgt);
+              if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
+                bad++;
+                continue;
+              }
+              rcd.off[l] = (uint16_t)(p - cb);
             }
-            r.off[6 + m] = (uint16_t)(p - cb);
-          }
-        } else {
-          const int32_t *mb = c->h_pm_col.data() + c->h_pm_rowptr[row], *me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
-          for (int m = 0; m < 3; ++m) {
-            const int32_t tgt = cdc[3 * m + 2];
-            const int32_t *p = std::lower_bound(mb, me, tgt);
-            if (p == me || *p != tgt) {
-              bad++;
-              continue;
+            const int32_t *mb = cb, *me = ce;
+            if (kind == 1) {
+              mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
+              me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
             }
-            r.off[6 + m] = (uint16_t)(p - mb);
+            for (int m = 0; m < 3; ++m) {
+              const int32_t tgt = cdc[3 * m + 2];
+              const int32_t *p = std::lower_bound(mb, me, tgt);
+              if (p == me || *p != tgt) {
+                bad++;
+                continue;
+              }
+              rcd.off[6 + m] = (uint16_t)(p - mb);
+            }
           }
+          recs[ci.rec_base + (int64_t)j * ci.n_threads + t] = rcd;
         }
-        recs[w++] = r;
+        ++t;
       }
-    }
-    iter_ptr[chunk_iter_start[b] + niter] = w;
+    if (t != ci.n_threads) bad++;
     int64_t stage;
     if (kind == 0)
-      stage = c->h_rowptr[2 * g1] - c->h_rowptr[2 * g0];
+      stage = c->h_rowptr[2 * (int64_t)ci.g1] - c->h_rowptr[2 * (int64_t)ci.g0] + 2 * (ci.g1 - ci.g0);
     else
-      stage = (c->h_rowptr[nu + g1] - c->h_rowptr[nu + g0]) + (c->h_pm_rowptr[nu + g1] - c->h_pm_rowptr[nu + g0]);
+      stage = (c->h_rowptr[nu + ci.g1] - c->h_rowptr[nu + ci.g0]) + (c->h_pm_rowptr[nu + ci.g1] - c->h_pm_rowptr[nu + ci.g0]);
     max_stage = std::max(max_stage, stage);
   }
   if (bad) return fail(NSG_ERR_ARG, "cell_dofs do not match the sparsity pattern (or a row has >= 65535 entries)");
   out->n_groups = ng;
   out->n_chunks = nchunks;
   out->n_pairs = npairs;
+  out->n_recs = nrecs;
   out->max_stage = max_stage;
-  NSG_TRY(upload(c, &out->work_group, work_group.data(), ng));
-  NSG_TRY(upload(c, &out->chunk_iter_start, chunk_iter_start.data(), nchunks + 1));
-  NSG_TRY(upload(c, &out->iter_ptr, iter_ptr.data(), (int64_t)iter_ptr.size()));
-  NSG_TRY(upload(c, &out->recs, recs.data(), npairs));
+  NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
+  NSG_TRY(upload(c, &out->tdesc, tdesc.data(), (int64_t)tdesc.size()));
+  NSG_TRY(upload(c, &out->recs, recs.data(), nrecs));
   NSG_CUDA(cudaStreamSynchronize(c->stream));  // host vectors die here
   return NSG_OK;
 }
 
 static void free_worklist(WorkList &w) {
-  dev_free(w.work_group);
-  dev_free(w.chunk_iter_start);
-  dev_free(w.iter_ptr);
+  dev_free(w.chunks);
+  dev_free(w.tdesc);
   dev_free(w.recs);
 }
 
@@ -232,6 +241,64 @@ static void make_spmv_chunks(const int64_t *rowptr, int64_t n, std::vector<int32
     chunks.push_back((int32_t)e);
     r = e;
   }
+}
+
+// pair-compressed column index (SpMV variant 2); returns false if the pattern does not have the
+// node-pair structure (then the plain CSR kernels are used)
+static bool build_paired_index(const nsg_ctx *c, const int64_t *rowptr, const int32_t *col, std::vector<GroupMeta> &meta,
+                               std::vector<int32_t> &items) {
+  const int64_t nu = c->n_own_u, nown = c->n_own, gu0 = nown, gu1 = nown + c->n_ghost_u;
+  const int64_t n_ug = nu / 2, G = n_ug + c->n_own_p;
+  meta.assign(G, GroupMeta{});
+  std::vector<int64_t> cnt(G + 1, 0);
+  auto is_pair_start = [&](int64_t cc, int64_t next) {
+    if (cc < nu) return (cc % 2 == 0) && next == cc + 1;
+    if (cc >= gu0 && cc < gu1) return ((cc - gu0) % 2 == 0) && next == cc + 1;
+    return false;
+  };
+  auto is_u = [&](int64_t cc) { return cc < nu || (cc >= gu0 && cc < gu1); };
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (int64_t g = 0; g < G; ++g) {
+    const int64_t row = g < n_ug ? 2 * g : nu + (g - n_ug);
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    if (g < n_ug) {
+      if (rowptr[row + 2] - e != e - s || std::memcmp(col + s, col + e, 4 * (size_t)(e - s)) != 0) bad++;
+    }
+    int seg = 0, n[4] = {0, 0, 0, 0};
+    for (int64_t p = s; p < e;) {
+      const int64_t cc = col[p];
+      const bool pr = is_pair_start(cc, p + 1 < e ? col[p + 1] : -1);
+      if (!pr && is_u(cc)) bad++;  // an unpaired velocity column
+      const int want = cc < nu ? 0 : (cc < nown ? 1 : (cc < gu1 ? 2 : 3));
+      if (want < seg) bad++;
+      seg = want;
+      n[seg]++;
+      p += pr ? 2 : 1;
+    }
+    for (int q = 0; q < 4; ++q)
+      if (n[q] > 65535) bad++;
+    meta[g].val_start = s;
+    meta[g].np1 = (uint16_t)n[0], meta[g].ns1 = (uint16_t)n[1], meta[g].np2 = (uint16_t)n[2], meta[g].ns2 = (uint16_t)n[3];
+    cnt[g + 1] = n[0] + n[1] + n[2] + n[3];
+  }
+  if (bad) return false;
+  for (int64_t g = 0; g < G; ++g) cnt[g + 1] += cnt[g];
+  if (cnt[G] >= (int64_t)UINT32_MAX) return false;
+  items.resize(cnt[G]);
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < G; ++g) {
+    const int64_t row = g < n_ug ? 2 * g : nu + (g - n_ug);
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    meta[g].item_start = (uint32_t)cnt[g];
+    int64_t w = cnt[g];
+    for (int64_t p = s; p < e;) {
+      const int64_t cc = col[p];
+      items[w++] = (int32_t)cc;
+      p += is_pair_start(cc, p + 1 < e ? col[p + 1] : -1) ? 2 : 1;
+    }
+  }
+  return true;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -278,7 +345,10 @@ static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr
 }
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
   NSG_TRY(halo_exchange(c, x_with_ghosts));
-  if (c->spmv_variant == 1)
+  if (c->spmv_variant == 2 && c->have_paired)
+    k_spmv_paired<<<(unsigned)((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
+        c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
+  else if (c->spmv_variant >= 1)
     k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
   else
@@ -410,7 +480,7 @@ void nsg_destroy(nsg_ctx *c) {
   cudaDeviceSynchronize();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
-  dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
@@ -470,6 +540,20 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   make_spmv_chunks(jac_rowptr, n, chunks);
   c->spmv_n_chunks = (int64_t)chunks.size() - 1;
   NSG_TRY(upload(c, &c->spmv_chunk_rows, chunks.data(), (int64_t)chunks.size()));
+  {
+    std::vector<GroupMeta> meta;
+    std::vector<int32_t> items;
+    c->have_paired = build_paired_index(c, jac_rowptr, jac_col, meta, items);
+    if (c->have_paired) {
+      c->n_ugroups = n_own_u / 2;
+      c->n_groups = (int64_t)meta.size();
+      c->n_items = (int64_t)items.size();
+      NSG_TRY(upload(c, &c->gmeta, meta.data(), c->n_groups));
+      NSG_TRY(upload(c, &c->gitems, items.data(), c->n_items));
+      NSG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->spmv_variant = c->have_paired ? 2 : 1;
+  }
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
     NSG_CUDA(cudaMemsetAsync(*v, 0, 8 * (size_t)c->stride, c->stream));
@@ -940,7 +1024,8 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   switch (key) {
     case 0:
-      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "spmv variant must be 0 (stream) or 1 (vector8)");
+      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "spmv variant must be 0 (stream), 1 (vector8) or 2 (paired)");
+      if (value == 2 && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
       c->spmv_variant = value;
       return NSG_OK;
     default: return fail(NSG_ERR_ARG, "unknown tuning key");

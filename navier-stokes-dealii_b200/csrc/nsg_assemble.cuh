@@ -60,153 +60,161 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
   __shared__ double s_w[7], s_psi[7][6], s_dpsi[7][6][2], s_chi[7][3];
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
-  const int64_t g0 = b * NPC, g1 = min(g0 + (int64_t)NPC, wl.n_groups);
-  const int64_t rs = rowptr[2 * g0], re = rowptr[2 * g1];
+  const ChunkInfo ci = wl.chunks[b];
+  const int ng = ci.g1 - ci.g0;
+  const int64_t rs = rowptr[2 * (int64_t)ci.g0], re = rowptr[2 * (int64_t)ci.g1];
   const int cnt = (int)(re - rs);
-  for (int i = t; i < cnt; i += NPC) s_vals[i] = 0.0;
+  double *s_res = s_vals + cnt;
+  for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
   if (t < 7) s_w[t] = c_fe.w[t];
   if (t < 42) (&s_psi[0][0])[t] = (&c_fe.psi[0][0])[t];
   if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
   if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
   __syncthreads();
 
-  const bool have = g0 + t < g1;
-  const int64_t node = have ? wl.work_group[g0 + t] : 0;
+  const bool have = t < ci.n_threads;
+  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
+  const int gl = desc & 0xff, slot = desc >> 8;
+  const int64_t node = ci.g0 + gl;
   const int64_t r0 = rowptr[2 * node];
   const int len = (int)(rowptr[2 * node + 1] - r0);
   double *row0 = s_vals + (r0 - rs), *row1 = row0 + len;
-  double res0 = 0.0, res1 = 0.0;
-
-  const int it0 = wl.chunk_iter_start[b], it1 = wl.chunk_iter_start[b + 1] - 1;  // last entry is the sentinel
   const double nurho = P.nu * P.rho;
-  for (int it = it0; it < it1; ++it) {
-    const int64_t base = wl.iter_ptr[it];
-    const int nact = (int)(wl.iter_ptr[it + 1] - base);
-    if (t >= nact) continue;
-    const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + base + t);
-    const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-    const int64_t c = (int)ra.x;
-    const int k = (int)ra.y;
-    const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
-                 a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
-    const int32_t *cd = cell_dofs + 15 * c;
-    double u[6][2], pr[3];
-#pragma unroll
-    for (int l = 0; l < 6; ++l) {
-      const int32_t d0 = __ldg(cd + uidx(l));
-      u[l][0] = sol[d0];
-      u[l][1] = sol[d0 + 1];
-    }
-#pragma unroll
-    for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
 
+  for (int j = 0; j < ASM_PPT; ++j) {
+    uint4 ra = make_uint4(0xffffffffu, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (have) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
+      ra = __ldcs(rp);
+      rb = __ldcs(rp + 1);
+    }
+    const bool work = (int)ra.x >= 0;
     double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
+    double res0 = 0.0, res1 = 0.0;
 #pragma unroll
     for (int l = 0; l < 6; ++l) A00[l] = A01[l] = A10[l] = A11[l] = 0.0;
 #pragma unroll
     for (int m = 0; m < 3; ++m) B0[m] = B1[m] = 0.0;
-
-#pragma unroll 1
-    for (int q = 0; q < 7; ++q) {
-      const double wq = adet * s_w[q];
-      double g[6][2];
-      double U0 = 0, U1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
-        g[l][0] = a00 * dx + a01 * dy;
-        g[l][1] = a10 * dx + a11 * dy;
-      }
-      if (!P.stokes) {
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          const double pl = s_psi[q][l];
-          U0 += u[l][0] * pl;
-          U1 += u[l][1] * pl;
-          G00 += u[l][0] * g[l][0];
-          G01 += u[l][0] * g[l][1];
-          G10 += u[l][1] * g[l][0];
-          G11 += u[l][1] * g[l][1];
-        }
-      }
-      const double pk = s_psi[q][k];
-      const double gkx = a00 * s_dpsi[q][k][0] + a01 * s_dpsi[q][k][1];
-      const double gky = a10 * s_dpsi[q][k][0] + a11 * s_dpsi[q][k][1];
-      const double wpk = wq * pk;
-      const double rw = P.rho * wpk;
-      const double mk = (P.use_mass && !P.stokes) ? wpk * P.dt_inv : 0.0;
-      const double vgx = nurho * wq * gkx, vgy = nurho * wq * gky;
-      // A[(a,k),(b,l)] += w [ d_ab (psi_k psi_l/dt + nu rho g_k.g_l) + rho G_ab psi_k psi_l + rho U_b (g_l)_a psi_k ]
-      const double d00 = mk + rw * G00, d01 = rw * G01, d10 = rw * G10, d11 = mk + rw * G11;
-      const double c0 = rw * U0, c1 = rw * U1;
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double pl = s_psi[q][l], glx = g[l][0], gly = g[l][1];
-        const double visc = vgx * glx + vgy * gly;
-        A00[l] += visc + d00 * pl + c0 * glx;
-        A01[l] += d01 * pl + c1 * glx;
-        A10[l] += d10 * pl + c0 * gly;
-        A11[l] += visc + d11 * pl + c1 * gly;
-      }
-      // B^T[(a,k),m] -= w (g_k)_a chi_m   (cpp:272-274)
-      const double bx = -wq * gkx, by = -wq * gky;
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const double cm = s_chi[q][m];
-        B0[m] += bx * cm;
-        B1[m] += by * cm;
-      }
-      // residual (cpp:287-311), time-derivative term added after the loop
-      if (!P.stokes) {
-        const double Pq = pr[0] * s_chi[q][0] + pr[1] * s_chi[q][1] + pr[2] * s_chi[q][2];
-        res0 += wq * (-nurho * (G00 * gkx + G01 * gky) - P.rho * (U0 * G00 + U1 * G10) * pk + Pq * gkx);
-        res1 += wq * (-nurho * (G10 * gkx + G11 * gky) - P.rho * (U0 * G01 + U1 * G11) * pk + Pq * gky);
-      }
-      res0 += wpk * P.f0;
-      res1 += wpk * P.f1;
-    }
-    if (!P.stokes && P.use_mass) {
-      // -rho (u - u_old)/dt psi_k integrated with the same 7-point rule = -rho/dt |detJ| sum_l mhat[k][l] (u_l - uold_l)
-      double t0 = 0, t1 = 0;
+    if (work) {
+      const int64_t c = (int)ra.x;
+      const int k = (int)ra.y;
+      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
+                   a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
+      const int32_t *cd = cell_dofs + 15 * c;
+      double u[6][2], pr[3];
 #pragma unroll
       for (int l = 0; l < 6; ++l) {
         const int32_t d0 = __ldg(cd + uidx(l));
-        const double mh = c_fe.mhat[k][l];
-        t0 += mh * (u[l][0] - sol_old[d0]);
-        t1 += mh * (u[l][1] - sol_old[d0 + 1]);
+        u[l][0] = sol[d0];
+        u[l][1] = sol[d0 + 1];
       }
-      const double f = -P.rho * P.dt_inv * adet;
-      res0 += f * t0;
-      res1 += f * t1;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
+#pragma unroll 1
+      for (int q = 0; q < 7; ++q) {
+        const double wq = adet * s_w[q];
+        double g[6][2];
+        double U0 = 0, U1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+          g[l][0] = a00 * dx + a01 * dy;
+          g[l][1] = a10 * dx + a11 * dy;
+        }
+        if (!P.stokes) {
+#pragma unroll
+          for (int l = 0; l < 6; ++l) {
+            const double pl = s_psi[q][l];
+            U0 += u[l][0] * pl;
+            U1 += u[l][1] * pl;
+            G00 += u[l][0] * g[l][0];
+            G01 += u[l][0] * g[l][1];
+            G10 += u[l][1] * g[l][0];
+            G11 += u[l][1] * g[l][1];
+          }
+        }
+        const double pk = s_psi[q][k];
+        const double gkx = a00 * s_dpsi[q][k][0] + a01 * s_dpsi[q][k][1];
+        const double gky = a10 * s_dpsi[q][k][0] + a11 * s_dpsi[q][k][1];
+        const double wpk = wq * pk;
+        const double rw = P.rho * wpk;
+        const double mk = (P.use_mass && !P.stokes) ? wpk * P.dt_inv : 0.0;
+        const double vgx = nurho * wq * gkx, vgy = nurho * wq * gky;
+        // A[(a,k),(b,l)] += w [ d_ab (psi_k psi_l/dt + nu rho g_k.g_l) + rho G_ab psi_k psi_l + rho U_b (g_l)_a psi_k ]
+        const double d00 = mk + rw * G00, d01 = rw * G01, d10 = rw * G10, d11 = mk + rw * G11;
+        const double c0 = rw * U0, c1 = rw * U1;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          const double pl = s_psi[q][l], glx = g[l][0], gly = g[l][1];
+          const double visc = vgx * glx + vgy * gly;
+          A00[l] += visc + d00 * pl + c0 * glx;
+          A01[l] += d01 * pl + c1 * glx;
+          A10[l] += d10 * pl + c0 * gly;
+          A11[l] += visc + d11 * pl + c1 * gly;
+        }
+        // B^T[(a,k),m] -= w (g_k)_a chi_m   (cpp:272-274)
+        const double bx = -wq * gkx, by = -wq * gky;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const double cm = s_chi[q][m];
+          B0[m] += bx * cm;
+          B1[m] += by * cm;
+        }
+        // residual (cpp:287-311), time-derivative term added after the loop
+        if (!P.stokes) {
+          const double Pq = pr[0] * s_chi[q][0] + pr[1] * s_chi[q][1] + pr[2] * s_chi[q][2];
+          res0 += wq * (-nurho * (G00 * gkx + G01 * gky) - P.rho * (U0 * G00 + U1 * G10) * pk + Pq * gkx);
+          res1 += wq * (-nurho * (G10 * gkx + G11 * gky) - P.rho * (U0 * G01 + U1 * G11) * pk + Pq * gky);
+        }
+        res0 += wpk * P.f0;
+        res1 += wpk * P.f1;
+      }
+      if (!P.stokes && P.use_mass) {
+        // -rho (u - u_old)/dt psi_k with the same 7-point rule = -rho/dt |detJ| sum_l mhat[k][l] (u_l - uold_l)
+        double t0 = 0, t1 = 0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          const int32_t d0 = __ldg(cd + uidx(l));
+          const double mh = c_fe.mhat[k][l];
+          t0 += mh * (u[l][0] - sol_old[d0]);
+          t1 += mh * (u[l][1] - sol_old[d0 + 1]);
+        }
+        const double f = -P.rho * P.dt_inv * adet;
+        res0 += f * t0;
+        res1 += f * t1;
+      }
     }
-    // scatter into the owner's private rows of the chunk image
+    // commit rounds: slot r of every owner adds its pair into the owner's rows, in cell order
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    for (int r = 0; r < ci.max_slots; ++r) {
+      if (work && slot == r) {
 #pragma unroll
-    for (int l = 0; l < 6; ++l) {
-      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-      row0[o] += A00[l];
-      row0[o + 1] += A01[l];
-      row1[o] += A10[l];
-      row1[o + 1] += A11[l];
-    }
+        for (int l = 0; l < 6; ++l) {
+          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+          row0[o] += A00[l];
+          row0[o + 1] += A01[l];
+          row1[o] += A10[l];
+          row1[o + 1] += A11[l];
+        }
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      const int l = 6 + m;
-      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-      row0[o] += B0[m];
-      row1[o] += B1[m];
+        for (int m = 0; m < 3; ++m) {
+          const int l = 6 + m;
+          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+          row0[o] += B0[m];
+          row1[o] += B1[m];
+        }
+        s_res[2 * gl] += res0;
+        s_res[2 * gl + 1] += res1;
+      }
+      __syncthreads();
     }
   }
-  if (have) {
-    R[2 * node] = res0;
-    R[2 * node + 1] = res1;
-  }
-  __syncthreads();
   for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
+  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
 
 // ---- pressure rows: B, the structurally present zero p-p block, pressure mass -------------------
-__global__ void __launch_bounds__(NPC, 3)
+__global__ void __launch_bounds__(NPC, 4)
 k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
              const int64_t *__restrict__ pm_rowptr, double *__restrict__ pm_vals, double *__restrict__ R,
              const double *__restrict__ geom, const AsmParams P) {
@@ -214,9 +222,10 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
   __shared__ double s_w[7], s_dpsi[7][6][2], s_chi[7][3];
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
-  const int64_t g0 = b * NPC, g1 = min(g0 + (int64_t)NPC, wl.n_groups);
-  const int64_t rs = rowptr[n_own_u + g0], re = rowptr[n_own_u + g1];
-  const int64_t ms = pm_rowptr[n_own_u + g0], me = pm_rowptr[n_own_u + g1];
+  const ChunkInfo ci = wl.chunks[b];
+  const int ng = ci.g1 - ci.g0;
+  const int64_t rs = rowptr[n_own_u + ci.g0], re = rowptr[n_own_u + ci.g1];
+  const int64_t ms = pm_rowptr[n_own_u + ci.g0], me = pm_rowptr[n_own_u + ci.g1];
   const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
   double *s_pm = s_vals + cnt;
   for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
@@ -224,60 +233,70 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
   if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
   if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
   __syncthreads();
-  const bool have = g0 + t < g1;
-  const int64_t prow = n_own_u + (have ? wl.work_group[g0 + t] : 0);
+  const bool have = t < ci.n_threads;
+  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
+  const int gl = desc & 0xff, slot = desc >> 8;
+  const int64_t prow = n_own_u + ci.g0 + gl;
   double *row = s_vals + (rowptr[prow] - rs);
   double *mrow = s_pm + (pm_rowptr[prow] - ms);
   const double inv_nu = 1.0 / P.nu;
-  const int it0 = wl.chunk_iter_start[b], it1 = wl.chunk_iter_start[b + 1] - 1;
-  for (int it = it0; it < it1; ++it) {
-    const int64_t base = wl.iter_ptr[it];
-    const int nact = (int)(wl.iter_ptr[it + 1] - base);
-    if (t >= nact) continue;
-    const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + base + t);
-    const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-    const int64_t c = (int)ra.x;
-    const int m = (int)ra.y;
-    const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
-                 a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
+  for (int j = 0; j < ASM_PPT; ++j) {
+    uint4 ra = make_uint4(0xffffffffu, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (have) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
+      ra = __ldcs(rp);
+      rb = __ldcs(rp + 1);
+    }
+    const bool work = (int)ra.x >= 0;
     double Bx[6], By[6], M[3];
 #pragma unroll
     for (int l = 0; l < 6; ++l) Bx[l] = By[l] = 0.0;
     M[0] = M[1] = M[2] = 0.0;
+    if (work) {
+      const int64_t c = (int)ra.x;
+      const int m = (int)ra.y;
+      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
+                   a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
 #pragma unroll 1
-    for (int q = 0; q < 7; ++q) {
-      const double wq = adet * s_w[q];
-      const double cm = s_chi[q][m];
-      const double wc = -wq * cm;
-      // B[m,(b,l)] -= w (g_l)_b chi_m   (cpp:277-279)
+      for (int q = 0; q < 7; ++q) {
+        const double wq = adet * s_w[q];
+        const double cm = s_chi[q][m];
+        const double wc = -wq * cm;
+        // B[m,(b,l)] -= w (g_l)_b chi_m   (cpp:277-279)
 #pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
-        Bx[l] += wc * (a00 * dx + a01 * dy);
-        By[l] += wc * (a10 * dx + a11 * dy);
+        for (int l = 0; l < 6; ++l) {
+          const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+          Bx[l] += wc * (a00 * dx + a01 * dy);
+          By[l] += wc * (a10 * dx + a11 * dy);
+        }
+        // Mp[m,n] += w chi_m chi_n / nu   (cpp:282-284)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) M[n] += cm * s_chi[q][n] * inv_nu * wq;
       }
-      // Mp[m,n] += w chi_m chi_n / nu   (cpp:282-284)
-#pragma unroll
-      for (int n = 0; n < 3; ++n) M[n] += cm * s_chi[q][n] * inv_nu * wq;
     }
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    for (int r = 0; r < ci.max_slots; ++r) {
+      if (work && slot == r) {
 #pragma unroll
-    for (int l = 0; l < 6; ++l) {
-      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-      row[o] += Bx[l];
-      row[o + 1] += By[l];
-    }
+        for (int l = 0; l < 6; ++l) {
+          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+          row[o] += Bx[l];
+          row[o + 1] += By[l];
+        }
 #pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      const int l = 6 + n;
-      const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-      mrow[o] += M[n];
+        for (int n = 0; n < 3; ++n) {
+          const int l = 6 + n;
+          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+          mrow[o] += M[n];
+        }
+      }
+      __syncthreads();
     }
   }
-  if (have) R[prow] = 0.0;  // no statement of the reference tests the pressure space
-  __syncthreads();
   for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
   for (int i = t; i < mcnt; i += NPC) __stcs(pm_vals + ms + i, s_pm[i]);
+  // no statement of the reference tests the pressure space: R_p == 0
+  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
 }
 
 // ---- K2: Neumann faces (cpp:315-336), one thread per boundary P2 node, faces in list order ------

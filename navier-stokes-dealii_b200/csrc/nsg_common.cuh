@@ -49,16 +49,38 @@ struct __align__(16) PairRec {
 };
 static_assert(sizeof(PairRec) == 32, "PairRec must be 32 bytes");
 
-// Row-owner work lists: `n_groups` owners in chunks of NPC; inside a chunk threads are sorted by
-// patch size (descending) so iteration j is served by a prefix of the threads.
-struct WorkList {
-  int64_t n_groups = 0, n_chunks = 0, n_pairs = 0;
-  int32_t *work_group = nullptr;      // [n_groups] owner handled by thread t of its chunk
-  int32_t *chunk_iter_start = nullptr;  // [n_chunks+1] index into iter_ptr
-  int64_t *iter_ptr = nullptr;        // record offsets per (chunk, iteration), +1 sentinel per chunk
-  PairRec *recs = nullptr;            // [n_pairs]
-  int64_t max_stage = 0;              // max number of staged matrix entries of a chunk
+// Row-owner work lists.  An owner (velocity node = 2 rows, or pressure row) with a patch of s cells
+// is served by ceil(s/PPT) thread "slots"; slot r integrates pairs r, r+nslots, ... so every thread
+// does at most PPT (owner, cell) pairs and the CTA is balanced.  Slots of one owner commit their
+// local rows to the shared chunk image in rounds (slot 0, barrier, slot 1, ...), i.e. in ascending
+// cell order: no atomics, fixed summation order.
+constexpr int ASM_PPT = 2;
+struct __align__(16) ChunkInfo {
+  int32_t g0, g1;        // owners [g0,g1) of this chunk (consecutive rows)
+  int32_t n_threads;     // sum of slots (<= NPC)
+  int32_t max_slots;     // commit rounds
+  int64_t rec_base;      // records of iteration j, thread t at rec_base + j*n_threads + t
+  int64_t pad;
 };
+struct WorkList {
+  int64_t n_groups = 0, n_chunks = 0, n_pairs = 0, n_recs = 0;
+  ChunkInfo *chunks = nullptr;   // [n_chunks]
+  uint16_t *tdesc = nullptr;     // [n_chunks*NPC] owner index inside the chunk | slot << 8
+  PairRec *recs = nullptr;       // [n_recs]; cell = -1 marks "no work"
+  int64_t max_stage = 0;         // max number of staged matrix entries of a chunk
+};
+
+// Pair-compressed column index of the fixed CSR (SpMV variant 2).  Rows 2n,2n+1 of a velocity node
+// have the same column pattern and velocity columns come in pairs (2m,2m+1), so one stored index
+// serves up to 4 matrix entries.  A group = the two rows of a velocity node or one pressure row; its
+// columns are [np1 pairs | ns1 singles | np2 pairs | ns2 singles] = [owned u | owned p | ghost u | ghost p].
+struct __align__(8) GroupMeta {
+  int64_t val_start;    // rowptr of the group's first row
+  uint32_t item_start;  // first compressed index
+  uint16_t np1, ns1, np2, ns2;
+  uint32_t pad;
+};
+static_assert(sizeof(GroupMeta) == 24, "GroupMeta must be 24 bytes");
 
 // deal.II SolverGMRES bookkeeping kept on the device
 constexpr int GM_MAX_TMP = 64;
@@ -112,6 +134,10 @@ struct nsg_ctx {
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
   int spmv_variant = 0;
+  nsg::GroupMeta *gmeta = nullptr;
+  int32_t *gitems = nullptr;
+  int64_t n_groups = 0, n_ugroups = 0, n_items = 0;
+  bool have_paired = false;
   int64_t spmv_n_chunks = 0;
   // mesh
   double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|

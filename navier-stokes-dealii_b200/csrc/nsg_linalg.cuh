@@ -87,6 +87,58 @@ k_spmv_vec8(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *_
   if (row < n_rows && l8 == 0) y[row] = acc;
 }
 
+// variant 2 ("paired CSR"): values stay in CSR order; the column index is pair-compressed (GroupMeta).
+// 8 lanes walk the flat value positions of a group; the two rows of a velocity node share every
+// decoded index and every gathered x entry.  ~9.4 instead of 12 bytes per non-zero.
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__ meta, const int32_t *__restrict__ items,
+              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+              const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  const int l8 = threadIdx.x & 7;
+  double acc0 = 0.0, acc1 = 0.0;
+  const bool two = g < n_ugroups;
+  if (g < n_groups) {
+    const GroupMeta m = meta[g];
+    const int np1 = m.np1, ns1 = m.ns1, np2 = m.np2;
+    const int b1 = 2 * np1, b2 = b1 + ns1, b3 = b2 + 2 * np2, len = b3 + m.ns2;
+    const double *v0 = vals + m.val_start;
+    const double *v1 = v0 + len;
+    const int32_t *it = items + m.item_start;
+#pragma unroll 4
+    for (int i = l8; i < len; i += 8) {
+      int j, sub;
+      if (i < b1) {
+        j = i >> 1, sub = i & 1;
+      } else if (i < b2) {
+        j = np1 + (i - b1), sub = 0;
+      } else if (i < b3) {
+        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
+      } else {
+        j = np1 + ns1 + np2 + (i - b3), sub = 0;
+      }
+      const double xv = __ldg(x + __ldg(it + j) + sub);
+      acc0 += __ldcs(v0 + i) * xv;
+      if (two) acc1 += __ldcs(v1 + i) * xv;
+    }
+  }
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+  if (g < n_groups && l8 == 0) {
+    if (two) {
+      y[2 * g] = acc0;
+      y[2 * g + 1] = acc1;
+    } else {
+      y[2 * n_ugroups + (g - n_ugroups)] = acc0;
+    }
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

