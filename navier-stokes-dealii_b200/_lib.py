@@ -180,7 +180,7 @@ def nsg():
     """The CUDA library. Loading needs libcudart/libnccl but no GPU; nsg_create needs a GPU."""
     global _nsg
     if _nsg is None:
-        path = os.path.join(_HERE, "libnsg.so")
+        path = os.environ.get("NSG_LIB", os.path.join(_HERE, "libnsg.so"))  # NSG_LIB: A/B builds of the same ABI
         if not os.path.exists(path):
             raise NsgError(-1, f"{path} is missing: the CUDA extension was not built and there is no fallback; "
                                "run `make` (or __graft_entry__.build())")

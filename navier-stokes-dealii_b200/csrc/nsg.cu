@@ -243,6 +243,18 @@ static void make_spmv_chunks(const int64_t *rowptr, int64_t n, std::vector<int32
   }
 }
 
+// Permutation that sorts rows (or groups) by length inside windows of `window` entries, so that the
+// 8-lane groups of one warp iterate the same number of times while x/y locality is kept.
+static void length_sorted_perm(int64_t n, int64_t window, const std::vector<int64_t> &len, std::vector<int32_t> &perm) {
+  perm.resize(n);
+#pragma omp parallel for schedule(static)
+  for (int64_t w0 = 0; w0 < n; w0 += window) {
+    const int64_t w1 = std::min(n, w0 + window);
+    for (int64_t i = w0; i < w1; ++i) perm[i] = (int32_t)i;
+    std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int32_t a, int32_t b) { return len[a] > len[b]; });
+  }
+}
+
 // pair-compressed column index (SpMV variant 2); returns false if the pattern does not have the
 // node-pair structure (then the plain CSR kernels are used)
 static bool build_paired_index(const nsg_ctx *c, const int64_t *rowptr, const int32_t *col, std::vector<GroupMeta> &meta,
@@ -347,10 +359,10 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
   NSG_TRY(halo_exchange(c, x_with_ghosts));
   if (c->spmv_variant == 2 && c->have_paired)
     k_spmv_paired<<<(unsigned)((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
+        c->n_groups, c->n_ugroups, c->group_perm, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
   else if (c->spmv_variant >= 1)
     k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+        c->n_own, c->row_perm, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
   else
     k_spmv_stream<<<(unsigned)c->spmv_n_chunks, SPMV_THREADS, 0, c->stream>>>(c->spmv_chunk_rows, c->rowptr, c->col, c->vals,
                                                                               x_with_ghosts, y, state);
@@ -480,7 +492,7 @@ void nsg_destroy(nsg_ctx *c) {
   cudaDeviceSynchronize();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
-  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
@@ -544,7 +556,20 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
     std::vector<GroupMeta> meta;
     std::vector<int32_t> items;
     c->have_paired = build_paired_index(c, jac_rowptr, jac_col, meta, items);
+    {
+      std::vector<int64_t> len(n);
+      std::vector<int32_t> perm;
+      for (int64_t i = 0; i < n; ++i) len[i] = jac_rowptr[i + 1] - jac_rowptr[i];
+      length_sorted_perm(n, 2048, len, perm);
+      NSG_TRY(upload(c, &c->row_perm, perm.data(), n));
+      NSG_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (c->have_paired) {
+      std::vector<int64_t> len(meta.size());
+      std::vector<int32_t> perm;
+      for (size_t g = 0; g < meta.size(); ++g) len[g] = 2 * meta[g].np1 + meta[g].ns1 + 2 * meta[g].np2 + meta[g].ns2;
+      length_sorted_perm((int64_t)meta.size(), 1024, len, perm);
+      NSG_TRY(upload(c, &c->group_perm, perm.data(), (int64_t)perm.size()));
       c->n_ugroups = n_own_u / 2;
       c->n_groups = (int64_t)meta.size();
       c->n_items = (int64_t)items.size();

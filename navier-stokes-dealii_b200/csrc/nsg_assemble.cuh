@@ -52,7 +52,10 @@ __global__ void k_cell_geometry(int64_t T, const double *__restrict__ xy, const 
 }
 
 // ---- velocity rows: A (both Frechet terms), B^T, residual --------------------------------------
-__global__ void __launch_bounds__(NPC, 3)
+#ifndef NSG_ASM_MINB
+#define NSG_ASM_MINB 3
+#endif
+__global__ void __launch_bounds__(NPC, NSG_ASM_MINB)
 k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
              double *__restrict__ R, const double *__restrict__ geom, const int32_t *__restrict__ cell_dofs,
              const double *__restrict__ sol, const double *__restrict__ sol_old, const AsmParams P) {
@@ -110,21 +113,21 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
       }
 #pragma unroll
       for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
-#pragma unroll 1
-      for (int q = 0; q < 7; ++q) {
-        const double wq = adet * s_w[q];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {  // fully unrolled: the reference-cell tables become constant-bank operands
+        const double wq = adet * c_fe.w[q];
         double g[6][2];
         double U0 = 0, U1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
-          const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+          const double dx = c_fe.dpsi[q][l][0], dy = c_fe.dpsi[q][l][1];
           g[l][0] = a00 * dx + a01 * dy;
           g[l][1] = a10 * dx + a11 * dy;
         }
         if (!P.stokes) {
 #pragma unroll
           for (int l = 0; l < 6; ++l) {
-            const double pl = s_psi[q][l];
+            const double pl = c_fe.psi[q][l];
             U0 += u[l][0] * pl;
             U1 += u[l][1] * pl;
             G00 += u[l][0] * g[l][0];
@@ -145,7 +148,7 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
         const double c0 = rw * U0, c1 = rw * U1;
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
-          const double pl = s_psi[q][l], glx = g[l][0], gly = g[l][1];
+          const double pl = c_fe.psi[q][l], glx = g[l][0], gly = g[l][1];
           const double visc = vgx * glx + vgy * gly;
           A00[l] += visc + d00 * pl + c0 * glx;
           A01[l] += d01 * pl + c1 * glx;
@@ -156,13 +159,13 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
         const double bx = -wq * gkx, by = -wq * gky;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
-          const double cm = s_chi[q][m];
+          const double cm = c_fe.chi[q][m];
           B0[m] += bx * cm;
           B1[m] += by * cm;
         }
         // residual (cpp:287-311), time-derivative term added after the loop
         if (!P.stokes) {
-          const double Pq = pr[0] * s_chi[q][0] + pr[1] * s_chi[q][1] + pr[2] * s_chi[q][2];
+          const double Pq = pr[0] * c_fe.chi[q][0] + pr[1] * c_fe.chi[q][1] + pr[2] * c_fe.chi[q][2];
           res0 += wq * (-nurho * (G00 * gkx + G01 * gky) - P.rho * (U0 * G00 + U1 * G10) * pk + Pq * gkx);
           res1 += wq * (-nurho * (G10 * gkx + G11 * gky) - P.rho * (U0 * G01 + U1 * G11) * pk + Pq * gky);
         }
@@ -257,21 +260,21 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
       const int m = (int)ra.y;
       const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
                    a11 = __ldg(geom + 5 * c + 3), adet = __ldg(geom + 5 * c + 4);
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < 7; ++q) {
-        const double wq = adet * s_w[q];
+        const double wq = adet * c_fe.w[q];
         const double cm = s_chi[q][m];
         const double wc = -wq * cm;
         // B[m,(b,l)] -= w (g_l)_b chi_m   (cpp:277-279)
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
-          const double dx = s_dpsi[q][l][0], dy = s_dpsi[q][l][1];
+          const double dx = c_fe.dpsi[q][l][0], dy = c_fe.dpsi[q][l][1];
           Bx[l] += wc * (a00 * dx + a01 * dy);
           By[l] += wc * (a10 * dx + a11 * dy);
         }
         // Mp[m,n] += w chi_m chi_n / nu   (cpp:282-284)
 #pragma unroll
-        for (int n = 0; n < 3; ++n) M[n] += cm * s_chi[q][n] * inv_nu * wq;
+        for (int n = 0; n < 3; ++n) M[n] += cm * c_fe.chi[q][n] * inv_nu * wq;
       }
     }
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};

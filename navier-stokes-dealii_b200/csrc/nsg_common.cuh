@@ -135,6 +135,7 @@ struct nsg_ctx {
   unsigned long long *first_idx = nullptr;
   int spmv_variant = 0;
   nsg::GroupMeta *gmeta = nullptr;
+  int32_t *row_perm = nullptr, *group_perm = nullptr;
   int32_t *gitems = nullptr;
   int64_t n_groups = 0, n_ugroups = 0, n_items = 0;
   bool have_paired = false;
