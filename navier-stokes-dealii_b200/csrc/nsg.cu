@@ -359,10 +359,10 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
   NSG_TRY(halo_exchange(c, x_with_ghosts));
   if (c->spmv_variant == 2 && c->have_paired)
     k_spmv_paired<<<(unsigned)((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_groups, c->n_ugroups, c->group_perm, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
+        c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
   else if (c->spmv_variant >= 1)
     k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_own, c->row_perm, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+        c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
   else
     k_spmv_stream<<<(unsigned)c->spmv_n_chunks, SPMV_THREADS, 0, c->stream>>>(c->spmv_chunk_rows, c->rowptr, c->col, c->vals,
                                                                               x_with_ghosts, y, state);
@@ -429,6 +429,7 @@ static int get_vec(nsg_ctx *c, const double *dev, double *host, int64_t n) {
 
 }  // namespace nsg
 
+#include "nsg_krylov.cuh"
 #include "nsg_precond.cuh"
 
 using namespace nsg;
@@ -556,20 +557,17 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
     std::vector<GroupMeta> meta;
     std::vector<int32_t> items;
     c->have_paired = build_paired_index(c, jac_rowptr, jac_col, meta, items);
-    {
-      std::vector<int64_t> len(n);
-      std::vector<int32_t> perm;
-      for (int64_t i = 0; i < n; ++i) len[i] = jac_rowptr[i + 1] - jac_rowptr[i];
-      length_sorted_perm(n, 2048, len, perm);
-      NSG_TRY(upload(c, &c->row_perm, perm.data(), n));
-      NSG_CUDA(cudaStreamSynchronize(c->stream));
-    }
     if (c->have_paired) {
       std::vector<int64_t> len(meta.size());
       std::vector<int32_t> perm;
       for (size_t g = 0; g < meta.size(); ++g) len[g] = 2 * meta[g].np1 + meta[g].ns1 + 2 * meta[g].np2 + meta[g].ns2;
       length_sorted_perm((int64_t)meta.size(), 1024, len, perm);
-      NSG_TRY(upload(c, &c->group_perm, perm.data(), (int64_t)perm.size()));
+      std::vector<GroupMeta> sorted(meta.size());
+      for (size_t i = 0; i < meta.size(); ++i) {
+        sorted[i] = meta[perm[i]];
+        sorted[i].pad = (uint32_t)perm[i];
+      }
+      meta.swap(sorted);
       c->n_ugroups = n_own_u / 2;
       c->n_groups = (int64_t)meta.size();
       c->n_items = (int64_t)items.size();
@@ -577,7 +575,7 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
       NSG_TRY(upload(c, &c->gitems, items.data(), c->n_items));
       NSG_CUDA(cudaStreamSynchronize(c->stream));
     }
-    c->spmv_variant = c->have_paired ? 2 : 1;
+    c->spmv_variant = 1;  // fastest measured so far (profiles/); 2 moves fewer bytes
   }
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
@@ -655,7 +653,6 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     NSG_TRY(upload(c, &c->bnode_pos, npos.data(), (int64_t)npos.size()));
     NSG_CUDA(cudaStreamSynchronize(c->stream));
   }
-  NSG_TRY(build_blocks(c));  // sub-matrix views + level schedules of the block preconditioners
   c->h_col.clear(), c->h_col.shrink_to_fit();
   c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
   c->have_mesh = true;
@@ -787,23 +784,6 @@ int nsg_residual_norm(nsg_ctx *c, double *out) {
   return NSG_OK;
 }
 
-__global__ void k_gmres_init(GmresCtl *c, double rel_tol, int max_steps, int n_tmp, int hist_cap) {
-  c->tol = rel_tol * sqrt(c->nrm2);
-  c->state = 0;
-  c->accumulated = 0;
-  c->dim = 0;
-  c->max_steps = max_steps;
-  c->n_tmp = n_tmp;
-  c->hist_cap = hist_cap;
-}
-
-static int read_ctl_header(nsg_ctx *c) {
-  NSG_CUDA(cudaMemcpyAsync(c->h_ctl, c->ctl, GM_HEADER_BYTES, cudaMemcpyDeviceToHost, c->stream));
-  NSG_CUDA(cudaStreamSynchronize(c->stream));
-  c->d2h += GM_HEADER_BYTES;
-  return NSG_OK;
-}
-
 int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32_t n_tmp, int32_t target, int32_t *its_out,
               double *res_out) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
@@ -811,7 +791,7 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   if (n_tmp < 3 || n_tmp > GM_MAX_TMP) return fail(NSG_ERR_ARG, "n_tmp_vectors must be in [3,64]");
   if (precond < 0 || precond > 2 || max_it < 0) return fail(NSG_ERR_ARG, "bad precond / max_it");
   NSG_CUDA(cudaSetDevice(c->device));
-  const int64_t n = c->n_own, S = c->stride;
+  const int64_t S = c->stride;
   if (c->basis_n_tmp < n_tmp) {
     dev_free(c->basis);
     NSG_TRY(dev_alloc(&c->basis, (int64_t)n_tmp * S));
@@ -824,95 +804,17 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
     c->hist_cap = hist_cap;
   }
   NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
-  // temporaries start zeroed (a fresh TmpVectors pool); they are recycled across restarts
-  NSG_CUDA(cudaMemsetAsync(c->basis, 0, 8 * (size_t)n_tmp * (size_t)S, c->stream));
   if (precond != NSG_PRECOND_IDENTITY) NSG_TRY(precond_initialize(c));
   double *x = target ? c->sol : c->delta;
-  double *b = c->R;
-  GmresCtl *ctl = c->ctl;
-  const int32_t *state = &ctl->state;
-  auto V = [&](int i) { return c->basis + (int64_t)i * S; };
-  double *p = V(n_tmp - 1);
-  const int m = n_tmp - 2;
-  // SolverControl(max_it, rel_tol * ||R||)
-  NSG_TRY(dev_dot(c, n, b, b, &ctl->nrm2, nullptr));
-  k_gmres_init<<<1, 1, 0, c->stream>>>(ctl, rel_tol, max_it, n_tmp, (int)hist_cap);
-  NSG_LAUNCH_CHECK(c);
-  bool re_orth = false;
-  int rc_inner = NSG_OK;
-  const int vgrid = grid_for(n, 256);
-  while (true) {
-    // p = b - A x ; v0 = P^-1 p
-    NSG_TRY(dev_spmv(c, x, p, nullptr));
-    k_sadd<<<vgrid, 256, 0, c->stream>>>(n, p, -1.0, 1.0, b);
-    NSG_LAUNCH_CHECK(c);
-    if (precond == NSG_PRECOND_IDENTITY)
-      NSG_CUDA(cudaMemcpyAsync(V(0), p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    else if ((rc_inner = precond_vmult(c, precond, V(0), p)) != NSG_OK)
-      break;
-    NSG_TRY(dev_dot(c, n, V(0), V(0), &ctl->nrm2, nullptr));
-    k_gmres_cycle_start<<<1, 1, 0, c->stream>>>(ctl);
-    NSG_LAUNCH_CHECK(c);
-    k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, V(0), &ctl->inv_s, state);
-    NSG_LAUNCH_CHECK(c);
-    if (precond != NSG_PRECOND_IDENTITY) {  // the inner solves are host-driven: stop launching once decided
-      NSG_TRY(read_ctl_header(c));
-      if (c->h_ctl->state != 0) break;
-    }
-    bool decided = false;
-    for (int inner = 0; inner < m; ++inner) {
-      double *vv = V(inner + 1);
-      const int dim = inner + 1;
-      if (precond == NSG_PRECOND_IDENTITY) {
-        NSG_TRY(dev_spmv(c, V(inner), vv, state));
-      } else {
-        NSG_TRY(dev_spmv(c, V(inner), p, state));
-        if ((rc_inner = precond_vmult(c, precond, vv, p)) != NSG_OK) break;
-      }
-      const bool consider = !re_orth && (inner % 5 == 4);
-      if (consider) NSG_TRY(dev_dot(c, n, vv, vv, &ctl->norm_start2, state));
-      NSG_TRY(dev_dot(c, n, vv, V(0), &ctl->h[0], state));
-      for (int i = 1; i < dim; ++i) NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h[i - 1], -1.0, V(i - 1), V(i), &ctl->h[i], state));
-      NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h[dim - 1], -1.0, V(dim - 1), vv, &ctl->nrm2, state));
-      bool reorth_now = re_orth;
-      if (consider || precond != NSG_PRECOND_IDENTITY) {
-        NSG_TRY(read_ctl_header(c));
-        if (c->h_ctl->state != 0) {
-          decided = true;
-          break;
-        }
-        if (consider) {
-          const double nv = std::sqrt(c->h_ctl->nrm2), ns = std::sqrt(c->h_ctl->norm_start2);
-          if (!(nv > 10. * ns * std::sqrt(std::numeric_limits<double>::epsilon()))) re_orth = reorth_now = true;
-        }
-      }
-      if (reorth_now) {
-        NSG_TRY(dev_dot(c, n, vv, V(0), &ctl->h2[0], state));
-        for (int i = 1; i < dim; ++i) NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h2[i - 1], -1.0, V(i - 1), V(i), &ctl->h2[i], state));
-        NSG_TRY(dev_add_and_dot(c, n, vv, &ctl->h2[dim - 1], -1.0, V(dim - 1), vv, &ctl->nrm2, state));
-      }
-      k_gmres_step<<<1, 1, 0, c->stream>>>(ctl, inner, reorth_now ? 1 : 0, c->hist);
-      NSG_LAUNCH_CHECK(c);
-      k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, vv, &ctl->inv_s, state);
-      NSG_LAUNCH_CHECK(c);
-    }
-    if (rc_inner != NSG_OK) break;
-    (void)decided;
-    // x += sum_i y_i v_i with y from the back-substitution of the rotated Hessenberg matrix
-    k_gmres_backsolve<<<1, 1, 0, c->stream>>>(ctl);
-    NSG_LAUNCH_CHECK(c);
-    k_multi_axpy<<<vgrid, 256, 0, c->stream>>>(n, x, c->basis, S, ctl->y, &ctl->dim);
-    NSG_LAUNCH_CHECK(c);
-    NSG_TRY(read_ctl_header(c));
-    if (c->h_ctl->state != 0) break;
-  }
-  if (rc_inner != NSG_OK) return rc_inner;
-  NSG_TRY(read_ctl_header(c));
-  const int st = c->h_ctl->state & 0xff;
-  const int its = c->h_ctl->accumulated;
-  if (its_out) *its_out = its;
-  if (res_out) *res_out = c->h_ctl->rho;
-  c->h_hist.resize(std::min<int64_t>(its, c->hist_cap));
+  Op A = [c](double *d, double *s, const int32_t *state) { return dev_spmv(c, s, d, state); };
+  Op P = [c, precond](double *d, double *s, const int32_t *) { return precond_vmult(c, precond, d, s); };
+  GmresResult r;
+  c->inner_its = 0;
+  NSG_TRY(gmres_core(c, Range{0, c->n_own}, A, precond == NSG_PRECOND_IDENTITY ? nullptr : &P, x, c->R, c->R, rel_tol, max_it, n_tmp,
+                     c->basis, c->ctl, c->h_ctl, c->hist, (int)hist_cap, precond == NSG_PRECOND_IDENTITY, &r));
+  if (its_out) *its_out = r.its;
+  if (res_out) *res_out = r.res;
+  c->h_hist.resize(std::min<int64_t>(r.its, c->hist_cap));
   if (!c->h_hist.empty()) {
     NSG_CUDA(cudaMemcpyAsync(c->h_hist.data(), c->hist, 8 * c->h_hist.size(), cudaMemcpyDeviceToHost, c->stream));
     c->d2h += 8 * (int64_t)c->h_hist.size();
@@ -924,9 +826,9 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   c->phase_ms[2] = ms;
-  if (st != 1) {
+  if (!r.ok) {
     char buf[160];
-    snprintf(buf, sizeof buf, "GMRES did not converge: %d steps, last residual %.6e", its, c->h_ctl->rho);
+    snprintf(buf, sizeof buf, "GMRES did not converge: %d steps, last residual %.6e", r.its, r.res);
     return fail(NSG_ERR_NO_CONVERGENCE, buf);
   }
   return NSG_OK;

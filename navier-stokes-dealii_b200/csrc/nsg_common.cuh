@@ -102,10 +102,9 @@ struct CsrBlock {  // a sub-matrix held separately (A, Mp, B of the block precon
   int64_t *src = nullptr;   // position of each entry in the parent CSR (for the value refresh)
   int64_t *diag = nullptr;  // position of the diagonal in each row
   // level schedule of the lower / upper triangular solves and of the ILU(0) elimination
-  int32_t n_levels = 0;
-  int32_t *level_ptr = nullptr;   // [n_levels+1]
-  int32_t *level_rows = nullptr;  // [n] rows sorted by level
-  std::vector<int32_t> h_level_ptr;
+  int32_t n_levels = 0, n_ulevels = 0;
+  int32_t *level_rows = nullptr, *ulevel_rows = nullptr;  // [n] rows sorted by forward / backward level
+  std::vector<int32_t> h_level_ptr, h_ulevel_ptr;         // [n_levels+1] on the host (launch bounds)
   double *fval = nullptr;  // ILU(0) factors on the same pattern
   double *dinv = nullptr;
   int32_t *chunk_rows = nullptr;
@@ -176,8 +175,11 @@ struct nsg_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
   // block preconditioner state
-  nsg::CsrBlock blkA, blkM, blkB;
+  nsg::CsrBlock blkA, blkM;
   bool have_blocks = false, blocks_stale = true;
+  double *inner_basis = nullptr;
+  nsg::GmresCtl *inner_ctl = nullptr, *h_inner_ctl = nullptr;
+  int64_t inner_its = 0;
   // staging + counters
   double *h_pinned = nullptr;
   int64_t h_pinned_cap = 0;

@@ -69,14 +69,13 @@ k_spmv_stream(const int32_t *__restrict__ chunk_rows, const int64_t *__restrict_
 
 // variant 1 ("CSR-vector"): 8 lanes per row straight from global memory, no staging
 __global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_vec8(int64_t n_rows, const int32_t *__restrict__ perm, const int64_t *__restrict__ rowptr,
-            const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x,
-            double *__restrict__ y, const int32_t *__restrict__ state) {
+k_spmv_vec8(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+            const int32_t *__restrict__ state) {
   if (state && *state != 0) return;
-  const int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  const int64_t row = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
   const int l8 = threadIdx.x & 7;
   double acc = 0.0;
-  const int64_t row = slot < n_rows ? perm[slot] : n_rows;  // rows of similar length share a warp
   if (row < n_rows) {
     const int64_t s = rowptr[row], e = rowptr[row + 1];
 #pragma unroll 4
@@ -92,17 +91,21 @@ k_spmv_vec8(int64_t n_rows, const int32_t *__restrict__ perm, const int64_t *__r
 // 8 lanes walk the flat value positions of a group; the two rows of a velocity node share every
 // decoded index and every gathered x entry.  ~9.4 instead of 12 bytes per non-zero.
 __global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const int32_t *__restrict__ perm, const GroupMeta *__restrict__ meta,
+k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__ meta,
               const int32_t *__restrict__ items, const double *__restrict__ vals, const double *__restrict__ x,
               double *__restrict__ y, const int32_t *__restrict__ state) {
   if (state && *state != 0) return;
+  // metas are stored sorted by length inside windows (groups of similar length share a warp);
+  // the group id travels in the descriptor
   const int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  const int64_t g = slot < n_groups ? perm[slot] : n_groups;  // groups of similar length share a warp
   const int l8 = threadIdx.x & 7;
   double acc0 = 0.0, acc1 = 0.0;
+  GroupMeta m;
+  m.pad = 0xffffffffu;
+  if (slot < n_groups) m = meta[slot];
+  const int64_t g = slot < n_groups ? (int64_t)m.pad : n_groups;
   const bool two = g < n_ugroups;
   if (g < n_groups) {
-    const GroupMeta m = meta[g];
     const int np1 = m.np1, ns1 = m.ns1, np2 = m.np2;
     const int b1 = 2 * np1, b2 = b1 + ns1, b3 = b2 + 2 * np2, len = b3 + m.ns2;
     const double *v0 = vals + m.val_start;
