@@ -98,8 +98,10 @@ int nsg_assemble(nsg_ctx *ctx);
 
 /* MatrixTools::apply_boundary_values(bv, jacobian_matrix, delta_owned, residual_vector, false)
  * (cpp:375-376) for the (dof, value) list the host evaluated with interpolate_boundary_values
- * (cpp:351-373); dofs are LOCAL owned ids. into_solution != 0 writes the values into `solution`
- * instead of `delta` (the Stokes path, cpp:529). */
+ * (cpp:351-373); dofs are LOCAL owned ids. into_solution != 0 is the Stokes call (cpp:529): the
+ * reference passes the GHOSTED `solution` there, which solve_stokes_system neither reads (it iterates
+ * on solution_owned) nor keeps (it is overwritten by the ghost import, cpp:556) - so only the matrix
+ * rows and the right-hand side are modified and no vector entry is written. */
 int nsg_apply_dirichlet(nsg_ctx *ctx, int64_t n, const int32_t *dofs, const double *values, int32_t into_solution);
 
 /* residual_vector.l2_norm() (cpp:602,566): global over all ranks; synchronises. */

@@ -758,7 +758,9 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
     k_first_nonzero_diag_value<<<1, 1, 0, c->stream>>>(c->diag_pos, c->vals, c->first_idx + b, c->scal + 8 + b);
     NSG_LAUNCH_CHECK(c);
   }
-  double *x = into_solution ? c->sol : c->delta;
+  // Stokes path (cpp:529): the reference writes the values into the GHOSTED `solution`, which the
+  // solve never reads (it iterates on solution_owned) and overwrites afterwards -> no vector write here.
+  double *x = into_solution ? nullptr : c->delta;
   k_apply_dirichlet<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(n, c->dir_dofs, c->dir_vals, c->n_own_u, c->rowptr,
                                                                              c->diag_pos, c->vals, x, c->R, c->scal + 8);
   NSG_LAUNCH_CHECK(c);
@@ -912,10 +914,10 @@ int nsg_ilu_apply(nsg_ctx *c, int32_t which, const double *x, double *y) {
   if (!c || !x || !y || which < 0 || which > 1) return fail(NSG_ERR_ARG, "bad argument");
   if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
   NSG_CUDA(cudaSetDevice(c->device));
+  NSG_TRY(precond_initialize(c));  // builds the blocks on first use
   CsrBlock &B = which == 0 ? c->blkA : c->blkM;
   double *dx = c->work, *dy = c->work + c->stride;
   NSG_TRY(put_vec(c, dx, x, B.n));
-  NSG_TRY(precond_initialize(c));
   NSG_TRY(ilu_apply(c, B, dy, dx));
   return get_vec(c, dy, y, B.n);
 }

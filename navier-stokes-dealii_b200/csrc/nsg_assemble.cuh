@@ -394,7 +394,7 @@ __global__ void k_apply_dirichlet(int64_t n, const int32_t *__restrict__ dofs, c
       diag = first_nz[i < n_own_u ? 0 : 1];
       vals[pd] = diag;
     }
-    x[i] = g[w];
+    if (x) x[i] = g[w];
     R[i] = g[w] * diag;
   }
 }

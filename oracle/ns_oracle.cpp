@@ -654,6 +654,7 @@ void orc_set_block_jacobi(void *h, int n_parts, const int64_t *u_off, const int6
 void orc_assemble(void *h) { assemble(*(Ctx *)h); }
 void orc_apply_dirichlet(void *h, int64_t n, const int32_t *dofs, const double *vals, int32_t into_solution) {
   Ctx *c = (Ctx *)h;
+  // into_solution: the values go to the ghosted `solution` (cpp:529), not to solution_owned
   apply_dirichlet(*c, n, dofs, vals, into_solution ? c->sol : c->delta);
 }
 double orc_residual_norm(void *h) {
