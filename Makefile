@@ -8,7 +8,7 @@ CXX      := /usr/bin/g++
 CXXFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=c++17 -fPIC -Wall -Wextra
 NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wall
 
-all: $(PKG)/libnst.so $(PKG)/libnsg.so oracle/libns_oracle.so
+all: $(PKG)/libnst.so $(PKG)/libnsg.so oracle/libns_oracle.so $(PKG)/host/ns_app
 
 $(PKG)/libnst.so: $(PKG)/csrc/nst.cpp include/nst.h
 	$(CXX) $(CXXFLAGS) -shared -o $@ $<
@@ -20,7 +20,7 @@ oracle/libns_oracle.so: oracle/ns_oracle.cpp
 	$(CXX) $(CXXFLAGS) -shared -o $@ $<
 
 $(PKG)/host/ns_app: $(PKG)/host/main.cpp $(PKG)/host/NavierStokesSolver.cpp $(PKG)/host/NavierStokesSolver.hpp $(PKG)/libnst.so $(PKG)/libnsg.so
-	$(CXX) -O2 -std=c++17 -Iinclude -o $@ $(PKG)/host/main.cpp $(PKG)/host/NavierStokesSolver.cpp -L$(PKG) -lnst -lnsg -Wl,-rpath,'$$ORIGIN/..'
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(PKG)/host/main.cpp $(PKG)/host/NavierStokesSolver.cpp -L$(PKG) -lnst -lnsg -Wl,-rpath,'$$ORIGIN/..' -Wl,-rpath-link,/usr/local/cuda/lib64
 
 clean:
 	rm -f $(PKG)/libnst.so $(PKG)/libnsg.so oracle/libns_oracle.so $(PKG)/host/ns_app
