@@ -147,8 +147,13 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
 /* Tuning knobs that do not change what is computed (only the summation order inside a row):
- * key 0 = SpMV kernel variant: 0 "CSR-stream", 1 "CSR-vector, 8 lanes per row", 2 "paired CSR"
- * (pair-compressed column index; default when the pattern has the P2 node-pair structure). */
+ * key 0 = SpMV kernel variant: 0 CSR-stream through shared memory; 1 CSR-vector, 8 lanes per row;
+ * 2 paired CSR (pair-compressed column index); 3 = 1 with all loads of a row in flight; 4 = 3
+ * persistent with prefetched row extents (default); 5 bulk-async-copy (TMA) stream; 6 = 2 in the
+ * form of 4. Measured rates: profiles/.
+ * key 1 = assembly kernel variant: 0 (default) literal 7-point quadrature loop for every term, as the
+ * reference sums them; 1 the same integrals with the quadrature sum factored into pre-integrated
+ * reference-cell tables (0.45x the fp64 instructions, same speed: the kernel is latency-bound). */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

@@ -83,6 +83,37 @@ static int upload_tables() {
   t.gl[0] = 0.5 - 0.5 * std::sqrt(0.6), t.gl[1] = 0.5, t.gl[2] = 0.5 + 0.5 * std::sqrt(0.6);
   t.gw[0] = 5.0 / 18.0, t.gw[1] = 8.0 / 18.0, t.gw[2] = 5.0 / 18.0;
   NSG_CUDA(cudaMemcpyToSymbol(c_fe, &t, sizeof t));
+  // pre-integrated tables of the factored kernels, from the same rule
+  FeTables2 f;
+  std::memset(&f, 0, sizeof f);
+  for (int q = 0; q < 7; ++q) {
+    f.qx[q] = px[q], f.qy[q] = py[q];
+    for (int k = 0; k < 6; ++k) {
+      f.mh[k] += t.w[q] * t.psi[q][k];
+      for (int l = 0; l < 6; ++l) {
+        const double m = t.w[q] * t.psi[q][k] * t.psi[q][l];
+        f.Mh[k][l] += m;
+        f.Mx[k][l] += m * px[q];
+        f.My[k][l] += m * py[q];
+        f.K00[k][l] += t.w[q] * t.dpsi[q][k][0] * t.dpsi[q][l][0];
+        f.K01s[k][l] += t.w[q] * (t.dpsi[q][k][0] * t.dpsi[q][l][1] + t.dpsi[q][k][1] * t.dpsi[q][l][0]);
+        f.K11[k][l] += t.w[q] * t.dpsi[q][k][1] * t.dpsi[q][l][1];
+      }
+      for (int m = 0; m < 3; ++m)
+        for (int c = 0; c < 2; ++c) f.Bh[k][m][c] += t.w[q] * t.dpsi[q][k][c] * t.chi[q][m];
+    }
+    for (int m = 0; m < 3; ++m)
+      for (int n = 0; n < 3; ++n) f.Mp[m][n] += t.w[q] * t.chi[q][m] * t.chi[q][n];
+  }
+  {
+    double p0[6], g0[6][2], gx[6][2], gy[6][2];
+    p2_eval(0, 0, p0, g0);
+    p2_eval(1, 0, p0, gx);
+    p2_eval(0, 1, p0, gy);
+    for (int l = 0; l < 6; ++l)
+      for (int c = 0; c < 2; ++c) f.ga[l][c] = g0[l][c], f.gb[l][c] = gx[l][c] - g0[l][c], f.gc[l][c] = gy[l][c] - g0[l][c];
+  }
+  NSG_CUDA(cudaMemcpyToSymbol(c_fe2, &f, sizeof f));
   return NSG_OK;
 }
 
@@ -360,6 +391,24 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
   if (c->spmv_variant == 2 && c->have_paired)
     k_spmv_paired<<<(unsigned)((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
+  else if (c->spmv_variant == 6 && c->have_paired) {
+    static int per_sm = 0;
+    if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_paired_p, SPMV_THREADS, 0);
+    k_spmv_paired_p<<<(unsigned)std::min<int64_t>((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm, 1)),
+                      SPMV_THREADS, 0, c->stream>>>(c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
+  } else if (c->spmv_variant == 5)
+    k_spmv_tma<<<(unsigned)std::min<int64_t>(c->spmv_n_chunks, 148 * 2), SPMV_THREADS, sizeof(TmaStage) * TMA_STAGES, c->stream>>>(
+        c->spmv_n_chunks, c->spmv_chunk_rows, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  else if (c->spmv_variant == 3)
+    k_spmv_vec8u<false><<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
+        c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  else if (c->spmv_variant == 4)
+  {
+    static int per_sm = 0;
+    if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_vec8u<true>, SPMV_THREADS, 0);
+    k_spmv_vec8u<true><<<(unsigned)std::min<int64_t>((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm, 1)),
+                         SPMV_THREADS, 0, c->stream>>>(c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  }
   else if (c->spmv_variant >= 1)
     k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
@@ -381,6 +430,18 @@ static AsmParams asm_params(const nsg_ctx *c) {
 
 static int launch_assembly(nsg_ctx *c) {
   const AsmParams P = asm_params(c);
+  if (c->asm_variant == 1) {
+    if (c->wl_u.n_chunks > 0) {
+      k_assemble_u2<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
+          c->wl_u, c->rowptr, c->vals, c->R, c->geom, c->cell_dofs, c->sol, c->sol_old, P);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_p.n_chunks > 0) {
+      k_assemble_p2<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
+          c->wl_p, c->n_own_u, c->rowptr, c->vals, c->pm_rowptr, c->pm_vals, c->R, c->geom, P);
+      NSG_LAUNCH_CHECK(c);
+    }
+  } else {
   if (c->wl_u.n_chunks > 0) {
     k_assemble_u<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
         c->wl_u, c->rowptr, c->vals, c->R, c->geom, c->cell_dofs, c->sol, c->sol_old, P);
@@ -390,6 +451,7 @@ static int launch_assembly(nsg_ctx *c) {
     k_assemble_p<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
         c->wl_p, c->n_own_u, c->rowptr, c->vals, c->pm_rowptr, c->pm_vals, c->R, c->geom, P);
     NSG_LAUNCH_CHECK(c);
+  }
   }
   if (c->n_bnodes > 0) {
     k_neumann<<<grid_for(c->n_bnodes, 128, 1 << 20), 128, 0, c->stream>>>(c->n_bnodes, c->bnode_dof, c->bnode_ptr, c->bnode_face,
@@ -535,11 +597,18 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   c->h_col.assign(jac_col, jac_col + c->nnz);
   c->h_pm_rowptr.assign(pm_rowptr, pm_rowptr + n + 1);
   c->h_pm_col.assign(pm_col, pm_col + c->pm_nnz);
-  NSG_TRY(upload(c, &c->rowptr, jac_rowptr, n + 1));
-  NSG_TRY(upload(c, &c->col, jac_col, c->nnz));
+  // +16 elements of slack: the bulk copies of SpMV variant 5 round their slices up to 16 bytes
+  NSG_TRY(dev_alloc(&c->rowptr, n + 1 + 16));
+  NSG_CUDA(cudaMemsetAsync(c->rowptr, 0, 8 * (size_t)(n + 17), c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->rowptr, jac_rowptr, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+  NSG_TRY(dev_alloc(&c->col, c->nnz + 16));
+  NSG_CUDA(cudaMemsetAsync(c->col, 0, 4 * (size_t)(c->nnz + 16), c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->col, jac_col, 4 * (size_t)c->nnz, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += 8 * (n + 1) + 4 * c->nnz;
   NSG_TRY(upload(c, &c->pm_rowptr, pm_rowptr, n + 1));
   NSG_TRY(upload(c, &c->pm_col, pm_col, c->pm_nnz));
-  NSG_TRY(dev_alloc(&c->vals, c->nnz));
+  NSG_TRY(dev_alloc(&c->vals, c->nnz + 16));
+  NSG_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TmaStage) * TMA_STAGES)));
   NSG_TRY(dev_alloc(&c->pm_vals, c->pm_nnz));
   NSG_CUDA(cudaMemsetAsync(c->vals, 0, 8 * (size_t)std::max<int64_t>(c->nnz, 1), c->stream));
   NSG_CUDA(cudaMemsetAsync(c->pm_vals, 0, 8 * (size_t)std::max<int64_t>(c->pm_nnz, 1), c->stream));
@@ -575,7 +644,7 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
       NSG_TRY(upload(c, &c->gitems, items.data(), c->n_items));
       NSG_CUDA(cudaStreamSynchronize(c->stream));
     }
-    c->spmv_variant = 1;  // fastest measured so far (profiles/); 2 moves fewer bytes
+    c->spmv_variant = 4;  // fastest measured so far (profiles/r01_spmv_variants.md)
   }
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
@@ -619,6 +688,8 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
   NSG_CUDA(cudaFuncSetAttribute(k_assemble_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
   NSG_CUDA(cudaFuncSetAttribute(k_assemble_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
   // Neumann: owned boundary P2 nodes -> (face, position on the face)
   {
     struct Ent {
@@ -953,9 +1024,13 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   switch (key) {
     case 0:
-      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "spmv variant must be 0 (stream), 1 (vector8) or 2 (paired)");
-      if (value == 2 && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
+      if (value < 0 || value > 6) return fail(NSG_ERR_ARG, "spmv variant must be 0..6");
+      if ((value == 2 || value == 6) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
       c->spmv_variant = value;
+      return NSG_OK;
+    case 1:
+      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "assembly variant must be 0 (quadrature loop) or 1 (factored)");
+      c->asm_variant = value;
       return NSG_OK;
     default: return fail(NSG_ERR_ARG, "unknown tuning key");
   }

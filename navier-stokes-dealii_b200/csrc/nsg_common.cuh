@@ -132,7 +132,7 @@ struct nsg_ctx {
   int32_t *spmv_chunk_rows = nullptr;
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
-  int spmv_variant = 0;
+  int spmv_variant = 0, asm_variant = 0;
   nsg::GroupMeta *gmeta = nullptr;
   int32_t *row_perm = nullptr, *group_perm = nullptr;
   int32_t *gitems = nullptr;

@@ -19,6 +19,17 @@ constexpr int SPMV_CAP = 4096;  // non-zeros per chunk (32 KB of products)
 constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// CTAs are dispatched roughly in index order: a CTA warms L2 with the row extents of the CTA that will
+// run SPMV_PF_DIST CTAs later, which takes one DRAM latency out of that CTA's dependent load chain
+constexpr int64_t SPMV_PF_DIST = 148 * 8 * 2;
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_stream(const int32_t *__restrict__ chunk_rows, const int64_t *__restrict__ rowptr,
               const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x,
@@ -75,6 +86,10 @@ k_spmv_vec8(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *_
   if (state && *state != 0) return;
   const int64_t row = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
   const int l8 = threadIdx.x & 7;
+  if (threadIdx.x < 3) {  // 33 row pointers of a future CTA = 3 lines
+    const int64_t fr = (blockIdx.x + SPMV_PF_DIST) * (int64_t)(SPMV_THREADS / 8) + 16 * threadIdx.x;
+    if (fr <= n_rows) prefetch_l2(rowptr + fr);
+  }
   double acc = 0.0;
   if (row < n_rows) {
     const int64_t s = rowptr[row], e = rowptr[row + 1];
@@ -85,6 +100,167 @@ k_spmv_vec8(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *_
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   if (row < n_rows && l8 == 0) y[row] = acc;
+}
+
+// variants 3/4: as variant 1, but the first 64 entries of a row are fetched by 8 predicated,
+// fully unrolled steps so that all value/index loads of a row are in flight together (memory-level
+// parallelism); variant 4 is persistent and prefetches the next row's extents.
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_vec8u(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+             const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
+  int64_t row = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t s = 0, e = 0;
+  if (row < n_rows) s = rowptr[row], e = rowptr[row + 1];
+  while (true) {
+    int64_t sn = 0, en = 0;
+    const int64_t rn = row + G;
+    if (PERSISTENT && rn < n_rows) sn = rowptr[rn], en = rowptr[rn + 1];
+    double v[8];
+    int32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t p = s + l8 + 8 * k;
+      const bool in = p < e;
+      v[k] = in ? __ldcs(vals + p) : 0.0;
+      c[k] = in ? __ldcs(col + p) : -1;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c[k] >= 0) acc += v[k] * __ldg(x + c[k]);
+    for (int64_t p = s + l8 + 64; p < e; p += 8) acc += __ldcs(vals + p) * __ldg(x + __ldcs(col + p));
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (row < n_rows && l8 == 0) y[row] = acc;
+    if (!PERSISTENT) break;
+    // all lanes of a warp leave together: the warp's four rows advance by the same stride
+    if (__all_sync(0xffffffffu, rn >= n_rows)) break;
+    row = rn, s = sn, e = en;
+    if (row >= n_rows) s = e = 0;
+  }
+}
+
+// variant 5 ("TMA stream"): persistent CTAs; the value / column / row-pointer slices of a chunk of
+// rows are brought into shared memory by 1-D bulk async copies (cp.async.bulk, completion on an
+// mbarrier) two chunks ahead of the compute, so the HBM stream never waits for the x gathers.
+constexpr int TMA_STAGES = 2;
+constexpr int TMA_VAL_ELEMS = SPMV_CAP + 8;          // slice start is aligned down to 4 elements
+constexpr int TMA_RP_ELEMS = SPMV_THREADS + 4;
+struct __align__(128) TmaStage {
+  double val[TMA_VAL_ELEMS];
+  int32_t col[TMA_VAL_ELEMS];
+  int64_t rp[TMA_RP_ELEMS];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_tma(int64_t n_chunks, const int32_t *__restrict__ chunk_rows, const int64_t *__restrict__ rowptr,
+           const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x,
+           double *__restrict__ y, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  TmaStage *stage = reinterpret_cast<TmaStage *>(s_raw);
+  __shared__ uint64_t bars[TMA_STAGES];
+  __shared__ int64_t s_base[TMA_STAGES];   // first (aligned) non-zero held by the stage
+  __shared__ int32_t s_r0[TMA_STAGES], s_nr[TMA_STAGES], s_rpo[TMA_STAGES];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    for (int i = 0; i < TMA_STAGES; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t chunk, int b) {  // thread 0 only
+    const int32_t r0 = chunk_rows[chunk], r1 = chunk_rows[chunk + 1];
+    const int64_t s = rowptr[r0], e = rowptr[r1];
+    const int64_t s4 = s & ~(int64_t)3, e4 = (e + 3) & ~(int64_t)3;
+    const int32_t r0e = r0 & ~1;
+    const int nrp = ((r1 - r0e + 1) + 1) & ~1;
+    s_base[b] = s4, s_r0[b] = r0, s_nr[b] = r1 - r0, s_rpo[b] = r0 - r0e;
+    const uint32_t nv = (uint32_t)(e4 - s4);
+    if (nv > (uint32_t)TMA_VAL_ELEMS) {  // a single over-long row: handled without staging
+      s_nr[b] = -1;
+      mbar_expect_tx(&bars[b], 0);
+      return;
+    }
+    mbar_expect_tx(&bars[b], nv * 12u + (uint32_t)nrp * 8u);
+    bulk_g2s(stage[b].val, vals + s4, nv * 8u, &bars[b]);
+    bulk_g2s(stage[b].col, col + s4, nv * 4u, &bars[b]);
+    bulk_g2s(stage[b].rp, rowptr + r0e, (uint32_t)nrp * 8u, &bars[b]);
+  };
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  if (t == 0)
+    for (int i = 0; i < TMA_STAGES; ++i)
+      if (first + i * stride < n_chunks) issue(first + i * stride, i);
+  __syncthreads();
+  const int sub = t >> 3, l8 = t & 7;
+  int it = 0;
+  for (int64_t chunk = first; chunk < n_chunks; chunk += stride, ++it) {
+    const int b = it % TMA_STAGES;
+    mbar_wait(&bars[b], (it / TMA_STAGES) & 1);
+    const int nr = s_nr[b];
+    const int32_t r0 = s_r0[b];
+    if (nr >= 0) {
+      const int64_t base = s_base[b];
+      const int64_t *rp = stage[b].rp + s_rpo[b];
+      const double *sv = stage[b].val;
+      const int32_t *sc = stage[b].col;
+      for (int rb = 0; rb < nr; rb += SPMV_THREADS / 8) {
+        const int r = rb + sub;
+        double acc = 0.0;
+        if (r < nr) {
+          const int pe = (int)(rp[r + 1] - base);
+#pragma unroll 4
+          for (int p = (int)(rp[r] - base) + l8; p < pe; p += 8) acc += sv[p] * __ldg(x + sc[p]);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (r < nr && l8 == 0) y[r0 + r] = acc;
+      }
+    } else {
+      const int64_t s = rowptr[r0], e = rowptr[r0 + 1];
+      double acc = 0.0;
+      for (int64_t p = s + t; p < e; p += SPMV_THREADS) acc += vals[p] * x[col[p]];
+      acc = warp_sum_all(acc);
+      __shared__ double s_part[SPMV_THREADS / 32];
+      if ((t & 31) == 0) s_part[t >> 5] = acc;
+      __syncthreads();
+      if (t == 0) {
+        double a = 0.0;
+        for (int i = 0; i < SPMV_THREADS / 32; ++i) a += s_part[i];
+        y[r0] = a;
+      }
+    }
+    __syncthreads();  // every thread is done with stage b
+    const int64_t nxt = chunk + TMA_STAGES * stride;
+    if (t == 0 && nxt < n_chunks) issue(nxt, b);
+    __syncthreads();  // s_* of stage b are published before anyone can pass the next wait on it
+  }
 }
 
 // variant 2 ("paired CSR"): values stay in CSR order; the column index is pair-compressed (GroupMeta).
@@ -99,6 +275,10 @@ k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__
   // the group id travels in the descriptor
   const int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
   const int l8 = threadIdx.x & 7;
+  if (threadIdx.x < 6) {  // 32 descriptors of a future CTA = 6 lines
+    const int64_t fs = (blockIdx.x + SPMV_PF_DIST) * (int64_t)(SPMV_THREADS / 8);
+    if (fs < n_groups) prefetch_l2(reinterpret_cast<const char *>(meta + fs) + 128 * threadIdx.x);
+  }
   double acc0 = 0.0, acc1 = 0.0;
   GroupMeta m;
   m.pad = 0xffffffffu;
@@ -141,6 +321,95 @@ k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__
     } else {
       y[2 * n_ugroups + (g - n_ugroups)] = acc0;
     }
+  }
+}
+
+// variant 6: the paired index of variant 2 in the persistent, extent-prefetching, fully unrolled
+// form of variant 4 (least bytes per non-zero AND a short dependent-load chain)
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_paired_p(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__ meta, const int32_t *__restrict__ items,
+                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t G = ((int64_t)gridDim.x * SPMV_THREADS) >> 3;
+  int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  GroupMeta m;
+  m.val_start = 0, m.item_start = 0, m.np1 = m.ns1 = m.np2 = m.ns2 = 0, m.pad = 0xffffffffu;
+  if (slot < n_groups) m = meta[slot];
+  while (true) {
+    GroupMeta mn;
+    mn.val_start = 0, mn.item_start = 0, mn.np1 = mn.ns1 = mn.np2 = mn.ns2 = 0, mn.pad = 0xffffffffu;
+    const int64_t sn = slot + G;
+    if (sn < n_groups) mn = meta[sn];
+    const int64_t g = (int64_t)m.pad;
+    const bool valid = slot < n_groups;
+    const bool two = valid && g < n_ugroups;
+    const int np1 = m.np1, ns1 = m.ns1, np2 = m.np2;
+    const int b1 = 2 * np1, b2 = b1 + ns1, b3 = b2 + 2 * np2, len = valid ? b3 + m.ns2 : 0;
+    const double *v0 = vals + m.val_start;
+    const double *v1 = v0 + len;
+    const int32_t *it = items + m.item_start;
+    double a0[8], a1[8];
+    int32_t cc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = l8 + 8 * k;
+      const bool in = i < len;
+      int j, sub;
+      if (i < b1) {
+        j = i >> 1, sub = i & 1;
+      } else if (i < b2) {
+        j = np1 + (i - b1), sub = 0;
+      } else if (i < b3) {
+        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
+      } else {
+        j = np1 + ns1 + np2 + (i - b3), sub = 0;
+      }
+      a0[k] = in ? __ldcs(v0 + i) : 0.0;
+      a1[k] = (in && two) ? __ldcs(v1 + i) : 0.0;
+      cc[k] = in ? __ldg(it + j) + sub : -1;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (cc[k] >= 0) {
+        const double xv = __ldg(x + cc[k]);
+        acc0 += a0[k] * xv;
+        acc1 += a1[k] * xv;
+      }
+    for (int i = l8 + 64; i < len; i += 8) {  // rows longer than 64 entries
+      int j, sub;
+      if (i < b1) {
+        j = i >> 1, sub = i & 1;
+      } else if (i < b2) {
+        j = np1 + (i - b1), sub = 0;
+      } else if (i < b3) {
+        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
+      } else {
+        j = np1 + ns1 + np2 + (i - b3), sub = 0;
+      }
+      const double xv = __ldg(x + __ldg(it + j) + sub);
+      acc0 += __ldcs(v0 + i) * xv;
+      if (two) acc1 += __ldcs(v1 + i) * xv;
+    }
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+    if (valid && l8 == 0) {
+      if (two) {
+        y[2 * g] = acc0;
+        y[2 * g + 1] = acc1;
+      } else {
+        y[2 * n_ugroups + (g - n_ugroups)] = acc0;
+      }
+    }
+    if (__all_sync(0xffffffffu, sn >= n_groups)) break;
+    slot = sn;
+    m = mn;
   }
 }
 

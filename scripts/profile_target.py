@@ -14,8 +14,10 @@ dev.set_delta(np.random.default_rng(0).standard_normal(part.n_own))
 print("cells", m.n_cells, "N", d.n, "nnz", part.nnz_jac)
 nb = 12 * part.nnz_jac + 8 * part.n_loc + 16 * part.n_own
 for rep in range(2):
-    print("assembly ms", dev.time_kernel(0, 3))
-    for v in (0, 1, 2):
+    for av in (0, 1):
+        dev.set_tuning(1, av)
+        print("assembly variant", av, "ms", dev.time_kernel(0, 3))
+    for v in (1, 2, 4, 6):
         dev.set_tuning(0, v)
         ms = dev.time_kernel(1, 5)
         print("spmv variant", v, "ms", ms, "GB/s", nb / ms / 1e6)
