@@ -287,8 +287,15 @@ def main():
     aad_ms = dev.time_kernel(2, reps)
     asm_k_ms = dev.time_kernel(0, reps)
     asm_bytes = (8 * nnz + 8 * part.nnz_pm + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
-    rl = {"bound": "hbm", "kernel": "k_spmv_stream", "achieved": spmv_bytes / spmv_ms / 1e6, "peak": hbm, "unit": "GB/s",
-          "frac": spmv_bytes / spmv_ms / 1e6 / hbm, "traffic": None, "peak_source": hbm_src,
+    traffic = None   # dram__bytes_read+write per launch of the same kernel on the same workload, from profiles/
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        for rec in json.load(open(tpath)):
+            if rec["mesh"] == args.mesh and rec["levels"] == args.levels and rec["n_gpus"] == world:
+                traffic = rec["dram_bytes_per_launch"]
+    rl = {"bound": "hbm", "kernel": "k_spmv_vec8u<persistent> (SpMV variant 4: CSR, 8 lanes/row, prefetched row extents)",
+          "achieved": spmv_bytes / spmv_ms / 1e6, "peak": hbm, "unit": "GB/s",
+          "frac": spmv_bytes / spmv_ms / 1e6 / hbm, "traffic": traffic, "peak_source": hbm_src,
           "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms}
     rl_other = {
         "k_add_and_dot": {"bound": "hbm", "achieved": 32 * n_rows / aad_ms / 1e6, "peak": hbm, "unit": "GB/s",
