@@ -186,12 +186,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mesh", default="cmy", choices=list(MESHES))
-    ap.add_argument("--levels", type=int, default=5)
+    # default workload = BASELINE.json configs[3]: the cylinder domain (surface entity 5 of mesh2d.msh) red-refined
+    # 8x = 18.9 M triangles, 85 M DoFs ("~16M triangles, ~70M DoFs"); --mesh cmy --levels 5 is the 6.6 M-cell case
+    ap.add_argument("--mesh", default="mesh2d", choices=list(MESHES))
+    ap.add_argument("--levels", type=int, default=8)
     ap.add_argument("--gmres-its", type=int, default=56)
-    ap.add_argument("--cpu-level", type=int, default=2)
+    ap.add_argument("--cpu-level", type=int, default=None, help="refinement level of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cpu_level is None:
+        args.cpu_level = {"cmy": 2, "mesh2d": 5}[args.mesh]
+    # torchrun exports OMP_NUM_THREADS=1; the host topology code (libnst.so) is OpenMP-parallel
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl != "reference":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world_env))
     if args.impl == "reference":
         return run_reference(args)
 
@@ -238,13 +246,13 @@ def main():
 
     def step_e2e(host_sol):
         t0 = time.perf_counter()
-        dev.set_solution(host_sol)                 # H2D: the step's input iterate
+        dev.set_solution(host_sol)                 # H2D from pinned host memory: the step's input iterate
         dev.assemble()
         dev.apply_dirichlet(ld, lv)
         r = dev.residual_norm()                    # D2H: the step's result (assembly metric)
         t_asm = time.perf_counter() - t0
         its, res, rc = dev.solve(0, 1e-2, args.gmres_its, 30, 0, check=False)
-        delta = dev.get_delta()                    # D2H: the Newton increment
+        delta = dev.get_delta(host_delta)          # D2H into pinned host memory: the Newton increment
         return t_asm, time.perf_counter() - t0, delta
 
     for _ in range(args.warmup):
@@ -307,7 +315,10 @@ def main():
 
     # end-to-end through the public API with host buffers
     e2e_asm, e2e_step = [], []
-    host_sol = sol.copy()
+    pin_in = torch.empty(part.n_own, dtype=torch.float64).pin_memory()
+    pin_out = torch.empty(max(part.n_own, 1), dtype=torch.float64).pin_memory()
+    host_sol, host_delta = pin_in.numpy(), pin_out.numpy()
+    host_sol[:] = sol
     for _ in range(2):
         step_e2e(host_sol)
     barrier()

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -150,8 +151,10 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
         }
       }
   }
-  // chunks: consecutive owners while the slots fit one CTA
-  auto nslots = [&](int64_t g) { return (int)((gptr[g + 1] - gptr[g] + ASM_PPT - 1) / ASM_PPT); };
+  // chunks: consecutive owners while their slots fit one CTA.  The slots of one owner occupy adjacent
+  // lanes of ONE warp (an owner never straddles a warp: pad to the next warp instead), so the ordered
+  // commit of an owner's pairs needs only __syncwarp(), never a CTA barrier.
+  auto nslots = [&](int64_t g) { return std::max((int)((gptr[g + 1] - gptr[g] + ASM_PPT - 1) / ASM_PPT), 1); };
   std::vector<ChunkInfo> chunks;
   {
     int64_t g = 0, rec = 0;
@@ -160,10 +163,12 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
       ci.g0 = (int32_t)g;
       int nt = 0, mx = 0;
       while (g < ng && g - ci.g0 < 255) {
-        const int ns = std::max(nslots(g), 1);
-        if (ns > NPC) return fail(NSG_ERR_ARG, "a vertex has too many incident cells for one CTA");
-        if (nt + ns > NPC) break;
-        nt += ns;
+        const int ns = nslots(g);
+        if (ns > 32) return fail(NSG_ERR_ARG, "a vertex has too many incident cells (more than 64)");
+        int pos = nt;
+        if ((pos & 31) + ns > 32) pos = (pos + 31) & ~31;  // next warp
+        if (pos + ns > NPC) break;
+        nt = pos + ns;
         mx = std::max(mx, ns);
         ++g;
       }
@@ -177,63 +182,64 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
   }
   const int64_t nchunks = (int64_t)chunks.size();
   const int64_t nrecs = nchunks ? chunks.back().rec_base + (int64_t)chunks.back().n_threads * ASM_PPT : 0;
-  std::vector<uint16_t> tdesc((size_t)nchunks * NPC, 0);
+  std::vector<uint16_t> tdesc((size_t)nchunks * NPC, 0xffff);  // 0xffff = padding lane
   std::vector<PairRec> recs(nrecs);
   int bad = 0;
   int64_t max_stage = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_stage) reduction(+ : bad)
   for (int64_t b = 0; b < nchunks; ++b) {
     const ChunkInfo &ci = chunks[b];
-    // thread order: all slot-0 threads (one per owner), then slot 1, ...
+    PairRec empty;
+    std::memset(&empty, 0, sizeof empty);
+    empty.cell = -1;
+    for (int j = 0; j < ASM_PPT; ++j)
+      for (int t = 0; t < ci.n_threads; ++t) recs[ci.rec_base + (int64_t)j * ci.n_threads + t] = empty;
     int t = 0;
-    for (int r = 0; r < ci.max_slots; ++r)
-      for (int64_t g = ci.g0; g < ci.g1; ++g) {
-        const int ns = std::max(nslots(g), 1);
-        if (r >= ns) continue;
+    for (int64_t g = ci.g0; g < ci.g1; ++g) {
+      const int ns = nslots(g);
+      if ((t & 31) + ns > 32) t = (t + 31) & ~31;
+      for (int r = 0; r < ns; ++r, ++t) {
         tdesc[b * NPC + t] = (uint16_t)((g - ci.g0) | (r << 8));
         for (int j = 0; j < ASM_PPT; ++j) {
-          PairRec rcd;
-          std::memset(&rcd, 0, sizeof rcd);
-          rcd.cell = -1;
           const int64_t pi = r + (int64_t)j * ns;
-          if (pi < gptr[g + 1] - gptr[g]) {
-            const int64_t src = gptr[g] + pi;
-            rcd.cell = pcell[src];
-            rcd.k = pk[src];
-            const int32_t *cdc = cd + 15 * (int64_t)rcd.cell;
-            const int64_t row = kind == 0 ? 2 * g : nu + g;
-            const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
-            if (re - rs >= 65535) bad++;
-            if (kind == 0 && c->h_rowptr[row + 2] - re != re - rs) bad++;
-            const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
-            for (int l = 0; l < 6; ++l) {
-              const int32_t tgt = cdc[uidx(l)];
-              const int32_t *p = std::lower_bound(cb, ce, tgt);
-              if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
-                bad++;
-                continue;
-              }
-              rcd.off[l] = (uint16_t)(p - cb);
+          if (pi >= gptr[g + 1] - gptr[g]) continue;
+          PairRec rcd = empty;
+          const int64_t src = gptr[g] + pi;
+          rcd.cell = pcell[src];
+          rcd.k = pk[src];
+          const int32_t *cdc = cd + 15 * (int64_t)rcd.cell;
+          const int64_t row = kind == 0 ? 2 * g : nu + g;
+          const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
+          if (re - rs >= 65535) bad++;
+          if (kind == 0 && c->h_rowptr[row + 2] - re != re - rs) bad++;
+          const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
+          for (int l = 0; l < 6; ++l) {
+            const int32_t tgt = cdc[uidx(l)];
+            const int32_t *p = std::lower_bound(cb, ce, tgt);
+            if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
+              bad++;
+              continue;
             }
-            const int32_t *mb = cb, *me = ce;
-            if (kind == 1) {
-              mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
-              me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+            rcd.off[l] = (uint16_t)(p - cb);
+          }
+          const int32_t *mb = cb, *me = ce;
+          if (kind == 1) {
+            mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
+            me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+          }
+          for (int m = 0; m < 3; ++m) {
+            const int32_t tgt = cdc[3 * m + 2];
+            const int32_t *p = std::lower_bound(mb, me, tgt);
+            if (p == me || *p != tgt) {
+              bad++;
+              continue;
             }
-            for (int m = 0; m < 3; ++m) {
-              const int32_t tgt = cdc[3 * m + 2];
-              const int32_t *p = std::lower_bound(mb, me, tgt);
-              if (p == me || *p != tgt) {
-                bad++;
-                continue;
-              }
-              rcd.off[6 + m] = (uint16_t)(p - mb);
-            }
+            rcd.off[6 + m] = (uint16_t)(p - mb);
           }
           recs[ci.rec_base + (int64_t)j * ci.n_threads + t] = rcd;
         }
-        ++t;
       }
+    }
     if (t != ci.n_threads) bad++;
     int64_t stage;
     if (kind == 0)
@@ -425,6 +431,7 @@ static AsmParams asm_params(const nsg_ctx *c) {
   P.dt_inv = c->prm.use_mass ? 1.0 / c->prm.deltat : 0.0;
   P.f0 = c->prm.forcing[0], P.f1 = c->prm.forcing[1];
   P.use_mass = c->prm.use_mass, P.stokes = c->prm.stokes, P.neumann_id = c->prm.neumann_id;
+  P.debug = std::getenv("NSG_ASM_DEBUG") ? std::atoi(std::getenv("NSG_ASM_DEBUG")) : 0;
   return P;
 }
 
@@ -471,20 +478,38 @@ static int ensure_pinned(nsg_ctx *c, int64_t n) {
   return NSG_OK;
 }
 
-// host (pageable or pinned) -> device vector of owned length, through the pinned staging buffer
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+// host -> device vector of owned length: straight DMA from page-locked caller memory, through the
+// context's pinned staging buffer otherwise
 static int put_vec(nsg_ctx *c, double *dev, const double *host, int64_t n) {
-  NSG_TRY(ensure_pinned(c, n));
-  std::memcpy(c->h_pinned, host, sizeof(double) * (size_t)n);
-  NSG_CUDA(cudaMemcpyAsync(dev, c->h_pinned, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  const double *src = host;
+  if (!is_pinned(host)) {
+    NSG_TRY(ensure_pinned(c, n));
+    std::memcpy(c->h_pinned, host, sizeof(double) * (size_t)n);
+    src = c->h_pinned;
+  }
+  NSG_CUDA(cudaMemcpyAsync(dev, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   c->h2d += 8 * n;
   return NSG_OK;
 }
 static int get_vec(nsg_ctx *c, const double *dev, double *host, int64_t n) {
-  NSG_TRY(ensure_pinned(c, n));
-  NSG_CUDA(cudaMemcpyAsync(c->h_pinned, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-  NSG_CUDA(cudaStreamSynchronize(c->stream));
-  std::memcpy(host, c->h_pinned, sizeof(double) * (size_t)n);
+  if (is_pinned(host)) {
+    NSG_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+  } else {
+    NSG_TRY(ensure_pinned(c, n));
+    NSG_CUDA(cudaMemcpyAsync(c->h_pinned, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+    std::memcpy(host, c->h_pinned, sizeof(double) * (size_t)n);
+  }
   c->d2h += 8 * n;
   return NSG_OK;
 }

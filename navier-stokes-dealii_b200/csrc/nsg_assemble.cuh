@@ -46,6 +46,7 @@ __constant__ FeTables2 c_fe2;
 struct AsmParams {
   double nu, rho, p_out, dt_inv, f0, f1;
   int32_t use_mass, stokes, neumann_id;
+  int32_t debug;  // NSG_ASM_DEBUG bit mask for bring-up experiments (0 in production)
 };
 
 // local scalar P2 index k -> position of its x-velocity dof in the 15-dof FESystem order
@@ -85,15 +86,17 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
   const int cnt = (int)(re - rs);
   double *s_res = s_vals + cnt;
   for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
-  if (t < 7) s_w[t] = c_fe.w[t];
-  if (t < 42) (&s_psi[0][0])[t] = (&c_fe.psi[0][0])[t];
-  if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
-  if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
+  for (int i = t; i < 7; i += NPC) s_w[i] = c_fe.w[i];
+  for (int i = t; i < 42; i += NPC) (&s_psi[0][0])[i] = (&c_fe.psi[0][0])[i];
+  for (int i = t; i < 84; i += NPC) (&s_dpsi[0][0][0])[i] = (&c_fe.dpsi[0][0][0])[i];
+  for (int i = t; i < 21; i += NPC) (&s_chi[0][0])[i] = (&c_fe.chi[0][0])[i];
   __syncthreads();
 
-  const bool have = t < ci.n_threads;
-  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
-  const int gl = desc & 0xff, slot = desc >> 8;
+  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
+  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
+  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
+  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
   const int64_t node = ci.g0 + gl;
   const int64_t r0 = rowptr[2 * node];
   const int len = (int)(rowptr[2 * node + 1] - r0);
@@ -107,7 +110,7 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
       ra = __ldcs(rp);
       rb = __ldcs(rp + 1);
     }
-    const bool work = (int)ra.x >= 0;
+    const bool work = (int)ra.x >= 0 && !(P.debug & 1);
     double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
     double res0 = 0.0, res1 = 0.0;
 #pragma unroll
@@ -205,8 +208,8 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
     }
     // commit rounds: slot r of every owner adds its pair into the owner's rows, in cell order
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < ci.max_slots; ++r) {
-      if (work && slot == r) {
+    for (int r = 0; r < wrounds; ++r) {
+      if (work && slot == r && !(P.debug & 4)) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
           const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
@@ -225,10 +228,12 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
         s_res[2 * gl] += res0;
         s_res[2 * gl + 1] += res1;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
-  for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
+  __syncthreads();
+  if (!(P.debug & 2))
+    for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
   for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
 
@@ -248,13 +253,15 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
   const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
   double *s_pm = s_vals + cnt;
   for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
-  if (t < 7) s_w[t] = c_fe.w[t];
-  if (t < 84) (&s_dpsi[0][0][0])[t] = (&c_fe.dpsi[0][0][0])[t];
-  if (t < 21) (&s_chi[0][0])[t] = (&c_fe.chi[0][0])[t];
+  for (int i = t; i < 7; i += NPC) s_w[i] = c_fe.w[i];
+  for (int i = t; i < 84; i += NPC) (&s_dpsi[0][0][0])[i] = (&c_fe.dpsi[0][0][0])[i];
+  for (int i = t; i < 21; i += NPC) (&s_chi[0][0])[i] = (&c_fe.chi[0][0])[i];
   __syncthreads();
-  const bool have = t < ci.n_threads;
-  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
-  const int gl = desc & 0xff, slot = desc >> 8;
+  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
+  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
+  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
+  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
   const int64_t prow = n_own_u + ci.g0 + gl;
   double *row = s_vals + (rowptr[prow] - rs);
   double *mrow = s_pm + (pm_rowptr[prow] - ms);
@@ -294,7 +301,7 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
       }
     }
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < ci.max_slots; ++r) {
+    for (int r = 0; r < wrounds; ++r) {
       if (work && slot == r) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
@@ -309,9 +316,10 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
           mrow[o] += M[n];
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
+  __syncthreads();
   for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
   for (int i = t; i < mcnt; i += NPC) __stcs(pm_vals + ms + i, s_pm[i]);
   // no statement of the reference tests the pressure space: R_p == 0
@@ -342,22 +350,24 @@ k_assemble_u2(const WorkList wl, const int64_t *__restrict__ rowptr, double *__r
   const int cnt = (int)(re - rs);
   double *s_res = s_vals + cnt;
   for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
-  if (t < 42) (&s_psi[0][0])[t] = (&c_fe.psi[0][0])[t];
-  if (t < 36) {
-    (&s_Mh[0][0])[t] = (&c_fe2.Mh[0][0])[t];
-    (&s_Mx[0][0])[t] = (&c_fe2.Mx[0][0])[t];
-    (&s_My[0][0])[t] = (&c_fe2.My[0][0])[t];
-    (&s_K00[0][0])[t] = (&c_fe2.K00[0][0])[t];
-    (&s_K01s[0][0])[t] = (&c_fe2.K01s[0][0])[t];
-    (&s_K11[0][0])[t] = (&c_fe2.K11[0][0])[t];
-    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
+  for (int i = t; i < 42; i += NPC) (&s_psi[0][0])[i] = (&c_fe.psi[0][0])[i];
+  for (int i = t; i < 36; i += NPC) {
+    (&s_Mh[0][0])[i] = (&c_fe2.Mh[0][0])[i];
+    (&s_Mx[0][0])[i] = (&c_fe2.Mx[0][0])[i];
+    (&s_My[0][0])[i] = (&c_fe2.My[0][0])[i];
+    (&s_K00[0][0])[i] = (&c_fe2.K00[0][0])[i];
+    (&s_K01s[0][0])[i] = (&c_fe2.K01s[0][0])[i];
+    (&s_K11[0][0])[i] = (&c_fe2.K11[0][0])[i];
+    (&s_Bh[0][0][0])[i] = (&c_fe2.Bh[0][0][0])[i];
   }
-  if (t < 6) s_mh[t] = c_fe2.mh[t];
+  for (int i = t; i < 6; i += NPC) s_mh[i] = c_fe2.mh[i];
   __syncthreads();
 
-  const bool have = t < ci.n_threads;
-  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
-  const int gl = desc & 0xff, slot = desc >> 8;
+  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
+  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
+  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
+  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
   const int64_t node = ci.g0 + gl;
   const int64_t r0 = rowptr[2 * node];
   const int len = (int)(rowptr[2 * node + 1] - r0);
@@ -504,7 +514,7 @@ k_assemble_u2(const WorkList wl, const int64_t *__restrict__ rowptr, double *__r
       res1 += P.f1 * d * s_mh[k];
     }
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < ci.max_slots; ++r) {
+    for (int r = 0; r < wrounds; ++r) {
       if (work && slot == r) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
@@ -524,9 +534,10 @@ k_assemble_u2(const WorkList wl, const int64_t *__restrict__ rowptr, double *__r
         s_res[2 * gl] += res0;
         s_res[2 * gl + 1] += res1;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
+  __syncthreads();
   for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
   for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
@@ -547,12 +558,14 @@ k_assemble_p2(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ ro
   const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
   double *s_pm = s_vals + cnt;
   for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
-  if (t < 36) (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
-  if (t < 9) (&s_Mp[0][0])[t] = (&c_fe2.Mp[0][0])[t];
+  for (int i = t; i < 36; i += NPC) (&s_Bh[0][0][0])[i] = (&c_fe2.Bh[0][0][0])[i];
+  for (int i = t; i < 9; i += NPC) (&s_Mp[0][0])[i] = (&c_fe2.Mp[0][0])[i];
   __syncthreads();
-  const bool have = t < ci.n_threads;
-  const int desc = have ? wl.tdesc[b * NPC + t] : 0;
-  const int gl = desc & 0xff, slot = desc >> 8;
+  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
+  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
+  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
+  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
   const int64_t prow = n_own_u + ci.g0 + gl;
   double *row = s_vals + (rowptr[prow] - rs);
   double *mrow = s_pm + (pm_rowptr[prow] - ms);
@@ -584,7 +597,7 @@ k_assemble_p2(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ ro
       for (int n = 0; n < 3; ++n) M[n] = s_Mp[m][n] * inv_nu * d;
     }
     const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < ci.max_slots; ++r) {
+    for (int r = 0; r < wrounds; ++r) {
       if (work && slot == r) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
@@ -599,9 +612,10 @@ k_assemble_p2(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ ro
           mrow[o] += M[n];
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
+  __syncthreads();
   for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
   for (int i = t; i < mcnt; i += NPC) __stcs(pm_vals + ms + i, s_pm[i]);
   for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;

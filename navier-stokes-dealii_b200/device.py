@@ -91,8 +91,9 @@ class DeviceProblem:
         assert v.shape == (self.n_own,), f"expected {self.n_own} owned entries, got {v.shape}"
         nsg_check(fn(self._h, v))
 
-    def _get(self, fn, n):
-        out = np.zeros(max(n, 1), np.float64)
+    def _get(self, fn, n, out=None):
+        if out is None:
+            out = np.zeros(max(n, 1), np.float64)
         nsg_check(fn(self._h, out))
         return out[:n]
 
@@ -108,8 +109,9 @@ class DeviceProblem:
     def get_solution(self):
         return self._get(self._L.nsg_get_solution, self.n_own)
 
-    def get_delta(self):
-        return self._get(self._L.nsg_get_delta, self.n_own)
+    def get_delta(self, out=None):
+        """out: optional preallocated (e.g. page-locked) float64 array of n_own entries."""
+        return self._get(self._L.nsg_get_delta, self.n_own, out)
 
     def get_residual(self):
         return self._get(self._L.nsg_get_residual, self.n_own)
