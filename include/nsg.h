@@ -133,6 +133,12 @@ int nsg_get_residual(nsg_ctx *ctx, double *host);
 int nsg_get_matrix_values(nsg_ctx *ctx, double *host /* nnz(J), CSR order */);
 int nsg_get_pm_values(nsg_ctx *ctx, double *host /* nnz(Mp) */);
 
+/* N3 (the reference has no drag/lift code): force of the fluid on the body bounded by the
+ * faces with `boundary_id` (13 = cylinder, cpp:368), from the current `solution`:
+ * F = -oint (rho nu grad(u) n - p n) ds, n = outward normal of the fluid domain, integrated with the
+ * reference's 3-point face rule (cpp:52). out2 = (drag F_x, lift F_y), global over all ranks. */
+int nsg_boundary_force(nsg_ctx *ctx, int32_t boundary_id, double *out2);
+
 /* Building blocks exported for parity tests and roofline measurement. x, y are host vectors of
  * owned length. nsg_spmv: y = J x (jacobian_matrix.vmult). nsg_precond_apply: y = P^-1 x for the
  * given kind with the CURRENT matrices (initialize + vmult, hpp:526-572 / 582-619).
@@ -153,7 +159,8 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * form of 4. Measured rates: profiles/.
  * key 1 = assembly kernel variant: 0 (default) literal 7-point quadrature loop for every term, as the
  * reference sums them; 1 the same integrals with the quadrature sum factored into pre-integrated
- * reference-cell tables (0.45x the fp64 instructions, same speed: the kernel is latency-bound). */
+ * reference-cell tables (0.45x the fp64 instructions, same speed: the kernel is latency-bound).
+ * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

@@ -144,6 +144,7 @@ _NSG_SIGS = {
     "nsg_get_residual": (C.c_int, [vp, f64p]),
     "nsg_get_matrix_values": (C.c_int, [vp, f64p]),
     "nsg_get_pm_values": (C.c_int, [vp, f64p]),
+    "nsg_boundary_force": (C.c_int, [vp, i32, f64p]),
     "nsg_spmv": (C.c_int, [vp, f64p, f64p]),
     "nsg_precond_apply": (C.c_int, [vp, i32, f64p, f64p]),
     "nsg_ilu_apply": (C.c_int, [vp, i32, f64p, f64p]),

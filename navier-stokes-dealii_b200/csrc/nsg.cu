@@ -578,6 +578,8 @@ void nsg_destroy(nsg_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
+  c->graphs.clear();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
@@ -1018,6 +1020,28 @@ int nsg_ilu_apply(nsg_ctx *c, int32_t which, const double *x, double *y) {
   return get_vec(c, dy, y, B.n);
 }
 
+int nsg_boundary_force(nsg_ctx *c, int32_t boundary_id, double *out2) {
+  if (!c || !out2) return fail(NSG_ERR_ARG, "null argument");
+  if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  out2[0] = out2[1] = 0.0;
+  double *fx = c->work + 2 * c->stride, *fy = c->work + 3 * c->stride;  // n_bfaces <= n_loc
+  if (c->n_bfaces > c->stride) return fail(NSG_ERR_ARG, "more boundary faces than DoFs");
+  if (c->n_bfaces > 0) {
+    k_face_force<<<grid_for(c->n_bfaces, 128, 1 << 30), 128, 0, c->stream>>>(c->n_bfaces, boundary_id, c->n_own_u, c->bface_cell,
+                                                                           c->bface_face, c->bface_tag, c->cell_vertices, c->cell_dofs,
+                                                                           c->xy, c->geom, c->sol, c->prm.rho * c->prm.nu, fx, fy);
+    NSG_LAUNCH_CHECK(c);
+  }
+  k_sum_ordered<<<1, 256, 0, c->stream>>>(c->n_bfaces, fx, fy, c->scal + 32);
+  NSG_LAUNCH_CHECK(c);
+  if (c->n_ranks > 1) NSG_NCCL(nccl_api().AllReduce(c->scal + 32, c->scal + 32, 2, ncclDouble, ncclSum, c->comm, c->stream));
+  NSG_CUDA(cudaMemcpyAsync(out2, c->scal + 32, 16, cudaMemcpyDeviceToHost, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h += 16;
+  return NSG_OK;
+}
+
 int nsg_time_kernel(nsg_ctx *c, int32_t what, int32_t reps, double *ms_per_launch) {
   if (!c || !ms_per_launch || reps < 1) return fail(NSG_ERR_ARG, "bad argument");
   if (!c->have_mesh) return fail(NSG_ERR_STATE, "nsg_set_mesh first");
@@ -1052,6 +1076,11 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       if (value < 0 || value > 6) return fail(NSG_ERR_ARG, "spmv variant must be 0..6");
       if ((value == 2 || value == 6) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
       c->spmv_variant = value;
+      for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
+      c->graphs.clear();  // captured segments embed the SpMV kernel
+      return NSG_OK;
+    case 2:
+      c->use_graphs = value != 0;
       return NSG_OK;
     case 1:
       if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "assembly variant must be 0 (quadrature loop) or 1 (factored)");

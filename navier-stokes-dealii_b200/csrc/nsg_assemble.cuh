@@ -77,7 +77,7 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
              double *__restrict__ R, const double *__restrict__ geom, const int32_t *__restrict__ cell_dofs,
              const double *__restrict__ sol, const double *__restrict__ sol_old, const AsmParams P) {
   extern __shared__ double s_vals[];
-  __shared__ double s_w[7], s_psi[7][6], s_dpsi[7][6][2], s_chi[7][3];
+  __shared__ double s_psi[7][6], s_dpsi[7][6][2];  // only the entries indexed by the owner's (per-thread) k
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
   const ChunkInfo ci = wl.chunks[b];
@@ -86,10 +86,8 @@ k_assemble_u(const WorkList wl, const int64_t *__restrict__ rowptr, double *__re
   const int cnt = (int)(re - rs);
   double *s_res = s_vals + cnt;
   for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
-  for (int i = t; i < 7; i += NPC) s_w[i] = c_fe.w[i];
   for (int i = t; i < 42; i += NPC) (&s_psi[0][0])[i] = (&c_fe.psi[0][0])[i];
   for (int i = t; i < 84; i += NPC) (&s_dpsi[0][0][0])[i] = (&c_fe.dpsi[0][0][0])[i];
-  for (int i = t; i < 21; i += NPC) (&s_chi[0][0])[i] = (&c_fe.chi[0][0])[i];
   __syncthreads();
 
   const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
@@ -243,7 +241,7 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
              const int64_t *__restrict__ pm_rowptr, double *__restrict__ pm_vals, double *__restrict__ R,
              const double *__restrict__ geom, const AsmParams P) {
   extern __shared__ double s_vals[];
-  __shared__ double s_w[7], s_dpsi[7][6][2], s_chi[7][3];
+  __shared__ double s_chi[7][3];  // indexed by the owner's (per-thread) m
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
   const ChunkInfo ci = wl.chunks[b];
@@ -253,8 +251,6 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
   const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
   double *s_pm = s_vals + cnt;
   for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
-  for (int i = t; i < 7; i += NPC) s_w[i] = c_fe.w[i];
-  for (int i = t; i < 84; i += NPC) (&s_dpsi[0][0][0])[i] = (&c_fe.dpsi[0][0][0])[i];
   for (int i = t; i < 21; i += NPC) (&s_chi[0][0])[i] = (&c_fe.chi[0][0])[i];
   __syncthreads();
   const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
@@ -659,6 +655,67 @@ __global__ void k_neumann(int64_t n_bnodes, const int32_t *__restrict__ bnode_do
     R[d] += r0;
     R[d + 1] += r1;
   }
+}
+
+// ---- N3: force of the fluid on the body bounded by the faces with `boundary_id` --------
+// F = -oint (rho nu grad(u) n - p n) ds, n = outward normal of the fluid, 3-point face rule. One thread per
+// boundary face writes its contribution (faces whose edge-midpoint node this rank owns); the per-face
+// values are then summed in index order by one block (deterministic).
+__global__ void k_face_force(int64_t n_bfaces, int32_t boundary_id, int64_t n_own_u, const int32_t *__restrict__ bface_cell,
+                             const int32_t *__restrict__ bface_face, const int32_t *__restrict__ bface_tag,
+                             const int32_t *__restrict__ cv, const int32_t *__restrict__ cell_dofs, const double *__restrict__ xy,
+                             const double *__restrict__ geom, const double *__restrict__ sol, double mu, double *__restrict__ fx,
+                             double *__restrict__ fy) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_bfaces) return;
+  double ax = 0.0, ay = 0.0;
+  const int64_t c = bface_cell[i];
+  const int f = bface_face[i];
+  const int32_t *cd = cell_dofs + 15 * c;
+  if (bface_tag[i] == boundary_id && cd[uidx(3 + f)] < n_own_u) {
+    const int32_t va = cv[3 * c + f], vb = cv[3 * c + (f + 1) % 3], vc = cv[3 * c + (f + 2) % 3];
+    const double ex = xy[2 * vb] - xy[2 * va], ey = xy[2 * vb + 1] - xy[2 * va + 1];
+    const double L = sqrt(ex * ex + ey * ey);
+    double nx = ey / L, ny = -ex / L;
+    if (nx * (xy[2 * vc] - xy[2 * va]) + ny * (xy[2 * vc + 1] - xy[2 * va + 1]) > 0) nx = -nx, ny = -ny;
+    const double a00 = geom[5 * c], a01 = geom[5 * c + 1], a10 = geom[5 * c + 2], a11 = geom[5 * c + 3];
+    const double rx[3] = {0, 1, 0}, ry[3] = {0, 0, 1};
+    const int ia = f, ib = (f + 1) % 3;
+    for (int q = 0; q < 3; ++q) {
+      const double s = c_fe.gl[q];
+      const double x = rx[ia] + s * (rx[ib] - rx[ia]), y = ry[ia] + s * (ry[ib] - ry[ia]);
+      const double l0 = 1 - x - y, l1 = x, l2 = y;
+      const double dp[6][2] = {{-(4 * l0 - 1), -(4 * l0 - 1)}, {4 * l1 - 1, 0.0}, {0.0, 4 * l2 - 1},
+                               {4 * (l0 - l1), -4 * l1},       {4 * l2, 4 * l1},  {-4 * l2, 4 * (l0 - l2)}};
+      double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+      for (int k = 0; k < 6; ++k) {
+        const double gx = a00 * dp[k][0] + a01 * dp[k][1], gy = a10 * dp[k][0] + a11 * dp[k][1];
+        const double u0 = sol[cd[uidx(k)]], u1 = sol[cd[uidx(k)] + 1];
+        G00 += u0 * gx, G01 += u0 * gy, G10 += u1 * gx, G11 += u1 * gy;
+      }
+      const double P = sol[cd[2]] * l0 + sol[cd[5]] * l1 + sol[cd[8]] * l2;
+      const double w = L * c_fe.gw[q];
+      ax += w * (mu * (G00 * nx + G01 * ny) - P * nx);
+      ay += w * (mu * (G10 * nx + G11 * ny) - P * ny);
+    }
+  }
+  fx[i] = -ax;
+  fy[i] = -ay;
+}
+__global__ void k_sum_ordered(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out2) {
+  __shared__ double sa[256], sb[256];
+  const int t = threadIdx.x;
+  // contiguous slabs per thread, then an index-ordered tree: the same result for a given n
+  const int64_t per = (n + 255) / 256, lo = min(n, t * per), hi = min(n, lo + per);
+  double x = 0.0, y = 0.0;
+  for (int64_t i = lo; i < hi; ++i) x += a[i], y += b[i];
+  sa[t] = x, sb[t] = y;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) sa[t] += sa[t + s], sb[t] += sb[t + s];
+    __syncthreads();
+  }
+  if (t == 0) out2[0] = sa[0], out2[1] = sb[0];
 }
 
 // ---- K3: MatrixTools::apply_boundary_values, Trilinos block version (cpp:375-376) ---

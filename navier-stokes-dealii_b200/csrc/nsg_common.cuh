@@ -94,6 +94,23 @@ struct GmresCtl {
 };
 constexpr size_t GM_HEADER_BYTES = 64;
 
+// One cached CUDA graph per launch segment of the identity-preconditioned restart cycle (the stretches
+// between two host synchronisation points).  Small meshes are launch-bound (~19 kernels per GMRES step);
+// replaying a captured segment costs a fraction of issuing its kernels one by one.
+struct GraphKey {
+  int seg, n_tmp;
+  int64_t n, off;
+  const void *x, *b, *basis, *hist;
+  bool operator==(const GraphKey &o) const {
+    return seg == o.seg && n_tmp == o.n_tmp && n == o.n && off == o.off && x == o.x && b == o.b && basis == o.basis && hist == o.hist;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;
+  int64_t launches;
+};
+
 struct CsrBlock {  // a sub-matrix held separately (A, Mp, B of the block preconditioners)
   int64_t n = 0, nnz = 0;
   int64_t *rowptr = nullptr;
@@ -133,6 +150,8 @@ struct nsg_ctx {
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
   int spmv_variant = 0, asm_variant = 0;
+  bool use_graphs = true;
+  std::vector<nsg::GraphEntry> graphs;
   nsg::GroupMeta *gmeta = nullptr;
   int32_t *row_perm = nullptr, *group_perm = nullptr;
   int32_t *gitems = nullptr;

@@ -61,8 +61,9 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
   k_gmres_init<<<1, 1, 0, c->stream>>>(ctl, rel_tol, max_steps, n_tmp, hist_cap);
   NSG_LAUNCH_CHECK(c);
   bool re_orth = false;
-  while (true) {
-    // p = b - A x ; v0 = P^-1 p
+
+  // ---- the pieces of one restart cycle ----
+  auto cycle_start = [&]() -> int {  // p = b - A x ; v0 = P^-1 p ; rho = ||v0|| ; v0 /= rho
     NSG_TRY(A(p, x, nullptr));
     k_sadd<<<vgrid, 256, 0, c->stream>>>(n, p + o, -1.0, 1.0, b + o);
     NSG_LAUNCH_CHECK(c);
@@ -75,52 +76,132 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
     NSG_LAUNCH_CHECK(c);
     k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, V(0) + o, &ctl->inv_s, state);
     NSG_LAUNCH_CHECK(c);
-    if (!lazy) {
-      NSG_TRY(read_ctl_header(c, ctl, h_ctl));
-      if (h_ctl->state != 0) break;
+    return NSG_OK;
+  };
+  auto iter_front = [&](int inner, bool consider) -> int {  // A v, P^-1, first Gram-Schmidt sweep
+    double *vv = V(inner + 1);
+    const int dim = inner + 1;
+    if (!Pinv) {
+      NSG_TRY(A(vv, V(inner), state));
+    } else {
+      NSG_TRY(A(p, V(inner), state));
+      NSG_TRY((*Pinv)(vv, p, state));
     }
-    for (int inner = 0; inner < m; ++inner) {
-      double *vv = V(inner + 1);
-      const int dim = inner + 1;
-      if (!Pinv) {
-        NSG_TRY(A(vv, V(inner), state));
-      } else {
-        NSG_TRY(A(p, V(inner), state));
-        NSG_TRY((*Pinv)(vv, p, state));
-      }
-      const bool consider = !re_orth && (inner % 5 == 4);
-      if (consider) NSG_TRY(dev_dot(c, n, vv + o, vv + o, &ctl->norm_start2, state));
-      NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h[0], state));
+    if (consider) NSG_TRY(dev_dot(c, n, vv + o, vv + o, &ctl->norm_start2, state));
+    NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h[0], state));
+    for (int i = 1; i < dim; ++i)
+      NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h[i], state));
+    NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h[dim - 1], -1.0, V(dim - 1) + o, vv + o, &ctl->nrm2, state));
+    return NSG_OK;
+  };
+  auto iter_back = [&](int inner, bool reorth_now) -> int {  // optional second sweep, Givens, scaling
+    double *vv = V(inner + 1);
+    const int dim = inner + 1;
+    if (reorth_now) {
+      NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h2[0], state));
       for (int i = 1; i < dim; ++i)
-        NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h[i], state));
-      NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h[dim - 1], -1.0, V(dim - 1) + o, vv + o, &ctl->nrm2, state));
-      bool reorth_now = re_orth;
-      if (consider) {
-        NSG_TRY(read_ctl_header(c, ctl, h_ctl));
-        if (h_ctl->state != 0) break;  // decided in an earlier step: everything since was skipped
-        const double nv = std::sqrt(h_ctl->nrm2), ns = std::sqrt(h_ctl->norm_start2);
-        if (!(nv > 10. * ns * std::sqrt(std::numeric_limits<double>::epsilon()))) re_orth = reorth_now = true;
-      }
-      if (reorth_now) {
-        NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h2[0], state));
-        for (int i = 1; i < dim; ++i)
-          NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h2[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h2[i], state));
-        NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h2[dim - 1], -1.0, V(dim - 1) + o, vv + o, &ctl->nrm2, state));
-      }
-      k_gmres_step<<<1, 1, 0, c->stream>>>(ctl, inner, reorth_now ? 1 : 0, hist);
-      NSG_LAUNCH_CHECK(c);
-      k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, vv + o, &ctl->inv_s, state);
-      NSG_LAUNCH_CHECK(c);
-      if (!lazy) {
-        NSG_TRY(read_ctl_header(c, ctl, h_ctl));
-        if (h_ctl->state != 0) break;
-      }
+        NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h2[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h2[i], state));
+      NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h2[dim - 1], -1.0, V(dim - 1) + o, vv + o, &ctl->nrm2, state));
     }
-    // x += sum_i y_i v_i with y from the back-substitution of the rotated Hessenberg matrix
+    k_gmres_step<<<1, 1, 0, c->stream>>>(ctl, inner, reorth_now ? 1 : 0, hist);
+    NSG_LAUNCH_CHECK(c);
+    k_scale_dev<<<vgrid, 256, 0, c->stream>>>(n, vv + o, &ctl->inv_s, state);
+    NSG_LAUNCH_CHECK(c);
+    return NSG_OK;
+  };
+  auto cycle_end = [&]() -> int {  // x += sum_i y_i v_i with y from the rotated Hessenberg matrix
     k_gmres_backsolve<<<1, 1, 0, c->stream>>>(ctl);
     NSG_LAUNCH_CHECK(c);
     k_multi_axpy<<<vgrid, 256, 0, c->stream>>>(n, x + o, basis + o, S, ctl->y, &ctl->dim);
     NSG_LAUNCH_CHECK(c);
+    return NSG_OK;
+  };
+  // after the consider-step test: true -> re-orthogonalise from now on
+  auto reorth_test = [&]() {
+    const double nv = std::sqrt(h_ctl->nrm2), ns = std::sqrt(h_ctl->norm_start2);
+    return !(nv > 10. * ns * std::sqrt(std::numeric_limits<double>::epsilon()));
+  };
+  // run `body` either directly or as a cached graph (captured on first use)
+  const bool use_graphs = lazy && c->use_graphs && c->n_ranks == 1;
+  auto run_segment = [&](int seg, const std::function<int()> &body) -> int {
+    if (!use_graphs || seg < 0) return body();
+    const GraphKey key{seg, n_tmp, n, o, x, b, basis, hist};
+    for (GraphEntry &e : c->graphs)
+      if (e.key == key) {
+        NSG_CUDA(cudaGraphLaunch(e.exec, c->stream));
+        c->launches += e.launches;
+        return NSG_OK;
+      }
+    const int64_t l0 = c->launches;
+    NSG_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+    if (rc != NSG_OK) return rc;
+    if (ce != cudaSuccess) return fail(NSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t ex = nullptr;
+    NSG_CUDA(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+    c->graphs.push_back(GraphEntry{key, ex, c->launches - l0});
+    NSG_CUDA(cudaGraphLaunch(ex, c->stream));
+    return NSG_OK;
+  };
+
+  while (true) {
+    if (lazy) {
+      // segments end right after the first sweep of every 5th step (where the host must compare the norms
+      // for the re-orthogonalisation test) and at the end of the cycle
+      int inner = 0, seg = 0;
+      bool pending = false;  // step `inner` has its first sweep done; Givens/scaling still to run
+      while (true) {
+        const int first = inner;
+        const bool pb = pending, at_start = (first == 0 && !pending), ro = re_orth;
+        int stop = pb ? first + 1 : first;                 // first step whose front this segment ends with
+        while (stop < m && (ro || stop % 5 != 4)) ++stop;  // no test any more once re-orthogonalisation is on
+        NSG_TRY(run_segment(ro ? -1 : seg, [&]() -> int {
+          if (at_start) NSG_TRY(cycle_start());
+          int i = first;
+          if (pb) {
+            NSG_TRY(iter_back(i, ro));
+            ++i;
+          }
+          for (; i < stop; ++i) {
+            NSG_TRY(iter_front(i, false));
+            NSG_TRY(iter_back(i, ro));
+          }
+          if (stop < m)
+            NSG_TRY(iter_front(stop, true));
+          else
+            NSG_TRY(cycle_end());
+          return NSG_OK;
+        }));
+        ++seg;
+        if (stop >= m) break;  // cycle complete, x updated
+        NSG_TRY(read_ctl_header(c, ctl, h_ctl));
+        if (h_ctl->state != 0) {  // decided in an earlier step: everything since was skipped
+          NSG_TRY(cycle_end());
+          break;
+        }
+        if (reorth_test()) re_orth = true;
+        inner = stop;
+        pending = true;
+      }
+    } else {
+      NSG_TRY(cycle_start());
+      NSG_TRY(read_ctl_header(c, ctl, h_ctl));
+      if (h_ctl->state != 0) break;
+      for (int inner = 0; inner < m; ++inner) {
+        const bool consider = !re_orth && (inner % 5 == 4);
+        NSG_TRY(iter_front(inner, consider));
+        NSG_TRY(read_ctl_header(c, ctl, h_ctl));
+        if (h_ctl->state != 0) break;
+        if (consider && reorth_test()) re_orth = true;
+        NSG_TRY(iter_back(inner, re_orth));
+        NSG_TRY(read_ctl_header(c, ctl, h_ctl));
+        if (h_ctl->state != 0) break;
+      }
+      NSG_TRY(cycle_end());
+    }
     NSG_TRY(read_ctl_header(c, ctl, h_ctl));
     if (h_ctl->state != 0) break;
   }

@@ -122,6 +122,12 @@ class DeviceProblem:
     def get_pm_values(self):
         return self._get(self._L.nsg_get_pm_values, self.pm_nnz)
 
+    def boundary_force(self, boundary_id):
+        """(drag, lift) on the body bounded by the faces with this boundary id (N3)."""
+        out = np.zeros(2)
+        nsg_check(self._L.nsg_boundary_force(self._h, int(boundary_id), out))
+        return out
+
     def spmv(self, x):
         x = np.ascontiguousarray(x, np.float64)
         y = np.zeros(self.n_own, np.float64)

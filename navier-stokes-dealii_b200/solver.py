@@ -217,6 +217,12 @@ class NavierStokesSolver:
         np.savez(os.path.join(self.prm.output_dir, f"{name}.rank{self.rank}.npz"), time=time, solution=sol,
                  l2g=self.part.l2g[: self.part.n_own], partitioning=self.rank)
 
+    # ---- N3: drag / lift on the cylinder (boundary id 13, cpp:368); not in the reference ----------------
+    def drag_lift(self, boundary_id=13, u_mean=1.0, diameter=0.1):
+        """Force (F_x, F_y) and the coefficients 2F/(rho U^2 D)."""
+        f = self.dev.boundary_force(boundary_id)
+        return f, 2.0 * f / (self.prm.rho * u_mean ** 2 * diameter)
+
     # ---- helpers ----------------------------------------------------------------------------------
     def gather_solution(self):
         """Owned solution entries scattered into a global-size vector (zeros elsewhere)."""

@@ -740,6 +740,61 @@ void orc_get_residual(void *h, double *o) { std::copy(((Ctx *)h)->R.begin(), ((C
 void orc_get_matrix_values(void *h, double *o) { std::copy(((Ctx *)h)->J.begin(), ((Ctx *)h)->J.end(), o); }
 void orc_get_pm_values(void *h, double *o) { std::copy(((Ctx *)h)->Mp.begin(), ((Ctx *)h)->Mp.end(), o); }
 
+// N3 (not in the reference, which has no drag/lift code): force of the fluid on the body
+// bounded by the faces with `boundary_id`,  F = -oint (rho nu grad(u) n - p n) ds  with n the outward
+// normal of the FLUID domain, integrated with the reference's own 3-point face rule
+// (QGaussSimplex<1>(3), cpp:52) and the reference's viscous form (grad u, not its symmetric part).
+void orc_boundary_force(void *h, int32_t boundary_id, double *out2) {
+  Ctx *c = (Ctx *)h;
+  const double gl[3] = {0.5 - 0.5 * std::sqrt(0.6), 0.5, 0.5 + 0.5 * std::sqrt(0.6)};
+  const double gw[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  const double ref[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+  double F[2] = {0, 0};
+  for (size_t i = 0; i < c->bf_cell.size(); ++i) {
+    if (c->bf_tag[i] != boundary_id) continue;
+    const int64_t cell = c->bf_cell[i];
+    const int f = c->bf_face[i];
+    const int32_t *v = &c->cv[3 * cell];
+    const int32_t *dof = &c->cd[15 * cell];
+    const double x0 = c->xy[2 * v[0]], y0 = c->xy[2 * v[0] + 1];
+    const double J00 = c->xy[2 * v[1]] - x0, J01 = c->xy[2 * v[2]] - x0;
+    const double J10 = c->xy[2 * v[1] + 1] - y0, J11 = c->xy[2 * v[2] + 1] - y0;
+    const double det = J00 * J11 - J01 * J10;
+    const double a00 = J11 / det, a01 = -J10 / det, a10 = -J01 / det, a11 = J00 / det;
+    const int va = f, vb = (f + 1) % 3;
+    const double ex = c->xy[2 * v[vb]] - c->xy[2 * v[va]], ey = c->xy[2 * v[vb] + 1] - c->xy[2 * v[va] + 1];
+    const double L = std::sqrt(ex * ex + ey * ey);
+    const double sgn = det > 0 ? 1.0 : -1.0;
+    const double n[2] = {sgn * ey / L, -sgn * ex / L};
+    double fx = 0, fy = 0;
+    for (int q = 0; q < 3; ++q) {
+      const double s = gl[q];
+      const double xr = ref[va][0] + s * (ref[vb][0] - ref[va][0]), yr = ref[va][1] + s * (ref[vb][1] - ref[va][1]);
+      double ps[6], dps[6][2];
+      p2_eval(xr, yr, ps, dps);
+      double G[2][2] = {{0, 0}, {0, 0}};
+      for (int k = 0; k < 6; ++k) {
+        const double gx = a00 * dps[k][0] + a01 * dps[k][1], gy = a10 * dps[k][0] + a11 * dps[k][1];
+        const int i0 = k < 3 ? 3 * k : 9 + 2 * (k - 3);
+        for (int a = 0; a < 2; ++a) {
+          G[a][0] += c->sol[dof[i0 + a]] * gx;
+          G[a][1] += c->sol[dof[i0 + a]] * gy;
+        }
+      }
+      const double lam[3] = {1 - xr - yr, xr, yr};
+      double P = 0;
+      for (int m = 0; m < 3; ++m) P += c->sol[dof[3 * m + 2]] * lam[m];
+      const double w = L * gw[q];
+      const double mu = c->prm.rho * c->prm.nu;
+      fx += w * (mu * (G[0][0] * n[0] + G[0][1] * n[1]) - P * n[0]);
+      fy += w * (mu * (G[1][0] * n[0] + G[1][1] * n[1]) - P * n[1]);
+    }
+    F[0] -= fx;
+    F[1] -= fy;
+  }
+  out2[0] = F[0], out2[1] = F[1];
+}
+
 // ILU(0) apply on the velocity block, exposed for the K7 parity tests.
 void orc_ilu_apply(void *h, int which, const double *x, double *y) {
   Ctx *c = (Ctx *)h;

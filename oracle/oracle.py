@@ -41,6 +41,7 @@ def lib():
                   "orc_get_residual", "orc_get_matrix_values", "orc_get_pm_values"):
             getattr(L, n).argtypes = [vp, f64p]
         L.orc_ilu_apply.argtypes = [vp, C.c_int, f64p, f64p]
+        L.orc_boundary_force.argtypes = [vp, i32, f64p]
         L.orc_quadrature.argtypes = [f64p, f64p, f64p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
@@ -136,6 +137,11 @@ class Oracle:
 
     def get_pm_values(self):
         return self._get(self._L.orc_get_pm_values, self.pm_nnz)
+
+    def boundary_force(self, boundary_id):
+        out = np.zeros(2)
+        self._L.orc_boundary_force(self._h, int(boundary_id), out)
+        return out
 
     def ilu_apply(self, which, x):
         x = np.ascontiguousarray(x, np.float64)

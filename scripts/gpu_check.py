@@ -36,7 +36,15 @@ print("R/bc rel", rel(dev.get_residual(), o.get_residual()))
 print("norm", dev.residual_norm(), o.residual_norm())
 x = np.random.default_rng(0).standard_normal(d.n)
 print("spmv rel", rel(dev.spmv(x), o.spmv(x)))
-t = time.time(); r1 = dev.solve(0, 1e-2, 100000, 30, 0); t1 = time.time()-t
+x0 = dev.get_delta()
+for g in (0, 1, 1):
+    dev.set_tuning(2, g); dev.set_delta(x0)
+x0 = dev.get_delta()
+for g in (0, 1, 1):
+    dev.set_tuning(2, g); dev.set_delta(x0)
+    t = time.time(); r1 = dev.solve(0, 1e-2, 100000, 30, 0); t1 = time.time()-t
+    print("graphs", g, "gmres", r1, "s", t1, "us/it", 1e6*t1/max(r1[0],1))
+    print("graphs", g, "gmres", r1, "s", t1, "us/it", 1e6*t1/max(r1[0],1))
 t = time.time(); r2 = o.solve(0, 1e-2, 100000, 30, 0); t2 = time.time()-t
 print("gmres dev", r1, t1, "oracle", r2, t2)
 print("delta rel", rel(dev.get_delta(), o.get_delta()))

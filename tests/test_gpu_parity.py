@@ -331,3 +331,35 @@ def test_stokes_path_parity(pkg):
     y = xy[:d.n_u:2, 1][on]
     np.testing.assert_allclose(out[0][1][:d.n_u:2][on], 6 * y * (1 - y), atol=1e-5)
     dev.close()
+
+
+def test_drag_lift_parity(pkg):
+    """N3: boundary force functional on the cylinder (id 13) — device vs oracle vs closed forms."""
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy")
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    xy = d.support_points()
+    sol = analytic_state(d, 0.3)
+    for obj in (dev, o):
+        obj.set_params(nu=0.01, rho=1.2)
+        obj.set_solution(sol)
+    fd, fo = dev.boundary_force(13), o.boundary_force(13)
+    assert np.abs(fd - fo).max() <= 1e-12 * np.abs(fo).max()
+    assert np.array_equal(dev.boundary_force(13), fd)          # deterministic
+    # u = 0, p = x: F = -oint(-p n_fluid) = -area_of_polygon * e_x  (divergence theorem on the polygonal hole)
+    sol2 = np.zeros(d.n)
+    sol2[d.n_u:] = xy[d.n_u:, 0]
+    dev.set_solution(sol2)
+    c, f, t = m.boundary_faces()
+    cyl = t == 13
+    cells, X = m.cells, m.xy
+    a = X[cells[c[cyl], f[cyl]]]
+    b = X[cells[c[cyl], (f[cyl] + 1) % 3]]
+    area = 0.5 * abs(np.sum(a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]))
+    F = dev.boundary_force(13)
+    assert abs(F[0] + area) <= 1e-12 * area and abs(F[1]) <= 1e-12 * area
+    assert abs(area - np.pi * 0.25) < 0.02
+    # a constant pressure exerts no net force on a closed body
+    sol2[d.n_u:] = 10.0
+    dev.set_solution(sol2)
+    assert np.abs(dev.boundary_force(13)).max() <= 1e-12
+    dev.close()
