@@ -293,6 +293,8 @@ def main():
     spmv_ms = dev.time_kernel(1, reps)
     spmv_bytes = 12 * nnz + 8 * n_cols + 8 * n_rows + 8 * (n_rows + 1)
     aad_ms = dev.time_kernel(2, reps)
+    g_its = int(its_seen[-1])
+    mgs_passes = sum(min(i % 28, 27) + 1 for i in range(g_its))   # add_and_dot launches of the MGS sweeps
     asm_k_ms = dev.time_kernel(0, reps)
     asm_bytes = (8 * nnz + 8 * part.nnz_pm + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
     traffic = None   # dram__bytes_read+write per launch of the same kernel on the same workload, from profiles/
@@ -304,10 +306,14 @@ def main():
     rl = {"bound": "hbm", "kernel": "k_spmv_vec8u<persistent> (SpMV variant 4: CSR, 8 lanes/row, prefetched row extents)",
           "achieved": spmv_bytes / spmv_ms / 1e6, "peak": hbm, "unit": "GB/s",
           "frac": spmv_bytes / spmv_ms / 1e6 / hbm, "traffic": traffic, "peak_source": hbm_src,
-          "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms}
+          "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
+          "launches_per_step": int(its_seen[-1]) + 2,
+          "share_of_step": (int(its_seen[-1]) + 2) * spmv_ms / t_step_ms}
     rl_other = {
         "k_add_and_dot": {"bound": "hbm", "achieved": 32 * n_rows / aad_ms / 1e6, "peak": hbm, "unit": "GB/s",
-                          "frac": 32 * n_rows / aad_ms / 1e6 / hbm, "ms_per_launch": aad_ms},
+                          "frac": 32 * n_rows / aad_ms / 1e6 / hbm, "ms_per_launch": aad_ms,
+                          "launches_per_step": int(mgs_passes), "share_of_step": mgs_passes * aad_ms / t_step_ms,
+                          "note": "modified Gram-Schmidt chain: the largest share of a step; 32 B/DoF per pass"},
         "assembly(k_assemble_u+k_assemble_p+k_neumann)": {
             "bound": "hbm", "achieved": asm_bytes / asm_k_ms / 1e6, "peak": hbm, "unit": "GB/s",
             "frac": asm_bytes / asm_k_ms / 1e6 / hbm, "ms_per_launch": asm_k_ms, "algorithmic_bytes_per_launch": asm_bytes,

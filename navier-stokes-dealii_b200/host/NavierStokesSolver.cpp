@@ -206,11 +206,18 @@ void NavierStokesSolver::dirichlet(bool stokes, std::vector<int32_t> &ldofs, std
   std::vector<double> gv(n > 0 ? n : 1);
   NST_CALL(nst_dirichlet_values(mesh, dofs, 2, call_ptr.data(), ids.data(), is_inlet.data(), &ip, &n, gd.data(), gv.data()));
   ldofs.clear(), lvals.clear();
+  // NS_INCREMENT_BC=consistent imposes g - u^k on the Newton increment; the default reproduces the reference,
+  // which imposes the full g on every increment (cpp:375-376; harmless as shipped because g == 0)
+  std::vector<double> cur;
+  if (!stokes && env_str("NS_INCREMENT_BC", "reference") == "consistent") cur = solution_owned_values();
   const int64_t nup = n_own - n_own_u;
   for (int64_t i = 0; i < n; ++i) {
     const int64_t gdof = gd[i];
     if (gdof < n_u_global) {
-      if (gdof >= u_lo && gdof < u_lo + n_own_u) ldofs.push_back((int32_t)(gdof - u_lo)), lvals.push_back(gv[i]);
+      if (gdof >= u_lo && gdof < u_lo + n_own_u) {
+        ldofs.push_back((int32_t)(gdof - u_lo));
+        lvals.push_back(cur.empty() ? gv[i] : gv[i] - cur[gdof - u_lo]);
+      }
     } else if (gdof - n_u_global >= p_lo && gdof - n_u_global < p_lo + nup)
       ldofs.push_back((int32_t)(n_own_u + gdof - n_u_global - p_lo)), lvals.push_back(gv[i]);
   }

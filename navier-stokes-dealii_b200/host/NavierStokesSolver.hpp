@@ -9,7 +9,7 @@
 // untouched:  NS_MESH, NS_SURFACE_ENTITY, NS_REFINE, NS_NU, NS_RHO, NS_P_OUT, NS_G, NS_U_M, NS_H,
 // NS_INLET_Y0, NS_INLET_TIME (frozen|live|constant), NS_NEUMANN_ID, NS_INLET_ID, NS_WALL_IDS ("12,13"),
 // NS_PRECONDITIONER (identity|block_diagonal|block_triangular), NS_STOKES_INIT, NS_OUTPUT_DIR,
-// NS_BOX_TAGS ("left,right,wall,other" geometric ids for untagged meshes).
+// NS_BOX_TAGS ("left,right,wall,other" geometric ids for untagged meshes), NS_INCREMENT_BC (reference|consistent).
 // Ranks: RANK / WORLD_SIZE / LOCAL_RANK (torchrun style) or OMPI_COMM_WORLD_*; the NCCL id travels
 // through the file NS_RENDEZVOUS (default /tmp/ns_nccl_id.<MASTER_PORT>).
 #ifndef NAVIER_STOKES_SOLVER_B200_HPP

@@ -41,6 +41,10 @@ class Parameters:
     inlet_id: int = 11                               # cpp:357
     wall_ids: tuple = (12, 13)                       # cpp:367-368
     clear_inlet_before_walls: bool = False           # cpp:364 has boundary_functions.clear() commented out
+    # The reference imposes the FULL boundary value g on every Newton increment (cpp:375-376), so with g != 0
+    # the boundary value of the iterate grows by g per Newton iteration (harmless as shipped: g == 0).
+    # "reference" reproduces that; "consistent" imposes g - u^k so that the iterate attains g.
+    increment_bc: str = "reference"
     use_mass: bool = True                            # implicit Euler terms, cpp:249-251,288-290
     newton_max_iters: int = 1000                     # cpp:593
     newton_tolerance: float = 1e-2                   # cpp:594
@@ -55,6 +59,7 @@ class Parameters:
     stokes_max_iters: int = 2000
     stokes_rel_tol: float = 1e-6
     output_dir: str = ""                             # "" = no files (cpp:681-728 writes XDMF/HDF5)
+    force_boundary_id: int = -1                      # >= 0: record drag/lift on this boundary after every time step (N3)
     extra: dict = field(default_factory=dict)
 
 
@@ -73,6 +78,7 @@ class NavierStokesSolver:
         self.verbose = verbose and rank == 0
         self.time = 0.0
         self.history = []        # (time_step, newton_iter, residual_norm, gmres_its)
+        self.force_history = []  # (time, F_x, F_y) when Parameters.force_boundary_id >= 0
 
     def pcout(self, *a, **k):
         if self.verbose:
@@ -125,7 +131,10 @@ class NavierStokesSolver:
         second = {} if (stokes or p.clear_inlet_before_walls) else {inlet_id: True}
         second.update({w: False for w in walls})
         gd, gv = self.dofs.dirichlet_values([{inlet_id: True}, second], self._inlet())
-        return self.part.localize_dirichlet(gd, gv)
+        ld, lv = self.part.localize_dirichlet(gd, gv)
+        if not stokes and p.increment_bc == "consistent" and len(ld):
+            lv = lv - self.dev.get_solution()[ld]
+        return ld, lv
 
     # ---- assemble_system (cpp:178-378) --------------------------------------------------------
     def assemble_system(self):
@@ -203,6 +212,9 @@ class NavierStokesSolver:
             self.dev.push_time_level()
             self.pcout(f"n = {time_step:3d}, t = {self.time:5f}")
             self.solve_newton(time_step)
+            if self.prm.force_boundary_id >= 0:
+                f = self.dev.boundary_force(self.prm.force_boundary_id)
+                self.force_history.append((self.time, float(f[0]), float(f[1])))
             self.output(time_step, self.time)
             self.pcout("")
 

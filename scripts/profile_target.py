@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module("navier-stokes-dealii_b200")
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-m, d, part, (ld, lv), neumann, sol = bench.build_problem(pkg, "cmy", L, 1, 0)
+MESH = sys.argv[2] if len(sys.argv) > 2 else "cmy"
+m, d, part, (ld, lv), neumann, sol = bench.build_problem(pkg, MESH, L, 1, 0)
 dev = pkg.DeviceProblem(part, 0)
 dev.set_params(neumann_id=neumann)
 dev.set_solution(sol); dev.set_solution_old(0.9 * sol)
