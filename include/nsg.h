@@ -160,6 +160,9 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * key 1 = assembly kernel variant: 0 (default) literal 7-point quadrature loop for every term, as the
  * reference sums them; 1 the same integrals with the quadrature sum factored into pre-integrated
  * reference-cell tables (0.45x the fp64 instructions, same speed: the kernel is latency-bound).
+ * key 3 = Gram-Schmidt variant of SolverGMRES: 0 (default) modified, the chain of add_and_dot that deal.II
+ * <= 9.4 runs; 1 classical (h = V^T w, w -= V h: two passes and two all-reduces per step
+ * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).
  * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 

@@ -392,6 +392,20 @@ static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr
   NSG_LAUNCH_CHECK(c);
   return allreduce_scalar(c, out);
 }
+// classical Gram-Schmidt building blocks (global over ranks)
+static int dev_multi_dot(nsg_ctx *c, int64_t n, const double *w, const double *basis, int k, double *out, const int32_t *state) {
+  k_multi_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, k, c->partials_k, c->ticket, out, state);
+  NSG_LAUNCH_CHECK(c);
+  if (c->n_ranks > 1) NSG_NCCL(nccl_api().AllReduce(out, out, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  return NSG_OK;
+}
+static int dev_multi_axpy_norm(nsg_ctx *c, int64_t n, double *w, const double *basis, const double *h, int k, double *out,
+                               const int32_t *state) {
+  k_multi_axpy_norm<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, h, k, c->partials, c->ticket, out, state);
+  NSG_LAUNCH_CHECK(c);
+  return allreduce_scalar(c, out);
+}
+
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
   NSG_TRY(halo_exchange(c, x_with_ghosts));
   if (c->spmv_variant == 2 && c->have_paired)
@@ -557,6 +571,7 @@ int nsg_create(int device, nsg_ctx **out) {
   cudaEventCreate(&c->ev1);
   int rc = upload_tables();
   if (rc == NSG_OK) rc = dev_alloc(&c->partials, RED_MAX_BLOCKS);
+  if (rc == NSG_OK) rc = dev_alloc(&c->partials_k, (int64_t)CGS_MAXK * RED_MAX_BLOCKS);
   if (rc == NSG_OK) rc = dev_alloc(&c->ticket, 4);
   if (rc == NSG_OK) rc = dev_alloc(&c->scal, 64);
   if (rc == NSG_OK) rc = dev_alloc(&c->ctl, 1);
@@ -587,7 +602,7 @@ void nsg_destroy(nsg_ctx *c) {
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
   dev_free(c->sol), dev_free(c->sol_old), dev_free(c->delta), dev_free(c->R), dev_free(c->basis), dev_free(c->work);
-  dev_free(c->partials), dev_free(c->ticket), dev_free(c->scal), dev_free(c->ctl), dev_free(c->hist);
+  dev_free(c->partials), dev_free(c->partials_k), dev_free(c->ticket), dev_free(c->scal), dev_free(c->ctl), dev_free(c->hist);
   dev_free(c->dir_dofs), dev_free(c->dir_vals), dev_free(c->send_idx), dev_free(c->recv_idx), dev_free(c->send_buf), dev_free(c->recv_buf);
   free_blocks(c);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1081,6 +1096,12 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       return NSG_OK;
     case 2:
       c->use_graphs = value != 0;
+      return NSG_OK;
+    case 3:
+      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "orthogonalization must be 0 (modified) or 1 (classical Gram-Schmidt)");
+      c->orthogonalization = value;
+      for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
+      c->graphs.clear();
       return NSG_OK;
     case 1:
       if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "assembly variant must be 0 (quadrature loop) or 1 (factored)");

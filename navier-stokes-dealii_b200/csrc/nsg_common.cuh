@@ -151,6 +151,7 @@ struct nsg_ctx {
   unsigned long long *first_idx = nullptr;
   int spmv_variant = 0, asm_variant = 0;
   bool use_graphs = true;
+  int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;
   nsg::GroupMeta *gmeta = nullptr;
   int32_t *row_perm = nullptr, *group_perm = nullptr;
@@ -173,7 +174,7 @@ struct nsg_ctx {
   int32_t basis_n_tmp = 0;
   double *work = nullptr;   // scratch vectors for the preconditioners (8 * stride)
   // reductions / control
-  double *partials = nullptr;
+  double *partials = nullptr, *partials_k = nullptr;
   unsigned int *ticket = nullptr;
   double *scal = nullptr;  // misc device scalars
   nsg::GmresCtl *ctl = nullptr, *h_ctl = nullptr;  // device / pinned host mirror

@@ -61,6 +61,7 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
   k_gmres_init<<<1, 1, 0, c->stream>>>(ctl, rel_tol, max_steps, n_tmp, hist_cap);
   NSG_LAUNCH_CHECK(c);
   bool re_orth = false;
+  const bool classical = c->orthogonalization == 1;
 
   // ---- the pieces of one restart cycle ----
   auto cycle_start = [&]() -> int {  // p = b - A x ; v0 = P^-1 p ; rho = ||v0|| ; v0 /= rho
@@ -88,6 +89,11 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
       NSG_TRY((*Pinv)(vv, p, state));
     }
     if (consider) NSG_TRY(dev_dot(c, n, vv + o, vv + o, &ctl->norm_start2, state));
+    if (classical && dim <= CGS_MAXK) {  // h = V^T vv ; vv -= V h ; ||vv||  (two passes over the basis)
+      NSG_TRY(dev_multi_dot(c, n, vv + o, basis + o, dim, &ctl->h[0], state));
+      NSG_TRY(dev_multi_axpy_norm(c, n, vv + o, basis + o, &ctl->h[0], dim, &ctl->nrm2, state));
+      return NSG_OK;
+    }
     NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h[0], state));
     for (int i = 1; i < dim; ++i)
       NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h[i], state));
@@ -97,7 +103,10 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
   auto iter_back = [&](int inner, bool reorth_now) -> int {  // optional second sweep, Givens, scaling
     double *vv = V(inner + 1);
     const int dim = inner + 1;
-    if (reorth_now) {
+    if (reorth_now && classical && dim <= CGS_MAXK) {
+      NSG_TRY(dev_multi_dot(c, n, vv + o, basis + o, dim, &ctl->h2[0], state));
+      NSG_TRY(dev_multi_axpy_norm(c, n, vv + o, basis + o, &ctl->h2[0], dim, &ctl->nrm2, state));
+    } else if (reorth_now) {
       NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h2[0], state));
       for (int i = 1; i < dim; ++i)
         NSG_TRY(dev_add_and_dot(c, n, vv + o, &ctl->h2[i - 1], -1.0, V(i - 1) + o, V(i) + o, &ctl->h2[i], state));

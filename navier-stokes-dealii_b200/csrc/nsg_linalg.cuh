@@ -504,6 +504,67 @@ k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const doub
   finish_reduce(acc, partials, ticket, out);
 }
 
+// ---- classical Gram-Schmidt sweep (tuning key 3): two passes over the basis instead of k dependent ones ----
+constexpr int CGS_MAXK = 32;
+// out[j] = w . v_j for j < k, one pass over w and the k basis vectors
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ basis, int64_t stride, int k,
+            double *partials /* [CGS_MAXK][gridDim.x] */, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  double acc[CGS_MAXK];
+#pragma unroll
+  for (int j = 0; j < CGS_MAXK; ++j) acc[j] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
+    const double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < CGS_MAXK; ++j)
+      if (j < k) acc[j] += wi * __ldcs(basis + j * stride + i);
+  }
+  __shared__ double s_part[RED_THREADS / 32][CGS_MAXK];
+  __shared__ bool s_last;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+#pragma unroll
+  for (int j = 0; j < CGS_MAXK; ++j) {
+    if (j < k) {
+      const double v = warp_sum(acc[j]);
+      if (lane == 0) s_part[wid][j] = v;
+    }
+  }
+  __syncthreads();
+  if (t < k) {
+    double v = 0.0;
+    for (int q = 0; q < RED_THREADS / 32; ++q) v += s_part[q][t];
+    partials[(int64_t)t * gridDim.x + blockIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (t < k) {
+      double v = 0.0;
+      for (unsigned g = 0; g < gridDim.x; ++g) v += __ldcg(partials + (int64_t)t * gridDim.x + g);  // index order
+      out[t] = v;
+    }
+    if (t == 0) *ticket = 0u;
+  }
+}
+// w -= sum_{j<k} h_j v_j (sequential in j per entry);  out = w . w
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_axpy_norm(int64_t n, double *__restrict__ w, const double *__restrict__ basis, int64_t stride, const double *__restrict__ h,
+                  int k, double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
+    double a = w[i];
+    for (int j = 0; j < k; ++j) a -= h[j] * __ldcs(basis + j * stride + i);
+    w[i] = a;
+    acc += a * a;
+  }
+  finish_reduce(acc, partials, ticket, out);
+}
+
 // v *= *sptr (skipped when the factor is not finite: lucky breakdown s == 0)
 __global__ void k_scale_dev(int64_t n, double *__restrict__ v, const double *__restrict__ sptr,
                             const int32_t *__restrict__ state) {

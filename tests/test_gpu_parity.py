@@ -363,3 +363,25 @@ def test_drag_lift_parity(pkg):
     dev.set_solution(sol2)
     assert np.abs(dev.boundary_force(13)).max() <= 1e-12
     dev.close()
+
+
+def test_classical_gram_schmidt_option(pkg):
+    """Tuning key 3: classical Gram-Schmidt (two passes per step) reaches the same solution as the default
+    modified sweep; identical in exact arithmetic, so the histories agree to rounding over a cycle."""
+    d, part, dev, o = _precond_system(pkg)
+    x0 = np.zeros(d.n)
+    res = {}
+    for orth in (0, 1):
+        dev.set_tuning(3, orth)
+        dev.set_delta(x0)
+        its, r, rc = dev.solve(0, 1e-8, 100000, 30, 0)
+        assert rc == 0
+        res[orth] = (its, dev.gmres_history(), dev.get_delta())
+    dev.set_tuning(3, 0)
+    assert abs(res[0][0] - res[1][0]) <= 2
+    assert np.abs(res[1][1][:28] / res[0][1][:28] - 1).max() <= 1e-8
+    assert np.abs(res[1][2] - res[0][2]).max() <= 1e-6 * np.abs(res[0][2]).max()
+    J = sp.csr_matrix((dev.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(d.n, d.n))
+    b = dev.get_residual()
+    assert np.linalg.norm(J @ res[1][2] - b) <= 1.5e-8 * np.linalg.norm(b)
+    dev.close()

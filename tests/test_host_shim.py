@@ -54,3 +54,17 @@ def test_app_matches_python_driver(pkg):
         assert (a["time_step"], a["newton"]) == (step, it)
         assert a["gmres"] == (-1 if its is None else its)
         assert a["residual"] == res          # same library, same device: bit-identical
+
+
+@pytest.mark.gpu
+def test_app_writes_output_files(tmp_path):
+    """N2: output() keeps the reference's one-file-per-step contract (cpp:681-728) with a minimal VTK writer."""
+    env = dict(os.environ, NS_MESH=mesh_path("square_h0.1.msh"), NS_T="0.1", NS_NEUMANN_ID="1", NS_INLET_ID="0",
+               NS_WALL_IDS="2,3", NS_OUTPUT_DIR=str(tmp_path))
+    r = subprocess.run([os.path.join(HOST, "ns_app")], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["output-0000.rank0.vtk", "output-0001.rank0.vtk", "output-0002.rank0.vtk"]
+    txt = open(os.path.join(tmp_path, files[-1])).read()
+    assert "CELLS 200 800" in txt and "VECTORS velocity double" in txt and "SCALARS pressure double 1" in txt
+    assert "SCALARS partitioning int 1" in txt
