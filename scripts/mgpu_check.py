@@ -72,7 +72,10 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
     rd = dev.solve(0, 1e-2, 100000, 30, 0, check=False)
     ro = o.solve(0, 1e-2, 100000, 30, 0)
     print(f"[rank {rank}] {name}: GMRES identity: device {rd} oracle {ro}", flush=True)
-    state["ok"] &= rd[2] == ro[2] and abs(rd[0] - ro[0]) <= max(2, 0.1 * ro[0])
+    good = rd[2] == ro[2] and abs(rd[0] - ro[0]) <= max(2, 0.1 * ro[0])
+    if not good:
+        print(f"[rank {rank}] {name}: GMRES identity step counts FAIL", flush=True)
+    state["ok"] &= good
     h1, h2 = dev.gmres_history(), o.gmres_history()
     k = min(28, len(h1), len(h2))
     check("GMRES history (first cycle)", h1[:k], h2[:k], 1e-9)
@@ -88,7 +91,10 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
         rd = dev.solve(precond, 1e-6, 2000, 30, 0, check=False)
         ro = o.solve(precond, 1e-6, 2000, 30, 0)
         print(f"[rank {rank}] {name}: GMRES precond {precond}: device {rd} oracle {ro}", flush=True)
-        state["ok"] &= rd[2] == ro[2] == 0 and rd[0] == ro[0]
+        good = rd[2] == ro[2] == 0 and rd[0] == ro[0]
+        if not good:
+            print(f"[rank {rank}] {name}: GMRES precond {precond} step counts FAIL", flush=True)
+        state["ok"] &= good
         check(f"delta precond {precond}", dev.get_delta(), o.get_delta()[own], 1e-6)
     dev.close()
 

@@ -18,4 +18,5 @@ def test_two_rank_parity():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "scripts", "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert "MGPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+    fails = [l for l in out.stdout.splitlines() if "FAIL" in l]
+    assert "MGPU_CHECK PASS" in out.stdout, "\n".join(fails) + out.stderr[-1500:]
