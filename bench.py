@@ -222,6 +222,7 @@ def main():
         uid = [pkg.DeviceProblem.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(rank, world, uid[0])
+        peer_ar = dev.enable_peer_allreduce(dist)
     dev.set_params(neumann_id=neumann)
     dev.set_solution(sol)
     dev.set_solution_old(0.9 * sol)
@@ -357,6 +358,8 @@ def main():
                 "assembly_ms": t_asm_ms, "gmres_ms_per_newton_step": t_sol_ms, "gmres_its": int(its_seen[-1]),
                 "gmres_ms_per_iteration": t_sol_ms / max(1, its_seen[-1]), "setup_s": t_setup,
                 "gmres_ms_per_newton_step_classical_gs": cgs_ms,
+                "krylov_allreduce": ("fused into the reduction kernels (NVLink peer mailboxes)" if world > 1 and peer_ar
+                                     else "nccl" if world > 1 else None),
                 "gpu_launches": int(c1["launches"] - c0["launches"]), "clocks": clocks, "roofline": rl,
                 "roofline_other": rl_other,
                 "e2e": {"value": N / e2e_asm_s / 1e6, "unit": "MDoF/s",

@@ -76,6 +76,13 @@ int nsg_set_halo(nsg_ctx *ctx, int32_t n_neighbors, const int32_t *neighbors, co
 int nsg_comm_unique_id(void *out128);
 int nsg_comm_init(nsg_ctx *ctx, int rank, int n_ranks, const void *unique_id128);
 
+/* Optional, after nsg_comm_init on every rank: fuse the scalar all-reduces of the Krylov inner products
+ * (MPI_Allreduce behind every dot/norm of SolverGMRES) into the reduction kernels as a one-shot
+ * exchange through NVLink peer memory. Each rank exports the CUDA-IPC handle of its mailbox (64 bytes), the
+ * host all-gathers them in rank order, nsg_comm_set_peers maps them. Without it NCCL does the all-reduce. */
+int nsg_comm_ipc_handle(nsg_ctx *ctx, void *out64);
+int nsg_comm_set_peers(nsg_ctx *ctx, const void *handles /* n_ranks x 64 bytes, rank order */);
+
 /* The compile-time constants of the reference as run-time parameters; defaults are the
  * reference's values (hpp:703-709 nu,rho,p_out; main.cpp:13 deltat; hpp:438 g=0; cpp:320 id 10). */
 typedef struct {

@@ -127,6 +127,8 @@ _NSG_SIGS = {
     "nsg_set_halo": (C.c_int, [vp, i32, i32p, i64p, i32p, i64p, i32p]),
     "nsg_comm_unique_id": (C.c_int, [C.c_char_p]),
     "nsg_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+    "nsg_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),
+    "nsg_comm_set_peers": (C.c_int, [vp, C.c_char_p]),
     "nsg_params_default": (None, [C.POINTER(NsgParams)]),
     "nsg_set_params": (C.c_int, [vp, C.POINTER(NsgParams)]),
     "nsg_assemble": (C.c_int, [vp]),

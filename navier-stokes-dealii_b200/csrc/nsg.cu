@@ -381,29 +381,32 @@ static int allreduce_scalar(nsg_ctx *c, double *d) {
 // -------------------------------------------------------------------------------------------------
 // vector-op wrappers (global over ranks)
 // -------------------------------------------------------------------------------------------------
+// With the peer mailboxes set up (nsg_comm_set_peers) the all-reduce is fused into the reduction kernel;
+// otherwise NCCL does it.
+static inline bool fused_ar(const nsg_ctx *c) { return c->peer.n_ranks > 1; }
 static int dev_dot(nsg_ctx *c, int64_t n, const double *a, const double *b, double *out, const int32_t *state) {
-  k_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, a, b, c->partials, c->ticket, out, state);
+  k_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, a, b, c->partials, c->ticket, out, state, c->peer);
   NSG_LAUNCH_CHECK(c);
-  return allreduce_scalar(c, out);
+  return fused_ar(c) ? NSG_OK : allreduce_scalar(c, out);
 }
 static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr, double sign, const double *V,
                            const double *W, double *out, const int32_t *state) {
-  k_add_and_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, vv, aptr, sign, V, W, c->partials, c->ticket, out, state);
+  k_add_and_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, vv, aptr, sign, V, W, c->partials, c->ticket, out, state, c->peer);
   NSG_LAUNCH_CHECK(c);
-  return allreduce_scalar(c, out);
+  return fused_ar(c) ? NSG_OK : allreduce_scalar(c, out);
 }
 // classical Gram-Schmidt building blocks (global over ranks)
 static int dev_multi_dot(nsg_ctx *c, int64_t n, const double *w, const double *basis, int k, double *out, const int32_t *state) {
-  k_multi_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, k, c->partials_k, c->ticket, out, state);
+  k_multi_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, k, c->partials_k, c->ticket, out, state, c->peer);
   NSG_LAUNCH_CHECK(c);
-  if (c->n_ranks > 1) NSG_NCCL(nccl_api().AllReduce(out, out, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->n_ranks > 1 && !fused_ar(c)) NSG_NCCL(nccl_api().AllReduce(out, out, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
   return NSG_OK;
 }
 static int dev_multi_axpy_norm(nsg_ctx *c, int64_t n, double *w, const double *basis, const double *h, int k, double *out,
                                const int32_t *state) {
-  k_multi_axpy_norm<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, h, k, c->partials, c->ticket, out, state);
+  k_multi_axpy_norm<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, h, k, c->partials, c->ticket, out, state, c->peer);
   NSG_LAUNCH_CHECK(c);
-  return allreduce_scalar(c, out);
+  return fused_ar(c) ? NSG_OK : allreduce_scalar(c, out);
 }
 
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
@@ -561,6 +564,7 @@ int nsg_create(int device, nsg_ctx **out) {
   NSG_CUDA(cudaSetDevice(device));
   auto *c = new nsg_ctx;
   c->device = device;
+  c->peer.n_ranks = 1;
   nsg_params_default(&c->prm);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -595,6 +599,9 @@ void nsg_destroy(nsg_ctx *c) {
   cudaDeviceSynchronize();
   for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
   c->graphs.clear();
+  for (void *m : c->peer_mapped)
+    if (m) cudaIpcCloseMemHandle(m);
+  dev_free(c->mailbox), dev_free(c->ar_seq);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
@@ -814,6 +821,48 @@ int nsg_comm_init(nsg_ctx *c, int rank, int n_ranks, const void *unique_id128) {
   ncclUniqueId id;
   std::memcpy(&id, unique_id128, sizeof id);
   NSG_NCCL(nccl_api().CommInitRank(&c->comm, n_ranks, id, rank));
+  return NSG_OK;
+}
+
+int nsg_comm_ipc_handle(nsg_ctx *c, void *out64) {
+  if (!c || !out64) return fail(NSG_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  NSG_CUDA(cudaSetDevice(c->device));
+  if (!c->mailbox) {
+    NSG_TRY(dev_alloc(&c->mailbox, 2 * PEER_MAX_RANKS));
+    NSG_CUDA(cudaMemset(c->mailbox, 0, sizeof(PeerSlot) * 2 * PEER_MAX_RANKS));
+  }
+  cudaIpcMemHandle_t h;
+  NSG_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
+  std::memcpy(out64, &h, sizeof h);
+  return NSG_OK;
+}
+
+int nsg_comm_set_peers(nsg_ctx *c, const void *handles) {
+  if (!c || !handles) return fail(NSG_ERR_ARG, "null argument");
+  if (c->n_ranks <= 1) return NSG_OK;
+  if (c->n_ranks > PEER_MAX_RANKS) return fail(NSG_ERR_ARG, "more ranks than mailbox slots");
+  if (!c->mailbox) return fail(NSG_ERR_STATE, "nsg_comm_ipc_handle must be called first");
+  NSG_CUDA(cudaSetDevice(c->device));
+  PeerComm pc{};
+  pc.rank = c->rank;
+  for (int p = 0; p < c->n_ranks; ++p) {
+    if (p == c->rank) {
+      pc.box[p] = c->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)handles + 64 * (size_t)p, sizeof h);
+    void *ptr = nullptr;
+    NSG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_mapped[p] = ptr;
+    pc.box[p] = (PeerSlot *)ptr;
+  }
+  if (!c->ar_seq) NSG_TRY(dev_alloc(&c->ar_seq, 1));
+  NSG_CUDA(cudaMemset(c->ar_seq, 0, sizeof(unsigned long long)));
+  pc.seq_ctr = c->ar_seq;
+  pc.n_ranks = c->n_ranks;  // switches the reductions to the fused all-reduce
+  c->peer = pc;
   return NSG_OK;
 }
 

@@ -70,6 +70,28 @@ struct WorkList {
   int64_t max_stage = 0;         // max number of staged matrix entries of a chunk
 };
 
+// One-shot all-reduce over NVLink peer memory, fused into the tail of the reduction kernels.  Every rank
+// owns a mailbox (two parities x one slot per source rank) that all peers can write (CUDA IPC).  A
+// reduction with sequence number s: write my partial value(s) into slot [s&1][my rank] of EVERY rank's
+// mailbox, fence, publish s in the slot's flag; then wait until all P flags of my own mailbox show s and
+// add the P values in rank order - every rank gets the bit-identical sum, with no host or NCCL call on
+// the critical path of the k+1 dependent reductions of a GMRES step.  (Parity double-buffering is safe:
+// nobody can start s+2 before everybody has finished reading s.)
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_MAX_VALS = 32;
+struct PeerSlot {
+  double v[PEER_MAX_VALS];
+  unsigned long long seq;
+  unsigned long long pad[3];
+};
+static_assert(sizeof(PeerSlot) == 288, "PeerSlot layout");
+constexpr long long PEER_TIMEOUT_CYCLES = 60000000000ll;  // ~30 s at 1.9 GHz: bounded, so a lost peer cannot hang the GPU
+struct PeerComm {
+  PeerSlot *box[PEER_MAX_RANKS];  // box[p] = mailbox of rank p: [2][PEER_MAX_RANKS] slots
+  unsigned long long *seq_ctr;    // this rank's count of completed fused reductions (device memory)
+  int rank, n_ranks;
+};
+
 // Pair-compressed column index of the fixed CSR (SpMV variant 2).  Rows 2n,2n+1 of a velocity node
 // have the same column pattern and velocity columns come in pairs (2m,2m+1), so one stored index
 // serves up to 4 matrix entries.  A group = the two rows of a velocity node or one pressure row; its
@@ -194,6 +216,10 @@ struct nsg_ctx {
   int64_t n_send = 0, n_recv = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
+  nsg::PeerSlot *mailbox = nullptr;      // this rank's mailbox (peer-writable)
+  nsg::PeerComm peer{};                  // n_ranks <= 1 until nsg_comm_set_peers
+  unsigned long long *ar_seq = nullptr;  // device counter behind peer.seq_ctr
+  void *peer_mapped[nsg::PEER_MAX_RANKS] = {};
   // block preconditioner state
   nsg::CsrBlock blkA, blkM;
   bool have_blocks = false, blocks_stale = true;

@@ -419,9 +419,48 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// peer all-reduce of cnt (<= blockDim.x, <= PEER_MAX_VALS) values held in shared memory `sv`, executed by
+// the last block of a reduction; result left in sv (identical bits on every rank).  The sequence number
+// lives on the device (pc.seq_ctr) and advances only when a reduction really runs, so kernels skipped by
+// the solver's `state` early-exit (identically on every rank) do not break the parity double-buffering.
+__device__ __forceinline__ void peer_allreduce_block(const PeerComm &pc, double *sv, int cnt) {
+  const int t = threadIdx.x;
+  const unsigned long long seq = *(volatile unsigned long long *)pc.seq_ctr + 1ull;  // written below, after the barriers
+  const int par = (int)(seq & 1ull);
+  if (t < cnt)
+    for (int p = 0; p < pc.n_ranks; ++p) pc.box[p][par * PEER_MAX_RANKS + pc.rank].v[t] = sv[t];
+  __threadfence_system();
+  __syncthreads();
+  if (t < pc.n_ranks) {
+    volatile unsigned long long *flag = &pc.box[t][par * PEER_MAX_RANKS + pc.rank].seq;
+    *flag = seq;  // publish to rank t
+    // wait for rank t's contribution in my own mailbox
+    volatile unsigned long long *mine = &pc.box[pc.rank][par * PEER_MAX_RANKS + t].seq;
+    const long long t0 = clock64();
+    while (*mine != seq) {
+      __nanosleep(32);
+      if (clock64() - t0 > PEER_TIMEOUT_CYCLES) break;  // a peer is gone: the NaN below surfaces as a solver failure
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < cnt) {
+    const PeerSlot *my = pc.box[pc.rank] + par * PEER_MAX_RANKS;
+    double a = 0.0;
+    bool ok = true;
+    for (int q = 0; q < pc.n_ranks; ++q) {
+      ok &= (*(volatile const unsigned long long *)&my[q].seq == seq);
+      a += *(volatile const double *)&my[q].v[t];
+    }
+    sv[t] = ok ? a : nan("");
+  }
+  if (t == 0) *pc.seq_ctr = seq;
+  __syncthreads();
+}
+
 // block partial -> partials[], last block sums partials in index order -> *out
 __device__ __forceinline__ void finish_reduce(double v, double *__restrict__ partials, unsigned int *ticket,
-                                              double *__restrict__ out) {
+                                              double *__restrict__ out, const PeerComm &pc) {
   __shared__ double s_w[RED_THREADS / 32];
   __shared__ bool s_last;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -450,10 +489,13 @@ __device__ __forceinline__ void finish_reduce(double v, double *__restrict__ par
     if (wid == 0) {
       a = lane < RED_THREADS / 32 ? s_w[lane] : 0.0;
       a = warp_sum(a);
-      if (lane == 0) {
-        *out = a;
-        *ticket = 0u;
-      }
+      if (lane == 0) s_w[0] = a;
+    }
+    __syncthreads();
+    if (pc.n_ranks > 1) peer_allreduce_block(pc, s_w, 1);  // fused all-reduce over NVLink peer memory
+    if (t == 0) {
+      *out = s_w[0];
+      *ticket = 0u;
     }
   }
 }
@@ -461,7 +503,7 @@ __device__ __forceinline__ void finish_reduce(double v, double *__restrict__ par
 // out = a . b
 __global__ void __launch_bounds__(RED_THREADS)
 k_dot(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *partials, unsigned int *ticket,
-      double *out, const int32_t *__restrict__ state) {
+      double *out, const int32_t *__restrict__ state, const PeerComm pc) {
   if (state && *state != 0) return;
   double acc = 0.0;
   const int64_t n2 = n >> 1;
@@ -472,13 +514,13 @@ k_dot(int64_t n, const double *__restrict__ a, const double *__restrict__ b, dou
     acc += x.y * y.y;
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc += a[n - 1] * b[n - 1];
-  finish_reduce(acc, partials, ticket, out);
+  finish_reduce(acc, partials, ticket, out, pc);
 }
 
 // vv += (sign * *aptr) * V ; out = vv . W   (W may alias vv)  — Vector::add_and_dot of the MGS sweep
 __global__ void __launch_bounds__(RED_THREADS)
 k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const double *__restrict__ V, const double *W,
-              double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+              double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state, const PeerComm pc) {
   if (state && *state != 0) return;
   const double a = sign * (*aptr);
   const bool self = (W == vv);
@@ -501,7 +543,7 @@ k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const doub
     vv[n - 1] = x;
     acc += x * (self ? x : W[n - 1]);
   }
-  finish_reduce(acc, partials, ticket, out);
+  finish_reduce(acc, partials, ticket, out, pc);
 }
 
 // ---- classical Gram-Schmidt sweep (tuning key 3): two passes over the basis instead of k dependent ones ----
@@ -509,7 +551,8 @@ constexpr int CGS_MAXK = 32;
 // out[j] = w . v_j for j < k, one pass over w and the k basis vectors
 __global__ void __launch_bounds__(RED_THREADS)
 k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ basis, int64_t stride, int k,
-            double *partials /* [CGS_MAXK][gridDim.x] */, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+            double *partials /* [CGS_MAXK][gridDim.x] */, unsigned int *ticket, double *out, const int32_t *__restrict__ state,
+            const PeerComm pc) {
   if (state && *state != 0) return;
   double acc[CGS_MAXK];
 #pragma unroll
@@ -542,18 +585,22 @@ k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ 
   __syncthreads();
   if (s_last) {
     __threadfence();
+    __shared__ double s_tot[CGS_MAXK];
     if (t < k) {
       double v = 0.0;
       for (unsigned g = 0; g < gridDim.x; ++g) v += __ldcg(partials + (int64_t)t * gridDim.x + g);  // index order
-      out[t] = v;
+      s_tot[t] = v;
     }
+    __syncthreads();
+    if (pc.n_ranks > 1) peer_allreduce_block(pc, s_tot, k);
+    if (t < k) out[t] = s_tot[t];
     if (t == 0) *ticket = 0u;
   }
 }
 // w -= sum_{j<k} h_j v_j (sequential in j per entry);  out = w . w
 __global__ void __launch_bounds__(RED_THREADS)
 k_multi_axpy_norm(int64_t n, double *__restrict__ w, const double *__restrict__ basis, int64_t stride, const double *__restrict__ h,
-                  int k, double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state) {
+                  int k, double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state, const PeerComm pc) {
   if (state && *state != 0) return;
   double acc = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
@@ -562,7 +609,7 @@ k_multi_axpy_norm(int64_t n, double *__restrict__ w, const double *__restrict__ 
     w[i] = a;
     acc += a * a;
   }
-  finish_reduce(acc, partials, ticket, out);
+  finish_reduce(acc, partials, ticket, out, pc);
 }
 
 // v *= *sptr (skipped when the factor is not finite: lucky breakdown s == 0)

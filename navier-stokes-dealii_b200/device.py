@@ -42,6 +42,28 @@ class DeviceProblem:
         nsg_check(self._L.nsg_set_halo(self._h, p.n_neighbors, _nz(p.neighbors), p.send_ptr, _nz(p.send_idx), p.recv_ptr,
                                        _nz(p.recv_idx)))
 
+    def comm_ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        nsg_check(self._L.nsg_comm_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def comm_set_peers(self, handles):
+        """handles: list of the 64-byte IPC handles of all ranks in rank order (fused NVLink all-reduce)."""
+        blob = b"".join(handles)
+        nsg_check(self._L.nsg_comm_set_peers(self._h, C.create_string_buffer(blob, len(blob))))
+
+    def enable_peer_allreduce(self, dist):
+        """All ranks: exchange the mailbox handles over torch.distributed and switch the Krylov inner products to
+        the all-reduce fused into the reduction kernels (NVLink peer memory).  NSG_NO_PEER_AR=1 keeps NCCL."""
+        import os
+        if os.environ.get("NSG_NO_PEER_AR", "0") == "1" or dist.get_world_size() <= 1:
+            return False
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, self.comm_ipc_handle())
+        self.comm_set_peers(handles)
+        dist.barrier()
+        return True
+
     # -- parameters -----------------------------------------------------------------------------
     def set_params(self, **kw):
         for k, v in kw.items():

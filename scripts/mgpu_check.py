@@ -26,6 +26,8 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
     part = pkg.Part(d, rank)
     dev = pkg.DeviceProblem(part, local)
     dev.comm_init(rank, world, uid)
+    if dev.enable_peer_allreduce(dist) and rank == 0:
+        print(f"{name}: Krylov all-reduces fused into the reduction kernels (NVLink peer mailboxes)", flush=True)
     own = part.l2g[: part.n_own]
     gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
     ld, lv = part.localize_dirichlet(gd, gv)
