@@ -164,9 +164,11 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * 2 paired CSR (pair-compressed column index); 3 = 1 with all loads of a row in flight; 4 = 3
  * persistent with prefetched row extents (default); 5 bulk-async-copy (TMA) stream; 6 = 2 in the
  * form of 4. Measured rates: profiles/.
- * key 1 = assembly kernel variant: 0 (default) literal 7-point quadrature loop for every term, as the
- * reference sums them; 1 the same integrals with the quadrature sum factored into pre-integrated
- * reference-cell tables (0.45x the fp64 instructions, same speed: the kernel is latency-bound).
+ * key 1 = assembly kernel variant: 0 literal 7-point quadrature loop for every term, as the reference sums
+ * them; 1 the same integrals with the quadrature sum factored into pre-integrated reference-cell tables;
+ * 2 = 1 on per-cell packets (everything that depends on the cell only is computed once per cell by a streaming
+ * pre-pass); 3 = 2 integrating the rows in two column halves; 4 (default) = 2 with one (owner, cell) pair per
+ * lane, lanes sorted by commit round, first-touch stores and a TMA bulk write-out. Measured: profiles/.
  * key 3 = Gram-Schmidt variant of SolverGMRES: 0 (default) modified, the chain of add_and_dot that deal.II
  * <= 9.4 runs; 1 classical (h = V^T w, w -= V h: two passes and two all-reduces per step
  * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).

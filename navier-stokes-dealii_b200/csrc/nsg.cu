@@ -155,6 +155,12 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
   // lanes of ONE warp (an owner never straddles a warp: pad to the next warp instead), so the ordered
   // commit of an owner's pairs needs only __syncwarp(), never a CTA barrier.
   auto nslots = [&](int64_t g) { return std::max((int)((gptr[g + 1] - gptr[g] + ASM_PPT - 1) / ASM_PPT), 1); };
+  // staged entries (shared-memory image) of owner g; a cap on the image keeps more CTAs resident per SM
+  auto stage_of = [&](int64_t g) -> int64_t {
+    if (kind == 0) return c->h_rowptr[2 * g + 2] - c->h_rowptr[2 * g] + 2;
+    return (c->h_rowptr[nu + g + 1] - c->h_rowptr[nu + g]) + (c->h_pm_rowptr[nu + g + 1] - c->h_pm_rowptr[nu + g]);
+  };
+  const int64_t stage_cap = std::getenv("NSG_ASM_STAGE_CAP") ? std::atoll(std::getenv("NSG_ASM_STAGE_CAP")) : ASM_STAGE_CAP;
   std::vector<ChunkInfo> chunks;
   {
     int64_t g = 0, rec = 0;
@@ -162,12 +168,15 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
       ChunkInfo ci{};
       ci.g0 = (int32_t)g;
       int nt = 0, mx = 0;
+      int64_t staged = 0;
       while (g < ng && g - ci.g0 < 255) {
         const int ns = nslots(g);
         if (ns > 32) return fail(NSG_ERR_ARG, "a vertex has too many incident cells (more than 64)");
         int pos = nt;
         if ((pos & 31) + ns > 32) pos = (pos + 31) & ~31;  // next warp
         if (pos + ns > NPC) break;
+        if (g > ci.g0 && staged + stage_of(g) > stage_cap) break;
+        staged += stage_of(g);
         nt = pos + ns;
         mx = std::max(mx, ns);
         ++g;
@@ -176,6 +185,13 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
       ci.n_threads = nt;
       ci.max_slots = mx;
       ci.rec_base = rec;
+      if (kind == 0) {
+        ci.rs = c->h_rowptr[2 * (int64_t)ci.g0];
+        ci.cnt = (int32_t)(c->h_rowptr[2 * (int64_t)ci.g1] - ci.rs);
+      } else {
+        ci.rs = c->h_rowptr[nu + ci.g0], ci.ms = c->h_pm_rowptr[nu + ci.g0];
+        ci.cnt = (int32_t)(c->h_rowptr[nu + ci.g1] - ci.rs), ci.mcnt = (int32_t)(c->h_pm_rowptr[nu + ci.g1] - ci.ms);
+      }
       rec += (int64_t)nt * ASM_PPT;
       chunks.push_back(ci);
     }
@@ -183,6 +199,7 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
   const int64_t nchunks = (int64_t)chunks.size();
   const int64_t nrecs = nchunks ? chunks.back().rec_base + (int64_t)chunks.back().n_threads * ASM_PPT : 0;
   std::vector<uint16_t> tdesc((size_t)nchunks * NPC, 0xffff);  // 0xffff = padding lane
+  std::vector<uint2> tdesc3((size_t)nchunks * NPC, make_uint2(0u, 0xffffffffu));
   std::vector<PairRec> recs(nrecs);
   int bad = 0;
   int64_t max_stage = 0;
@@ -200,6 +217,13 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
       if ((t & 31) + ns > 32) t = (t + 31) & ~31;
       for (int r = 0; r < ns; ++r, ++t) {
         tdesc[b * NPC + t] = (uint16_t)((g - ci.g0) | (r << 8));
+        {
+          const int64_t row = kind == 0 ? 2 * g : nu + g;
+          const int64_t off = c->h_rowptr[row] - ci.rs, len = c->h_rowptr[row + 1] - c->h_rowptr[row];
+          const int64_t moff = kind == 0 ? 0 : c->h_pm_rowptr[row] - ci.ms;
+          if (off >= 65536 || moff >= 65536 || len >= 65536) bad++;
+          tdesc3[b * NPC + t] = make_uint2((uint32_t)(off | (moff << 16)), (uint32_t)(len | ((uint32_t)r << 16) | ((uint32_t)(g - ci.g0) << 24)));
+        }
         for (int j = 0; j < ASM_PPT; ++j) {
           const int64_t pi = r + (int64_t)j * ns;
           if (pi >= gptr[g + 1] - gptr[g]) continue;
@@ -253,17 +277,204 @@ static int build_worklist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out
   out->n_chunks = nchunks;
   out->n_pairs = npairs;
   out->n_recs = nrecs;
-  out->max_stage = max_stage;
+  out->max_stage = max_stage + 2;  // the 128-bit zero-fill may touch one padding element
   NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
   NSG_TRY(upload(c, &out->tdesc, tdesc.data(), (int64_t)tdesc.size()));
+  NSG_TRY(upload(c, &out->tdesc3, tdesc3.data(), (int64_t)tdesc3.size()));
   NSG_TRY(upload(c, &out->recs, recs.data(), nrecs));
   NSG_CUDA(cudaStreamSynchronize(c->stream));  // host vectors die here
+  return NSG_OK;
+}
+
+// Work list of assembly variant 4 (k_assemble_u5 / k_assemble_p5): ONE (owner, cell) pair per lane, the lanes
+// of a chunk sorted by (commit round, cell).  Round = rank of the cell among the owner's cells, so all lanes
+// of a warp commit together (full shared-memory wavefronts instead of 3 mostly idle rounds per warp) and
+// lanes that read the same cell packet sit next to each other (fewer L1 wavefronts per load).  The record
+// carries everything the lane needs: no descriptor array, no row-pointer loads.
+//   rec.k    = k | round << 3 | owner-in-chunk << 8 | first-touch bits of the 9 column groups << 16 | first-touch of R << 25
+//   rec.off  = [0..8] column offsets (as PairRec), [9] image offset of the owner's first row (pressure: J row),
+//              [10] row length (pressure: image offset of the pressure-mass row)
+static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out) {
+  const int64_t T = c->n_cells, nu = c->n_own_u, nown = c->n_own;
+  const int64_t ng = kind == 0 ? nu / 2 : c->n_own_p;
+  const int nk = kind == 0 ? 6 : 3;
+  auto group_of = [&](int64_t cell, int k) -> int64_t {
+    const int32_t d = cd[15 * cell + (kind == 0 ? uidx(k) : 3 * k + 2)];
+    if (kind == 0) return d < nu ? d / 2 : -1;
+    return (d >= nu && d < nown) ? d - nu : -1;
+  };
+  std::vector<int64_t> gptr(ng + 1, 0);
+  for (int64_t cell = 0; cell < T; ++cell)
+    for (int k = 0; k < nk; ++k) {
+      const int64_t g = group_of(cell, k);
+      if (g >= 0) gptr[g + 1]++;
+    }
+  for (int64_t g = 0; g < ng; ++g) gptr[g + 1] += gptr[g];
+  const int64_t npairs = gptr[ng];
+  std::vector<int32_t> pcell(npairs);
+  std::vector<uint8_t> pk(npairs);
+  {
+    std::vector<int64_t> pos(gptr.begin(), gptr.end() - 1);
+    for (int64_t cell = 0; cell < T; ++cell)  // ascending cell order per owner
+      for (int k = 0; k < nk; ++k) {
+        const int64_t g = group_of(cell, k);
+        if (g >= 0) {
+          pcell[pos[g]] = (int32_t)cell;
+          pk[pos[g]++] = (uint8_t)k;
+        }
+      }
+  }
+  auto stage_of = [&](int64_t g) -> int64_t {
+    if (kind == 0) return c->h_rowptr[2 * g + 2] - c->h_rowptr[2 * g] + 2;
+    return (c->h_rowptr[nu + g + 1] - c->h_rowptr[nu + g]) + (c->h_pm_rowptr[nu + g + 1] - c->h_pm_rowptr[nu + g]);
+  };
+  const int64_t stage_cap = std::getenv("NSG_ASM_STAGE_CAP") ? std::atoll(std::getenv("NSG_ASM_STAGE_CAP")) : ASM_STAGE_CAP;
+  std::vector<ChunkInfo> chunks;
+  {
+    int64_t g = 0, rec = 0;
+    while (g < ng) {
+      ChunkInfo ci{};
+      ci.g0 = (int32_t)g;
+      int nt = 0, mx = 0;
+      int64_t staged = 0;
+      while (g < ng && g - ci.g0 < 255) {
+        const int np = (int)(gptr[g + 1] - gptr[g]);
+        if (np > 31) return fail(NSG_ERR_ARG, "a vertex has too many incident cells (more than 31)");
+        if (nt + np > NPC && g > ci.g0) break;
+        if (g > ci.g0 && staged + stage_of(g) > stage_cap) break;
+        staged += stage_of(g);
+        nt += np;
+        mx = std::max(mx, np);
+        ++g;
+      }
+      ci.g1 = (int32_t)g;
+      ci.n_threads = nt;
+      ci.max_slots = mx;
+      ci.rec_base = rec;  // == chunk index * NPC: a lane finds its record without reading the chunk header
+      if (kind == 0) {
+        ci.rs = c->h_rowptr[2 * (int64_t)ci.g0];
+        ci.cnt = (int32_t)(c->h_rowptr[2 * (int64_t)ci.g1] - ci.rs);
+      } else {
+        ci.rs = c->h_rowptr[nu + ci.g0], ci.ms = c->h_pm_rowptr[nu + ci.g0];
+        ci.cnt = (int32_t)(c->h_rowptr[nu + ci.g1] - ci.rs), ci.mcnt = (int32_t)(c->h_pm_rowptr[nu + ci.g1] - ci.ms);
+      }
+      rec += NPC;
+      chunks.push_back(ci);
+    }
+  }
+  const int64_t nchunks = (int64_t)chunks.size();
+  PairRec no_work;
+  std::memset(&no_work, 0, sizeof no_work);
+  no_work.cell = -1;
+  std::vector<PairRec> recs((size_t)nchunks * NPC, no_work);
+  int bad = 0;
+  int64_t max_stage = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_stage) reduction(+ : bad)
+  for (int64_t b = 0; b < nchunks; ++b) {
+    ChunkInfo &ci = chunks[b];
+    struct Lane {
+      int32_t round, cell, k, gl;
+    };
+    std::vector<Lane> lanes;
+    lanes.reserve(NPC);
+    for (int64_t g = ci.g0; g < ci.g1; ++g)
+      for (int64_t pi = gptr[g]; pi < gptr[g + 1]; ++pi) lanes.push_back({(int32_t)(pi - gptr[g]), pcell[pi], pk[pi], (int32_t)(g - ci.g0)});
+    std::sort(lanes.begin(), lanes.end(), [](const Lane &a, const Lane &b2) {
+      if (a.round != b2.round) return a.round < b2.round;
+      if (a.cell != b2.cell) return a.cell < b2.cell;
+      return a.k < b2.k;
+    });
+    if ((int)lanes.size() != ci.n_threads || ci.n_threads > NPC) bad++;
+    // first-touch bookkeeping per image entry
+    const int64_t img = kind == 0 ? ci.cnt : (int64_t)ci.cnt + ci.mcnt;
+    std::vector<uint8_t> touched((size_t)img, 0), rtouched((size_t)(ci.g1 - ci.g0), 0);
+    int64_t n_touched = 0;
+    for (size_t t = 0; t < lanes.size(); ++t) {
+      const Lane &ln = lanes[t];
+      PairRec rcd;
+      std::memset(&rcd, 0, sizeof rcd);
+      rcd.cell = ln.cell;
+      const int64_t g = ci.g0 + ln.gl;
+      const int32_t *cdc = cd + 15 * (int64_t)ln.cell;
+      const int64_t row = kind == 0 ? 2 * g : nu + g;
+      const int64_t rs = c->h_rowptr[row], re = c->h_rowptr[row + 1];
+      const int64_t len = re - rs, roff = rs - ci.rs;
+      if (len >= 65535 || roff >= 65535) bad++;
+      if (kind == 0 && c->h_rowptr[row + 2] - re != len) bad++;
+      uint32_t first = 0;
+      const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
+      for (int l = 0; l < 6; ++l) {
+        const int32_t tgt = cdc[uidx(l)];
+        const int32_t *p = std::lower_bound(cb, ce, tgt);
+        if (p == ce || *p != tgt || p + 1 == ce || p[1] != tgt + 1) {
+          bad++;
+          continue;
+        }
+        rcd.off[l] = (uint16_t)(p - cb);
+        // lanes are visited in commit order (round-major), so "not yet touched" == first contribution
+        uint8_t &f = touched[(size_t)(roff + (p - cb))];
+        if (!f) {
+          first |= 1u << l;
+          f = 1;
+          n_touched += kind == 0 ? 4 : 2;
+          touched[(size_t)(roff + (p - cb) + 1)] = 1;
+          if (kind == 0) touched[(size_t)(roff + len + (p - cb))] = touched[(size_t)(roff + len + (p - cb) + 1)] = 1;
+        }
+      }
+      const int32_t *mb = cb, *me = ce;
+      int64_t moff = roff;
+      if (kind == 1) {
+        mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
+        me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+        moff = ci.cnt + (c->h_pm_rowptr[row] - ci.ms);
+        if (c->h_pm_rowptr[row] - ci.ms >= 65535) bad++;
+      }
+      for (int m = 0; m < 3; ++m) {
+        const int32_t tgt = cdc[3 * m + 2];
+        const int32_t *p = std::lower_bound(mb, me, tgt);
+        if (p == me || *p != tgt) {
+          bad++;
+          continue;
+        }
+        rcd.off[6 + m] = (uint16_t)(p - mb);
+        uint8_t &f = touched[(size_t)(moff + (p - mb))];
+        if (!f) {
+          first |= 1u << (6 + m);
+          f = 1;
+          n_touched += 1;
+          if (kind == 0) touched[(size_t)(roff + len + (p - mb))] = 1, n_touched += 1;
+        }
+      }
+      uint32_t rfirst = 0;
+      if (!rtouched[ln.gl]) rfirst = 1, rtouched[ln.gl] = 1;
+      rcd.k = (int32_t)((uint32_t)ln.k | ((uint32_t)ln.round << 3) | ((uint32_t)ln.gl << 8) | (first << 16) | (rfirst << 25));
+      rcd.off[9] = (uint16_t)roff;
+      rcd.off[10] = kind == 0 ? (uint16_t)len : (uint16_t)(c->h_pm_rowptr[row] - ci.ms);
+      recs[ci.rec_base + (int64_t)t] = rcd;
+    }
+    // an entry of the pattern no cell contributes to (a pattern wider than the mesh implies) must still be written: zero-fill
+    bool all_r = true;
+    for (uint8_t f : rtouched) all_r &= f != 0;
+    ci.pad = (n_touched == img && all_r) ? 0 : 1;
+    const int64_t stage = kind == 0 ? (int64_t)ci.cnt + 2 * (ci.g1 - ci.g0) : (int64_t)ci.cnt + ci.mcnt;
+    max_stage = std::max(max_stage, stage);
+  }
+  if (bad) return fail(NSG_ERR_ARG, "cell_dofs do not match the sparsity pattern (or a row has >= 65535 entries)");
+  out->n_groups = ng;
+  out->n_chunks = nchunks;
+  out->n_pairs = npairs;
+  out->n_recs = nchunks * NPC;
+  out->max_stage = max_stage + 2;
+  NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
+  NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
   return NSG_OK;
 }
 
 static void free_worklist(WorkList &w) {
   dev_free(w.chunks);
   dev_free(w.tdesc);
+  dev_free(w.tdesc3);
   dev_free(w.recs);
 }
 
@@ -454,7 +665,63 @@ static AsmParams asm_params(const nsg_ctx *c) {
 
 static int launch_assembly(nsg_ctx *c) {
   const AsmParams P = asm_params(c);
-  if (c->asm_variant == 1) {
+  if (c->asm_variant == 4) {
+    if (c->n_cells > 0) {
+      k_cell_packets<<<grid_for(c->n_cells, 128, 1 << 30), 128, 0, c->stream>>>(c->n_cells, c->geom, c->cell_dofs, c->sol, c->sol_old,
+                                                                                P, c->cellpk);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_u5.n_chunks > 0) {
+      const unsigned grid = (unsigned)c->wl_u5.n_chunks;
+      const size_t smem = sizeof(double) * (size_t)c->wl_u5.max_stage;
+      const int minb = std::getenv("NSG_ASM3_MINB") ? std::atoi(std::getenv("NSG_ASM3_MINB")) : 3;
+      // a CTA pulls the records and packets of the CTA that will follow it on its SM slot towards L2
+      const int pf = std::getenv("NSG_ASM_PF") ? std::atoi(std::getenv("NSG_ASM_PF")) : 0;  // measured: no gain (profiles/r01_summary.md)
+      if (minb <= 3)
+        k_assemble_u5<3><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+      else if (minb == 4)
+        k_assemble_u5<4><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+      else
+        k_assemble_u5<5><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_p5.n_chunks > 0) {
+      k_assemble_p5<<<(unsigned)c->wl_p5.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p5.max_stage, c->stream>>>(
+          c->wl_p5, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
+      NSG_LAUNCH_CHECK(c);
+    }
+  } else if (c->asm_variant >= 2) {
+    if (c->n_cells > 0) {
+      k_cell_packets<<<grid_for(c->n_cells, 128, 1 << 30), 128, 0, c->stream>>>(c->n_cells, c->geom, c->cell_dofs, c->sol, c->sol_old,
+                                                                                P, c->cellpk);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_u.n_chunks > 0) {
+      const unsigned grid = (unsigned)c->wl_u.n_chunks;
+      const size_t smem = sizeof(double) * (size_t)c->wl_u.max_stage;
+      // resident CTAs per SM the register allocation is sized for (env NSG_ASM3_MINB: 3, 4 or 5)
+      const int minb = std::getenv("NSG_ASM3_MINB") ? std::atoi(std::getenv("NSG_ASM3_MINB")) : 4;
+      if (c->asm_variant == 3) {
+        if (minb <= 3)
+          k_assemble_u4<3><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+        else if (minb == 4)
+          k_assemble_u4<4><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+        else
+          k_assemble_u4<5><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+      } else if (minb <= 3)
+        k_assemble_u3<3><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+      else if (minb == 4)
+        k_assemble_u3<4><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+      else
+        k_assemble_u3<5><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_p.n_chunks > 0) {
+      k_assemble_p3<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
+          c->wl_p, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
+      NSG_LAUNCH_CHECK(c);
+    }
+  } else if (c->asm_variant == 1) {
     if (c->wl_u.n_chunks > 0) {
       k_assemble_u2<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
           c->wl_u, c->rowptr, c->vals, c->R, c->geom, c->cell_dofs, c->sol, c->sol_old, P);
@@ -482,6 +749,42 @@ static int launch_assembly(nsg_ctx *c) {
                                                                         c->bnode_pos, c->bface_cell, c->bface_face, c->bface_tag,
                                                                         c->cell_vertices, c->xy, c->R, P);
     NSG_LAUNCH_CHECK(c);
+  }
+  return NSG_OK;
+}
+
+// Work lists of the assembly variants 0..3 (slot-based, two pairs per thread): built when one of them is first
+// selected, so the default path (variant 4) does not pay their host time and device memory.
+static int ensure_slot_worklists(nsg_ctx *c) {
+  if (c->wl_u.chunks || c->wl_p.chunks || !c->have_mesh) return NSG_OK;
+  std::vector<int32_t> cell_dofs_h((size_t)(15 * c->n_cells));
+  NSG_CUDA(cudaMemcpy(cell_dofs_h.data(), c->cell_dofs, sizeof(int32_t) * cell_dofs_h.size(), cudaMemcpyDeviceToHost));
+  const int32_t *cell_dofs = cell_dofs_h.data();
+  const bool fetch_cols = c->h_col.empty() && c->nnz > 0;  // nsg_set_mesh drops the host copy of the column indices
+  if (fetch_cols) {
+    c->h_col.resize((size_t)c->nnz), c->h_pm_col.resize((size_t)c->pm_nnz);
+    NSG_CUDA(cudaMemcpy(c->h_col.data(), c->col, sizeof(int32_t) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
+    NSG_CUDA(cudaMemcpy(c->h_pm_col.data(), c->pm_col, sizeof(int32_t) * (size_t)c->pm_nnz, cudaMemcpyDeviceToHost));
+  }
+  NSG_TRY(build_worklist(c, 0, cell_dofs, &c->wl_u));
+  NSG_TRY(build_worklist(c, 1, cell_dofs, &c->wl_p));
+  const size_t smem_u = 8 * (size_t)c->wl_u.max_stage, smem_p = 8 * (size_t)c->wl_p.max_stage;
+  if (smem_u > 200 * 1024 || smem_p > 200 * 1024)
+    return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  if (fetch_cols) {
+    c->h_col.clear(), c->h_col.shrink_to_fit();
+    c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
   }
   return NSG_OK;
 }
@@ -604,8 +907,8 @@ void nsg_destroy(nsg_ctx *c) {
   dev_free(c->mailbox), dev_free(c->ar_seq);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
-  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
-  free_worklist(c->wl_u), free_worklist(c->wl_p);
+  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  free_worklist(c->wl_u), free_worklist(c->wl_p), free_worklist(c->wl_u5), free_worklist(c->wl_p5);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
   dev_free(c->sol), dev_free(c->sol_old), dev_free(c->delta), dev_free(c->R), dev_free(c->basis), dev_free(c->work);
@@ -730,15 +1033,19 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     k_cell_geometry<<<grid_for(n_cells, 256, 1 << 30), 256, 0, c->stream>>>(n_cells, c->xy, c->cell_vertices, c->geom);
     NSG_LAUNCH_CHECK(c);
   }
-  NSG_TRY(build_worklist(c, 0, cell_dofs, &c->wl_u));
-  NSG_TRY(build_worklist(c, 1, cell_dofs, &c->wl_p));
-  const size_t smem_u = 8 * (size_t)c->wl_u.max_stage, smem_p = 8 * (size_t)c->wl_p.max_stage;
-  if (smem_u > 200 * 1024 || smem_p > 200 * 1024)
-    return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
+  // the work lists of the older assembly variants (0..3) are built on demand (nsg_set_tuning key 1)
+  NSG_TRY(dev_alloc(&c->cellpk, PK * n_cells + 2));
+  NSG_TRY(build_worklist5(c, 0, cell_dofs, &c->wl_u5));
+  NSG_TRY(build_worklist5(c, 1, cell_dofs, &c->wl_p5));
+  {
+    const size_t s5u = 8 * (size_t)c->wl_u5.max_stage, s5p = 8 * (size_t)c->wl_p5.max_stage;
+    if (s5u > 200 * 1024 || s5p > 200 * 1024)
+      return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
+    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+    NSG_CUDA(cudaFuncSetAttribute(k_assemble_p5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5p, 1024)));
+  }
   // Neumann: owned boundary P2 nodes -> (face, position on the face)
   {
     struct Ent {
@@ -776,6 +1083,7 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
   c->h_col.clear(), c->h_col.shrink_to_fit();
   c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
   c->have_mesh = true;
+  if (c->asm_variant < 4) NSG_TRY(ensure_slot_worklists(c));
   return NSG_OK;
 }
 
@@ -1153,7 +1461,8 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       c->graphs.clear();
       return NSG_OK;
     case 1:
-      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "assembly variant must be 0 (quadrature loop) or 1 (factored)");
+      if (value < 0 || value > 4) return fail(NSG_ERR_ARG, "assembly variant must be 0..4 (see nsg.h)");
+      if (value < 4) NSG_TRY(ensure_slot_worklists(c));
       c->asm_variant = value;
       return NSG_OK;
     default: return fail(NSG_ERR_ARG, "unknown tuning key");

@@ -617,6 +617,808 @@ k_assemble_p2(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ ro
   for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
 }
 
+// ---- variant 2 ("cell packets"): everything that depends on the cell only is computed ONCE per cell ---------
+// The row-owner kernels above redo the field interpolation of a cell in each of its 6 velocity pairs and walk
+// a chain of three dependent gathers (record -> cell_dofs -> solution) per pair.  Here a streaming pre-pass
+// (k_cell_packets, one thread per cell) gathers the nodal values once and stores, per cell, a 352-byte packet:
+//   [0..4]   J^-T (a00 a01 a10 a11) and d = |det J|            [5] unused
+//   [6..17]  rho d x (G0, Gx, Gy): the affine physical velocity gradient G(xi,eta) = G0 + Gx xi + Gy eta
+//   [18..31] u^k at the 7 quadrature points
+//   [32..43] the cell's local residual for its 6 velocity nodes (cpp:287-311), complete
+// so a pair reads ONE contiguous packet (two dependent loads instead of three, 128-bit loads instead of ~47
+// scalar gathers), needs no nodal values at all, and integrates its two rows with the factored tables.
+constexpr int PK = 44;  // doubles per cell packet
+
+__global__ void __launch_bounds__(128)
+k_cell_packets(int64_t T, const double *__restrict__ geom, const int32_t *__restrict__ cell_dofs, const double *__restrict__ sol,
+               const double *__restrict__ sol_old, const AsmParams P, double *__restrict__ cellpk) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2), a11 = __ldg(geom + 5 * c + 3),
+               d = __ldg(geom + 5 * c + 4);
+  const bool ns = !P.stokes;
+  const double nurho = P.nu * P.rho, rd = P.rho * d, vd = nurho * d;
+  double G0[2][2] = {{0, 0}, {0, 0}}, Gx[2][2] = {{0, 0}, {0, 0}}, Gy[2][2] = {{0, 0}, {0, 0}};
+  double Uq[7][2];
+  double res[6][2];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) Uq[q][0] = Uq[q][1] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) res[k][0] = res[k][1] = 0.0;
+  if (ns) {
+    const int32_t *cd = cell_dofs + 15 * c;
+    double u[6][2], pr[3];
+    int32_t dof[6];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      dof[l] = __ldg(cd + uidx(l));
+      u[l][0] = sol[dof[l]];
+      u[l][1] = sol[dof[l] + 1];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
+    double h0[2][2] = {{0, 0}, {0, 0}}, hx[2][2] = {{0, 0}, {0, 0}}, hy[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+    for (int l = 0; l < 6; ++l)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          h0[a][cc] += u[l][a] * c_fe2.ga[l][cc];
+          hx[a][cc] += u[l][a] * c_fe2.gb[l][cc];
+          hy[a][cc] += u[l][a] * c_fe2.gc[l][cc];
+        }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      G0[a][0] = a00 * h0[a][0] + a01 * h0[a][1], G0[a][1] = a10 * h0[a][0] + a11 * h0[a][1];
+      Gx[a][0] = a00 * hx[a][0] + a01 * hx[a][1], Gx[a][1] = a10 * hx[a][0] + a11 * hx[a][1];
+      Gy[a][0] = a00 * hy[a][0] + a01 * hy[a][1], Gy[a][1] = a10 * hy[a][0] + a11 * hy[a][1];
+    }
+    // convective residual: cr[k][a] = sum_q w psi_k (U . grad) u_a
+    double cr[6][2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cr[k][0] = cr[k][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      double U0 = 0, U1 = 0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        U0 += u[l][0] * c_fe.psi[q][l];
+        U1 += u[l][1] * c_fe.psi[q][l];
+      }
+      Uq[q][0] = U0, Uq[q][1] = U1;
+      const double g00 = G0[0][0] + Gx[0][0] * c_fe2.qx[q] + Gy[0][0] * c_fe2.qy[q];
+      const double g01 = G0[0][1] + Gx[0][1] * c_fe2.qx[q] + Gy[0][1] * c_fe2.qy[q];
+      const double g10 = G0[1][0] + Gx[1][0] * c_fe2.qx[q] + Gy[1][0] * c_fe2.qy[q];
+      const double g11 = G0[1][1] + Gx[1][1] * c_fe2.qx[q] + Gy[1][1] * c_fe2.qy[q];
+      const double t0 = c_fe.w[q] * (U0 * g00 + U1 * g10), t1 = c_fe.w[q] * (U0 * g01 + U1 * g11);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        cr[k][0] += c_fe.psi[q][k] * t0;
+        cr[k][1] += c_fe.psi[q][k] * t1;
+      }
+    }
+    const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
+    double du[6][2];
+    if (P.use_mass) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        du[l][0] = u[l][0] - sol_old[dof[l]];
+        du[l][1] = u[l][1] - sol_old[dof[l] + 1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double rv0 = 0, rv1 = 0, pb0 = 0, pb1 = 0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double Kkl = S00 * c_fe2.K00[k][l] + S01 * c_fe2.K01s[k][l] + S11 * c_fe2.K11[k][l];
+        rv0 += Kkl * u[l][0];
+        rv1 += Kkl * u[l][1];
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const double bh0 = c_fe2.Bh[k][m][0], bh1 = c_fe2.Bh[k][m][1];
+        pb0 += pr[m] * (a00 * bh0 + a01 * bh1);
+        pb1 += pr[m] * (a10 * bh0 + a11 * bh1);
+      }
+      double r0 = -vd * rv0 - rd * cr[k][0] + d * pb0, r1 = -vd * rv1 - rd * cr[k][1] + d * pb1;
+      if (P.use_mass) {
+        double t0 = 0, t1 = 0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          t0 += c_fe2.Mh[k][l] * du[l][0];
+          t1 += c_fe2.Mh[k][l] * du[l][1];
+        }
+        r0 -= P.rho * P.dt_inv * d * t0;
+        r1 -= P.rho * P.dt_inv * d * t1;
+      }
+      res[k][0] = r0, res[k][1] = r1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    res[k][0] += P.f0 * d * c_fe2.mh[k];
+    res[k][1] += P.f1 * d * c_fe2.mh[k];
+  }
+  double2 *o = reinterpret_cast<double2 *>(cellpk + PK * c);
+  o[0] = make_double2(a00, a01), o[1] = make_double2(a10, a11), o[2] = make_double2(d, 0.0);
+  o[3] = make_double2(rd * G0[0][0], rd * G0[0][1]), o[4] = make_double2(rd * G0[1][0], rd * G0[1][1]);
+  o[5] = make_double2(rd * Gx[0][0], rd * Gx[0][1]), o[6] = make_double2(rd * Gx[1][0], rd * Gx[1][1]);
+  o[7] = make_double2(rd * Gy[0][0], rd * Gy[0][1]), o[8] = make_double2(rd * Gy[1][0], rd * Gy[1][1]);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) o[9 + q] = make_double2(Uq[q][0], Uq[q][1]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o[16 + k] = make_double2(res[k][0], res[k][1]);
+}
+
+// row tables indexed by the owner's local index k, laid out for conflict-free 128-bit shared-memory reads
+struct __align__(16) KlTab {
+  double Mh, Mx, My, K00, K01s, K11;
+};
+constexpr int KL_STRIDE = 38;  // doubles per k row (6 x 6 entries + 2 pad): rows land on disjoint banks
+
+template <int MINB>
+__global__ void __launch_bounds__(NPC, MINB)
+k_assemble_u3(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
+              const AsmParams P) {
+  extern __shared__ __align__(16) double s_vals[];
+  __shared__ __align__(16) double s_kl[6 * KL_STRIDE];
+  __shared__ __align__(16) double s_Bh[6][3][2];
+  __shared__ double s_wpsi[7][6];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const ChunkInfo ci = wl.chunks[b];
+  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
+  uint4 ra[ASM_PPT], rb[ASM_PPT];
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
+    if (t < ci.n_threads) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
+      ra[j] = __ldcs(rp);
+      rb[j] = __ldcs(rp + 1);
+    }
+  }
+  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
+  double *s_res = s_vals + cnt;
+  for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
+  if (t < 36) {
+    const int k = t / 6, l = t % 6;
+    double *e = s_kl + k * KL_STRIDE + 6 * l;
+    e[0] = c_fe2.Mh[k][l], e[1] = c_fe2.Mx[k][l], e[2] = c_fe2.My[k][l];
+    e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
+    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
+  }
+  if (t >= 64 && t < 64 + 42) {
+    const int q = (t - 64) / 6, k = (t - 64) % 6;
+    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
+  }
+  __syncthreads();
+
+  const bool have = td.y != 0xffffffffu;
+  const int len = have ? (int)(td.y & 0xffffu) : 0, slot = have ? (int)((td.y >> 16) & 0xffu) : 0, gl = have ? (int)(td.y >> 24) : 0;
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
+  double *row0 = s_vals + (have ? (td.x & 0xffffu) : 0u), *row1 = row0 + len;
+  const bool ns = !P.stokes;
+  const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
+
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    const bool work = (int)ra[j].x >= 0;
+    double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
+    double res0 = 0.0, res1 = 0.0;
+    if (work) {
+      const int k = (int)ra[j].y;
+      const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(int)ra[j].x);
+      const double2 ga = __ldg(pk), gb = __ldg(pk + 1), gd = __ldg(pk + 2);
+      const double a00 = ga.x, a01 = ga.y, a10 = gb.x, a11 = gb.y, d = gd.x;
+      const double2 rk = __ldg(pk + 16 + k);
+      res0 = rk.x, res1 = rk.y;
+      double H[2][6][2];
+#pragma unroll
+      for (int l = 0; l < 6; ++l) H[0][l][0] = H[0][l][1] = H[1][l][0] = H[1][l][1] = 0.0;
+      double2 g0a = make_double2(0, 0), g0b = g0a, gxa = g0a, gxb = g0a, gya = g0a, gyb = g0a;
+      if (ns) {
+        g0a = __ldg(pk + 3), g0b = __ldg(pk + 4), gxa = __ldg(pk + 5), gxb = __ldg(pk + 6), gya = __ldg(pk + 7), gyb = __ldg(pk + 8);
+        // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l   (second Frechet term, cpp:265-269)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const double2 U = __ldg(pk + 9 + q);
+          const double wk = s_wpsi[q][k];
+          const double c0 = wk * U.x, c1 = wk * U.y;
+#pragma unroll
+          for (int l = 0; l < 6; ++l) {
+            H[0][l][0] += c0 * c_fe.dpsi[q][l][0];
+            H[0][l][1] += c0 * c_fe.dpsi[q][l][1];
+            H[1][l][0] += c1 * c_fe.dpsi[q][l][0];
+            H[1][l][1] += c1 * c_fe.dpsi[q][l][1];
+          }
+        }
+      }
+      const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
+      const double rd = P.rho * d, md = mdt * d, vd = nurho * d;
+      const double r00 = rd * a00, r01 = rd * a01, r10 = rd * a10, r11 = rd * a11;
+      const double *kl = s_kl + k * KL_STRIDE;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double2 e0 = *reinterpret_cast<const double2 *>(kl + 6 * l), e1 = *reinterpret_cast<const double2 *>(kl + 6 * l + 2),
+                      e2 = *reinterpret_cast<const double2 *>(kl + 6 * l + 4);
+        const double Mkl = e0.x, Mx = e0.y, My = e1.x;
+        const double Kkl = S00 * e1.y + S01 * e2.x + S11 * e2.y;  // (1/d) sum_q w g_k.g_l
+        const double D = md * Mkl + vd * Kkl;
+        // rho w G_ab psi_k psi_l (cpp:259-263) + rho w psi_k U_b (g_l)_a (cpp:265-269)
+        A00[l] = D + (g0a.x * Mkl + gxa.x * Mx + gya.x * My) + (r00 * H[0][l][0] + r01 * H[0][l][1]);
+        A01[l] = (g0a.y * Mkl + gxa.y * Mx + gya.y * My) + (r00 * H[1][l][0] + r01 * H[1][l][1]);
+        A10[l] = (g0b.x * Mkl + gxb.x * Mx + gyb.x * My) + (r10 * H[0][l][0] + r11 * H[0][l][1]);
+        A11[l] = D + (g0b.y * Mkl + gxb.y * Mx + gyb.y * My) + (r10 * H[1][l][0] + r11 * H[1][l][1]);
+      }
+      // B^T[(a,k),m] = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[k][m][0]);
+        B0[m] = -d * (a00 * bh.x + a01 * bh.y);
+        B1[m] = -d * (a10 * bh.x + a11 * bh.y);
+      }
+    }
+    // commit rounds: slot r of every owner adds its pair into the owner's rows, in cell order; all 15 entries
+    // of a row are loaded before any is written back (they are distinct, which the compiler cannot know)
+    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
+    for (int r = 0; r < wrounds; ++r) {
+      if (work && slot == r) {
+        int o[9];
+#pragma unroll
+        for (int l = 0; l < 9; ++l) o[l] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+        double x[15], y[15];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          x[2 * l] = row0[o[l]], x[2 * l + 1] = row0[o[l] + 1];
+          y[2 * l] = row1[o[l]], y[2 * l + 1] = row1[o[l] + 1];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) x[12 + m] = row0[o[6 + m]], y[12 + m] = row1[o[6 + m]];
+        const double e0 = s_res[2 * gl], e1 = s_res[2 * gl + 1];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          row0[o[l]] = x[2 * l] + A00[l], row0[o[l] + 1] = x[2 * l + 1] + A01[l];
+          row1[o[l]] = y[2 * l] + A10[l], row1[o[l] + 1] = y[2 * l + 1] + A11[l];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) row0[o[6 + m]] = x[12 + m] + B0[m], row1[o[6 + m]] = y[12 + m] + B1[m];
+        s_res[2 * gl] = e0 + res0, s_res[2 * gl + 1] = e1 + res1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  double *out = vals + ci.rs;
+  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
+}
+
+// pressure rows of variant 2: the factored integrals of k_assemble_p2 on the chain-free skeleton above
+__global__ void __launch_bounds__(NPC, 6)
+k_assemble_p3(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, double *__restrict__ pm_vals, double *__restrict__ R,
+              const double *__restrict__ geom, const AsmParams P) {
+  extern __shared__ __align__(16) double s_vals[];
+  __shared__ __align__(16) double s_Bh[3][6][2];  // [m][l][c]
+  __shared__ double s_Mp[3][3];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const ChunkInfo ci = wl.chunks[b];
+  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
+  uint4 ra[ASM_PPT], rb[ASM_PPT];
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
+    if (t < ci.n_threads) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
+      ra[j] = __ldcs(rp);
+      rb[j] = __ldcs(rp + 1);
+    }
+  }
+  const int cnt = ci.cnt, mcnt = ci.mcnt, ng = ci.g1 - ci.g0;
+  double *s_pm = s_vals + cnt;
+  for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
+  if (t < 36) {
+    const int l = t / 6, m = (t % 6) / 2, cc = t % 2;
+    s_Bh[m][l][cc] = c_fe2.Bh[l][m][cc];
+  }
+  if (t >= 64 && t < 73) (&s_Mp[0][0])[t - 64] = (&c_fe2.Mp[0][0])[t - 64];
+  __syncthreads();
+  const bool have = td.y != 0xffffffffu;
+  const int slot = have ? (int)((td.y >> 16) & 0xffu) : 0;
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
+  double *row = s_vals + (have ? (td.x & 0xffffu) : 0u);
+  double *mrow = s_pm + (have ? (td.x >> 16) : 0u);
+  const double inv_nu = 1.0 / P.nu;
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    const bool work = (int)ra[j].x >= 0;
+    double Bx[6], By[6], M[3];
+    if (work) {
+      const int64_t c = (int)ra[j].x;
+      const int m = (int)ra[j].y;
+      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
+                   a11 = __ldg(geom + 5 * c + 3), d = __ldg(geom + 5 * c + 4);
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[m][l][0]);
+        Bx[l] = -d * (a00 * bh.x + a01 * bh.y);
+        By[l] = -d * (a10 * bh.x + a11 * bh.y);
+      }
+#pragma unroll
+      for (int n = 0; n < 3; ++n) M[n] = s_Mp[m][n] * inv_nu * d;
+    }
+    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
+    for (int r = 0; r < wrounds; ++r) {
+      if (work && slot == r) {
+        int o[9];
+#pragma unroll
+        for (int l = 0; l < 9; ++l) o[l] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+        double x[12], y[3];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) x[2 * l] = row[o[l]], x[2 * l + 1] = row[o[l] + 1];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) y[n] = mrow[o[6 + n]];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) row[o[l]] = x[2 * l] + Bx[l], row[o[l] + 1] = x[2 * l + 1] + By[l];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) mrow[o[6 + n]] = y[n] + M[n];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  double *out = vals + ci.rs, *mout = pm_vals + ci.ms;
+  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+  for (int i = t; i < mcnt; i += NPC) __stcs(mout + i, s_pm[i]);
+  // no statement of the reference tests the pressure space: R_p == 0
+  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
+}
+
+// ---- variant 3: variant 2 restructured for latency ----------------------------------------------------------
+// ncu on k_assemble_u3 (profiles/r01_asm_variants.md): 3 warps per scheduler (162 registers), issue slots 25 %
+// used; stall samples: 30 % waiting for the packet loads, 31 % in the commit rounds, 16 % zero-fill and
+// write-out.  Changes: (1) the two rows are integrated in two column halves (l = 0..2, then 3..5), so only 12
+// accumulators of H and 12 of A are live at a time; (2) the first pair's geometry is requested BEFORE the image
+// is zero-filled and the second pair's packet is prefetched into L2 meanwhile; (3) zero-fill with 128-bit
+// stores, write-out by ONE bulk async copy (TMA, shared -> global) per chunk instead of a store loop.
+__device__ __forceinline__ double2 ldg_v2_volatile(const double2 *p) {  // not CSE'd: a re-load is cheaper than 4 live registers
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// whole-image write-out: one elected thread hands the copy to the TMA engine and waits until the engine has
+// READ the shared memory (the CTA may then retire; the global writes complete asynchronously)
+__device__ __forceinline__ void bulk_store_image(double *dst, const double *src_smem, uint32_t bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr_u32(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(NPC, MINB)
+k_assemble_u4(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
+              const AsmParams P) {
+  extern __shared__ __align__(16) double s_vals[];
+  __shared__ __align__(16) double s_kl[6 * KL_STRIDE];
+  __shared__ __align__(16) double s_Bh[6][3][2];
+  __shared__ double s_wpsi[7][6];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const ChunkInfo ci = wl.chunks[b];
+  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
+  uint4 ra[ASM_PPT], rb[ASM_PPT];
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
+    if (t < ci.n_threads) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
+      ra[j] = __ldcs(rp);
+      rb[j] = __ldcs(rp + 1);
+    }
+  }
+  // request the first pair's geometry now; pull the later pairs' packets towards L2 while the image is prepared
+  double2 hd0 = make_double2(0, 0), hd1 = hd0, hd2 = hd0;
+  if ((int)ra[0].x >= 0) {
+    const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(int)ra[0].x);
+    hd0 = __ldg(pk), hd1 = __ldg(pk + 1), hd2 = __ldg(pk + 2);
+  }
+#pragma unroll
+  for (int j = 1; j < ASM_PPT; ++j)
+    if ((int)ra[j].x >= 0) {
+      const char *pb = reinterpret_cast<const char *>(cellpk + PK * (int64_t)(int)ra[j].x);
+      pf_l2(pb), pf_l2(pb + 128), pf_l2(pb + 256), pf_l2(pb + 8 * PK - 8);
+    }
+  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
+  double *s_res = s_vals + cnt;
+  {
+    const int n2 = (cnt + 2 * ng + 1) >> 1;  // the image is 16-byte aligned and padded to an even length
+    double2 *z = reinterpret_cast<double2 *>(s_vals);
+    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
+  }
+  if (t < 36) {
+    const int k = t / 6, l = t % 6;
+    double *e = s_kl + k * KL_STRIDE + 6 * l;
+    e[0] = c_fe2.Mh[k][l], e[1] = c_fe2.Mx[k][l], e[2] = c_fe2.My[k][l];
+    e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
+    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
+  }
+  if (t >= 64 && t < 64 + 42) {
+    const int q = (t - 64) / 6, k = (t - 64) % 6;
+    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
+  }
+  __syncthreads();
+
+  const bool have = td.y != 0xffffffffu;
+  const int len = have ? (int)(td.y & 0xffffu) : 0, slot = have ? (int)((td.y >> 16) & 0xffu) : 0, gl = have ? (int)(td.y >> 24) : 0;
+  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
+  double *row0 = s_vals + (have ? (td.x & 0xffffu) : 0u), *row1 = row0 + len;
+  const bool ns = !P.stokes;
+  const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
+
+#pragma unroll
+  for (int j = 0; j < ASM_PPT; ++j) {
+    const bool work = (int)ra[j].x >= 0;
+    const int k = work ? (int)ra[j].y : 0;
+    const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(work ? (int)ra[j].x : 0));
+    double a00 = 0, a01 = 0, a10 = 0, a11 = 0, d = 0, res0 = 0, res1 = 0;
+    if (work) {
+      if (j == 0) {
+        a00 = hd0.x, a01 = hd0.y, a10 = hd1.x, a11 = hd1.y, d = hd2.x;
+      } else {
+        const double2 ga = __ldg(pk), gb = __ldg(pk + 1), gd = __ldg(pk + 2);
+        a00 = ga.x, a01 = ga.y, a10 = gb.x, a11 = gb.y, d = gd.x;
+      }
+      const double2 rk = __ldg(pk + 16 + k);
+      res0 = rk.x, res1 = rk.y;
+    }
+    const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
+    const double rd = P.rho * d, md = mdt * d, vd = nurho * d;
+    const double r00 = rd * a00, r01 = rd * a01, r10 = rd * a10, r11 = rd * a11;
+    const double *kl = s_kl + k * KL_STRIDE;
+    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double A00[3], A01[3], A10[3], A11[3], B0[3], B1[3];
+      if (work) {
+        double H[2][3][2];
+#pragma unroll
+        for (int ll = 0; ll < 3; ++ll) H[0][ll][0] = H[0][ll][1] = H[1][ll][0] = H[1][ll][1] = 0.0;
+        if (ns) {
+          // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l   (second Frechet term, cpp:265-269)
+#pragma unroll
+          for (int q = 0; q < 7; ++q) {
+            const double2 U = ldg_v2_volatile(pk + 9 + q);
+            const double wk = s_wpsi[q][k];
+            const double c0 = wk * U.x, c1 = wk * U.y;
+#pragma unroll
+            for (int ll = 0; ll < 3; ++ll) {
+              const int l = 3 * half + ll;
+              H[0][ll][0] += c0 * c_fe.dpsi[q][l][0];
+              H[0][ll][1] += c0 * c_fe.dpsi[q][l][1];
+              H[1][ll][0] += c1 * c_fe.dpsi[q][l][0];
+              H[1][ll][1] += c1 * c_fe.dpsi[q][l][1];
+            }
+          }
+        }
+        double2 g0a = make_double2(0, 0), g0b = g0a, gxa = g0a, gxb = g0a, gya = g0a, gyb = g0a;
+        if (ns) {
+          g0a = ldg_v2_volatile(pk + 3), g0b = ldg_v2_volatile(pk + 4), gxa = ldg_v2_volatile(pk + 5);
+          gxb = ldg_v2_volatile(pk + 6), gya = ldg_v2_volatile(pk + 7), gyb = ldg_v2_volatile(pk + 8);
+        }
+#pragma unroll
+        for (int ll = 0; ll < 3; ++ll) {
+          const int l = 3 * half + ll;
+          const double2 e0 = *reinterpret_cast<const double2 *>(kl + 6 * l), e1 = *reinterpret_cast<const double2 *>(kl + 6 * l + 2),
+                        e2 = *reinterpret_cast<const double2 *>(kl + 6 * l + 4);
+          const double Mkl = e0.x, Mx = e0.y, My = e1.x;
+          const double Kkl = S00 * e1.y + S01 * e2.x + S11 * e2.y;  // (1/d) sum_q w g_k.g_l
+          const double D = md * Mkl + vd * Kkl;
+          // rho w G_ab psi_k psi_l (cpp:259-263) + rho w psi_k U_b (g_l)_a (cpp:265-269)
+          A00[ll] = D + (g0a.x * Mkl + gxa.x * Mx + gya.x * My) + (r00 * H[0][ll][0] + r01 * H[0][ll][1]);
+          A01[ll] = (g0a.y * Mkl + gxa.y * Mx + gya.y * My) + (r00 * H[1][ll][0] + r01 * H[1][ll][1]);
+          A10[ll] = (g0b.x * Mkl + gxb.x * Mx + gyb.x * My) + (r10 * H[0][ll][0] + r11 * H[0][ll][1]);
+          A11[ll] = D + (g0b.y * Mkl + gxb.y * Mx + gyb.y * My) + (r10 * H[1][ll][0] + r11 * H[1][ll][1]);
+        }
+        if (half == 0) {
+          // B^T[(a,k),m] = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[k][m][0]);
+            B0[m] = -d * (a00 * bh.x + a01 * bh.y);
+            B1[m] = -d * (a10 * bh.x + a11 * bh.y);
+          }
+        }
+      }
+      // commit rounds: slot r of every owner adds its half pair into the owner's rows, in cell order; all
+      // entries are loaded before any is written back (they are distinct, which the compiler cannot know)
+      for (int r = 0; r < wrounds; ++r) {
+        if (work && slot == r) {
+          int o[3];
+#pragma unroll
+          for (int ll = 0; ll < 3; ++ll) {
+            const int l = 3 * half + ll;
+            o[ll] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+          }
+          double x[6], y[6];
+#pragma unroll
+          for (int ll = 0; ll < 3; ++ll) {
+            x[2 * ll] = row0[o[ll]], x[2 * ll + 1] = row0[o[ll] + 1];
+            y[2 * ll] = row1[o[ll]], y[2 * ll + 1] = row1[o[ll] + 1];
+          }
+          if (half == 0) {
+            int op[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) op[m] = (ow[(6 + m) >> 1] >> (((6 + m) & 1) * 16)) & 0xffff;
+            double xb[3], yb[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) xb[m] = row0[op[m]], yb[m] = row1[op[m]];
+            const double e0 = s_res[2 * gl], e1 = s_res[2 * gl + 1];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) row0[op[m]] = xb[m] + B0[m], row1[op[m]] = yb[m] + B1[m];
+            s_res[2 * gl] = e0 + res0, s_res[2 * gl + 1] = e1 + res1;
+          }
+#pragma unroll
+          for (int ll = 0; ll < 3; ++ll) {
+            row0[o[ll]] = x[2 * ll] + A00[ll], row0[o[ll] + 1] = x[2 * ll + 1] + A01[ll];
+            row1[o[ll]] = y[2 * ll] + A10[ll], row1[o[ll] + 1] = y[2 * ll + 1] + A11[ll];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  double *out = vals + ci.rs;
+  if (((ci.rs | (int64_t)cnt) & 1) == 0) {
+    if (t == 0 && cnt > 0) bulk_store_image(out, s_vals, (uint32_t)cnt * 8u);
+  } else {
+    for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+  }
+  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
+}
+
+// ---- variant 4: one pair per lane, lanes sorted by (commit round, cell), first-touch stores ----------------
+// ncu on variants 2/3: the LSU data pipe (l1tex__data_pipe_lsu_wavefronts) runs at 93 % of peak - the kernel
+// is bound by shared-memory / L1 WAVEFRONTS, two thirds of them from the warp-local commit rounds (3 rounds
+// per warp, the later ones with 1/6 of the lanes active, every entry read-modify-written).  Here
+//   * a lane integrates ONE pair; the lanes of a chunk are sorted by round (= rank of the cell among the
+//     owner's cells), so a warp commits once with all lanes active; rounds are separated by CTA barriers;
+//   * the first contribution to an image entry is a plain store (flag bits in the record): no zero-fill, and
+//     only the ~1/3 of the contributions that are not the first read the image back;
+//   * lanes of a warp that share a cell are adjacent: one L1 wavefront serves them all;
+//   * the image leaves by one bulk async copy (TMA).
+template <int MINB>
+__global__ void __launch_bounds__(NPC, MINB)
+k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
+              const AsmParams P, const int pf_dist) {
+  extern __shared__ __align__(16) double s_vals[];
+  __shared__ __align__(16) double s_kl[6 * KL_STRIDE];
+  __shared__ __align__(16) double s_Bh[6][3][2];
+  __shared__ double s_wpsi[7][6];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  // the lane's record sits at a fixed place (chunk * NPC + lane): requested together with the chunk header
+  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC + t);
+  const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
+  const ChunkInfo ci = wl.chunks[b];
+  // the CTA that follows this one on its SM slot: pull its header and records towards L2 now, its packets at the end
+  const int64_t bn = b + pf_dist;
+  int next_cell = -1;
+  if (pf_dist > 0 && bn < wl.n_chunks) {
+    next_cell = __ldg(&wl.recs[bn * NPC + t].cell);
+    if (t == 0) pf_l2(wl.chunks + bn);
+  }
+  const bool work = (int)ra.x >= 0;
+  const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(work ? (int)ra.x : 0));
+  // one request per 128-byte line of the packet goes out NOW (in flight while the tables are staged); the
+  // remaining loads after the barrier then hit L1 instead of paying a second DRAM round trip
+  const int k = (int)(ra.y & 7u);
+  double2 hd0 = make_double2(0, 0), hd1 = hd0, hd2 = hd0, g0a = hd0, U0 = hd0, U4 = hd0, rk = hd0;
+  if (work) {
+    hd0 = __ldg(pk), hd1 = __ldg(pk + 1), hd2 = __ldg(pk + 2);
+    g0a = __ldg(pk + 3), U0 = __ldg(pk + 9), U4 = __ldg(pk + 13), rk = __ldg(pk + 16 + k);
+  }
+  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
+  double *s_res = s_vals + cnt;
+  if (ci.pad) {  // the pattern has entries no cell contributes to: they must read zero
+    const int n2 = (cnt + 2 * ng + 1) >> 1;
+    double2 *z = reinterpret_cast<double2 *>(s_vals);
+    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
+  }
+  if (t < 36) {
+    const int k = t / 6, l = t % 6;
+    double *e = s_kl + k * KL_STRIDE + 6 * l;
+    e[0] = c_fe2.Mh[k][l], e[1] = c_fe2.Mx[k][l], e[2] = c_fe2.My[k][l];
+    e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
+    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
+  }
+  if (t >= 64 && t < 64 + 42) {
+    const int q = (t - 64) / 6, k = (t - 64) % 6;
+    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
+  }
+  __syncthreads();
+
+  const uint32_t kw = ra.y;
+  const int round = (int)((kw >> 3) & 31u), gl = (int)((kw >> 8) & 255u);
+  const uint32_t first = (kw >> 16) & 0x3ffu;  // bits 0..8 column groups, bit 9 residual
+  double *row0 = s_vals + (rb.z >> 16), *row1 = row0 + (rb.w & 0xffffu);  // off[9] = image offset, off[10] = row length
+  const bool ns = !P.stokes;
+  const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
+
+  double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
+  double res0 = 0.0, res1 = 0.0;
+  if (work) {
+    const double a00 = hd0.x, a01 = hd0.y, a10 = hd1.x, a11 = hd1.y, d = hd2.x;
+    res0 = rk.x, res1 = rk.y;
+    double H[2][6][2];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) H[0][l][0] = H[0][l][1] = H[1][l][0] = H[1][l][1] = 0.0;
+    double2 g0b = make_double2(0, 0), gxa = g0b, gxb = g0b, gya = g0b, gyb = g0b;
+    if (ns) {
+      g0b = __ldg(pk + 4), gxa = __ldg(pk + 5), gxb = __ldg(pk + 6), gya = __ldg(pk + 7), gyb = __ldg(pk + 8);
+      // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l   (second Frechet term, cpp:265-269)
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const double2 U = q == 0 ? U0 : (q == 4 ? U4 : __ldg(pk + 9 + q));
+        const double wk = s_wpsi[q][k];
+        const double c0 = wk * U.x, c1 = wk * U.y;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          H[0][l][0] += c0 * c_fe.dpsi[q][l][0];
+          H[0][l][1] += c0 * c_fe.dpsi[q][l][1];
+          H[1][l][0] += c1 * c_fe.dpsi[q][l][0];
+          H[1][l][1] += c1 * c_fe.dpsi[q][l][1];
+        }
+      }
+    }
+    const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
+    const double rd = P.rho * d, md = mdt * d, vd = nurho * d;
+    const double r00 = rd * a00, r01 = rd * a01, r10 = rd * a10, r11 = rd * a11;
+    const double *kl = s_kl + k * KL_STRIDE;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const double2 e0 = *reinterpret_cast<const double2 *>(kl + 6 * l), e1 = *reinterpret_cast<const double2 *>(kl + 6 * l + 2),
+                    e2 = *reinterpret_cast<const double2 *>(kl + 6 * l + 4);
+      const double Mkl = e0.x, Mx = e0.y, My = e1.x;
+      const double Kkl = S00 * e1.y + S01 * e2.x + S11 * e2.y;  // (1/d) sum_q w g_k.g_l
+      const double D = md * Mkl + vd * Kkl;
+      // rho w G_ab psi_k psi_l (cpp:259-263) + rho w psi_k U_b (g_l)_a (cpp:265-269)
+      A00[l] = D + (g0a.x * Mkl + gxa.x * Mx + gya.x * My) + (r00 * H[0][l][0] + r01 * H[0][l][1]);
+      A01[l] = (g0a.y * Mkl + gxa.y * Mx + gya.y * My) + (r00 * H[1][l][0] + r01 * H[1][l][1]);
+      A10[l] = (g0b.x * Mkl + gxb.x * Mx + gyb.x * My) + (r10 * H[0][l][0] + r11 * H[0][l][1]);
+      A11[l] = D + (g0b.y * Mkl + gxb.y * Mx + gyb.y * My) + (r10 * H[1][l][0] + r11 * H[1][l][1]);
+    }
+    // B^T[(a,k),m] = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[k][m][0]);
+      B0[m] = -d * (a00 * bh.x + a01 * bh.y);
+      B1[m] = -d * (a10 * bh.x + a11 * bh.y);
+    }
+  }
+  // commit: round r = the owner's r-th cell in ascending order; a lane's first contribution to an entry stores
+  const uint32_t ow[5] = {ra.z, ra.w, rb.x, rb.y, rb.z};
+  for (int r = 0; r < ci.max_slots; ++r) {
+    if (work && round == r) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+        if (!((first >> l) & 1u)) x0 = row0[o], x1 = row0[o + 1], y0 = row1[o], y1 = row1[o + 1];
+        row0[o] = x0 + A00[l], row0[o + 1] = x1 + A01[l];
+        row1[o] = y0 + A10[l], row1[o + 1] = y1 + A11[l];
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int l = 6 + m;
+        const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+        double x0 = 0.0, y0 = 0.0;
+        if (!((first >> l) & 1u)) x0 = row0[o], y0 = row1[o];
+        row0[o] = x0 + B0[m], row1[o] = y0 + B1[m];
+      }
+      double e0 = 0.0, e1 = 0.0;
+      if (!((first >> 9) & 1u)) e0 = s_res[2 * gl], e1 = s_res[2 * gl + 1];
+      s_res[2 * gl] = e0 + res0, s_res[2 * gl + 1] = e1 + res1;
+    }
+    __syncthreads();
+  }
+  double *out = vals + ci.rs;
+  if (((ci.rs | (int64_t)cnt) & 1) == 0) {
+    if (t == 0 && cnt > 0) bulk_store_image(out, s_vals, (uint32_t)cnt * 8u);
+  } else {
+    for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+  }
+  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
+  if (next_cell >= 0) {
+    const char *pb = reinterpret_cast<const char *>(cellpk + PK * (int64_t)next_cell);
+    pf_l2(pb), pf_l2(pb + 128), pf_l2(pb + 256), pf_l2(pb + 8 * PK - 8);
+  }
+}
+
+// pressure rows of variant 4 (B, the structurally present zero p-p block, pressure mass), same scheme
+__global__ void __launch_bounds__(NPC, 6)
+k_assemble_p5(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, double *__restrict__ pm_vals, double *__restrict__ R,
+              const double *__restrict__ geom, const AsmParams P) {
+  extern __shared__ __align__(16) double s_vals[];
+  __shared__ __align__(16) double s_Bh[3][6][2];  // [m][l][c]
+  __shared__ double s_Mp[3][3];
+  const int t = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC + t);
+  const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
+  const ChunkInfo ci = wl.chunks[b];
+  const bool work = (int)ra.x >= 0;
+  const int64_t c = work ? (int)ra.x : 0;
+  double a00 = 0, a01 = 0, a10 = 0, a11 = 0, d = 0;
+  if (work) a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2), a11 = __ldg(geom + 5 * c + 3), d = __ldg(geom + 5 * c + 4);
+  const int cnt = ci.cnt, mcnt = ci.mcnt, ng = ci.g1 - ci.g0;
+  double *s_pm = s_vals + cnt;
+  // the p-p block of the Jacobian is structurally present and identically zero (cpp:107-110): no pair writes it
+  {
+    const int n2 = (cnt + mcnt + 1) >> 1;
+    double2 *z = reinterpret_cast<double2 *>(s_vals);
+    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
+  }
+  if (t < 36) {
+    const int l = t / 6, m = (t % 6) / 2, cc = t % 2;
+    s_Bh[m][l][cc] = c_fe2.Bh[l][m][cc];
+  }
+  if (t >= 64 && t < 73) (&s_Mp[0][0])[t - 64] = (&c_fe2.Mp[0][0])[t - 64];
+  __syncthreads();
+  const uint32_t kw = ra.y;
+  const int m = (int)(kw & 7u), round = (int)((kw >> 3) & 31u);
+  double *row = s_vals + (rb.z >> 16), *mrow = s_pm + (rb.w & 0xffffu);
+  const double inv_nu = 1.0 / P.nu;
+  double Bx[6], By[6], M[3];
+  if (work) {
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[m][l][0]);
+      Bx[l] = -d * (a00 * bh.x + a01 * bh.y);
+      By[l] = -d * (a10 * bh.x + a11 * bh.y);
+    }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) M[n] = s_Mp[m][n] * inv_nu * d;
+  }
+  const uint32_t ow[5] = {ra.z, ra.w, rb.x, rb.y, rb.z};
+  for (int r = 0; r < ci.max_slots; ++r) {
+    if (work && round == r) {
+      int o[9];
+#pragma unroll
+      for (int l = 0; l < 9; ++l) o[l] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
+      const uint32_t first = kw >> 16;  // bits 0..8: the lane's contribution is the first one to that entry
+      double x[12], y[3];
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        x[2 * l] = x[2 * l + 1] = 0.0;
+        if (!((first >> l) & 1u)) x[2 * l] = row[o[l]], x[2 * l + 1] = row[o[l] + 1];
+      }
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        y[n] = 0.0;
+        if (!((first >> (6 + n)) & 1u)) y[n] = mrow[o[6 + n]];
+      }
+#pragma unroll
+      for (int l = 0; l < 6; ++l) row[o[l]] = x[2 * l] + Bx[l], row[o[l] + 1] = x[2 * l + 1] + By[l];
+#pragma unroll
+      for (int n = 0; n < 3; ++n) mrow[o[6 + n]] = y[n] + M[n];
+    }
+    __syncthreads();
+  }
+  double *out = vals + ci.rs, *mout = pm_vals + ci.ms;
+  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+  for (int i = t; i < mcnt; i += NPC) __stcs(mout + i, s_pm[i]);
+  // no statement of the reference tests the pressure space: R_p == 0
+  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
+}
+
 // ---- K2: Neumann faces (cpp:315-336), one thread per boundary P2 node, faces in list order ------
 __global__ void k_neumann(int64_t n_bnodes, const int32_t *__restrict__ bnode_dof, const int32_t *__restrict__ bnode_ptr,
                           const int32_t *__restrict__ bnode_face, const int32_t *__restrict__ bnode_pos,

@@ -55,17 +55,26 @@ static_assert(sizeof(PairRec) == 32, "PairRec must be 32 bytes");
 // local rows to the shared chunk image in rounds (slot 0, barrier, slot 1, ...), i.e. in ascending
 // cell order: no atomics, fixed summation order.
 constexpr int ASM_PPT = 2;
+constexpr int64_t ASM_STAGE_CAP = int64_t(1) << 30;  // max staged entries per chunk (env NSG_ASM_STAGE_CAP overrides)
 struct __align__(16) ChunkInfo {
   int32_t g0, g1;        // owners [g0,g1) of this chunk (consecutive rows)
   int32_t n_threads;     // sum of slots (<= NPC)
   int32_t max_slots;     // commit rounds
   int64_t rec_base;      // records of iteration j, thread t at rec_base + j*n_threads + t
+  // everything the packet-based kernels (variant 2) need without a dependent row-pointer load:
+  int64_t rs;            // first Jacobian entry of the chunk's rows
+  int64_t ms;            // first pressure-mass entry (pressure chunks)
+  int32_t cnt, mcnt;     // number of Jacobian / pressure-mass entries of the chunk
   int64_t pad;
 };
+static_assert(sizeof(ChunkInfo) == 64, "ChunkInfo layout");
 struct WorkList {
   int64_t n_groups = 0, n_chunks = 0, n_pairs = 0, n_recs = 0;
   ChunkInfo *chunks = nullptr;   // [n_chunks]
   uint16_t *tdesc = nullptr;     // [n_chunks*NPC] owner index inside the chunk | slot << 8
+  uint2 *tdesc3 = nullptr;       // [n_chunks*NPC] x = offset of the owner's first row in the chunk image (pressure: x =
+                                 // J-row offset | mass-row offset << 16); y = row length | slot << 16 | owner << 24;
+                                 // y = 0xffffffff marks a padding lane
   PairRec *recs = nullptr;       // [n_recs]; cell = -1 marks "no work"
   int64_t max_stage = 0;         // max number of staged matrix entries of a chunk
 };
@@ -171,7 +180,7 @@ struct nsg_ctx {
   int32_t *spmv_chunk_rows = nullptr;
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
-  int spmv_variant = 0, asm_variant = 0;
+  int spmv_variant = 0, asm_variant = 4;
   bool use_graphs = true;
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;
@@ -183,9 +192,11 @@ struct nsg_ctx {
   int64_t spmv_n_chunks = 0;
   // mesh
   double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|
+  double *cellpk = nullptr;  // [44T] per-cell packets of assembly variant 2 (rewritten by every nsg_assemble)
   double *xy = nullptr;
   int32_t *cell_vertices = nullptr, *cell_dofs = nullptr;
   nsg::WorkList wl_u, wl_p;
+  nsg::WorkList wl_u5, wl_p5;  // assembly variant 4: one pair per lane, lanes sorted by (round, cell)
   // Neumann: boundary nodes -> faces
   int64_t n_bnodes = 0;
   int32_t *bnode_dof = nullptr, *bnode_ptr = nullptr, *bnode_face = nullptr, *bnode_pos = nullptr;

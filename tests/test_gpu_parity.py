@@ -39,11 +39,11 @@ def rel(a, b):
 
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("mode", ["newton", "steady", "stokes"])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_assembly_parity(pkg, case, mode, variant):
     m, d, part, calls, neumann, inlet = build(pkg, case)
     dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
-    dev.set_tuning(1, variant)     # 0: literal quadrature loop (default), 1: factored tables
+    dev.set_tuning(1, variant)     # 0: literal quadrature loop, 1: factored tables, 2: factored + per-cell packets
     # the factored variant re-associates the quadrature sums (geometry x pre-integrated table):
     # same integrals, a few more ulps of difference from the oracle's literal loop
     tol = 1e-12 if variant == 0 else 5e-12
