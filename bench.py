@@ -315,10 +315,12 @@ def main():
                           "frac": 32 * n_rows / aad_ms / 1e6 / hbm, "ms_per_launch": aad_ms,
                           "launches_per_step": int(mgs_passes), "share_of_step": mgs_passes * aad_ms / t_step_ms,
                           "note": "modified Gram-Schmidt chain: the largest share of a step; 32 B/DoF per pass"},
-        "assembly(k_assemble_u+k_assemble_p+k_neumann)": {
+        "assembly(k_cell_packets+k_assemble_u5+k_assemble_p5+k_neumann)": {
             "bound": "hbm", "achieved": asm_bytes / asm_k_ms / 1e6, "peak": hbm, "unit": "GB/s",
             "frac": asm_bytes / asm_k_ms / 1e6 / hbm, "ms_per_launch": asm_k_ms, "algorithmic_bytes_per_launch": asm_bytes,
-            "mdofs": part.n_own / asm_k_ms / 1e3}}
+            "mdofs": part.n_own / asm_k_ms / 1e3,
+            "note": "variant 4; ncu: bound by L1/shared-memory wavefronts (LSU data pipe 72 %) and CTA barriers, FP64 pipe 21 % "
+                    "(profiles/r01_summary.md)"}}
 
     # the same GMRES steps with classical Gram-Schmidt (tuning key 3; NOT the reference default): reported beside
     dev.set_tuning(3, 1)

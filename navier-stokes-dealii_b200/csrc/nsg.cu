@@ -674,7 +674,7 @@ static int launch_assembly(nsg_ctx *c) {
     if (c->wl_u5.n_chunks > 0) {
       const unsigned grid = (unsigned)c->wl_u5.n_chunks;
       const size_t smem = sizeof(double) * (size_t)c->wl_u5.max_stage;
-      const int minb = std::getenv("NSG_ASM3_MINB") ? std::atoi(std::getenv("NSG_ASM3_MINB")) : 3;
+      const int minb = std::getenv("NSG_ASM3_MINB") ? std::atoi(std::getenv("NSG_ASM3_MINB")) : 4;
       // a CTA pulls the records and packets of the CTA that will follow it on its SM slot towards L2
       const int pf = std::getenv("NSG_ASM_PF") ? std::atoi(std::getenv("NSG_ASM_PF")) : 0;  // measured: no gain (profiles/r01_summary.md)
       if (minb <= 3)
@@ -868,6 +868,7 @@ int nsg_create(int device, nsg_ctx **out) {
   auto *c = new nsg_ctx;
   c->device = device;
   c->peer.n_ranks = 1;
+  if (const char *v = std::getenv("NSG_ASM_VARIANT")) c->asm_variant = std::min(std::max(std::atoi(v), 0), 4);
   nsg_params_default(&c->prm);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
