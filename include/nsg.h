@@ -172,6 +172,8 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * key 3 = Gram-Schmidt variant of SolverGMRES: 0 (default) modified, the chain of add_and_dot that deal.II
  * <= 9.4 runs; 1 classical (h = V^T w, w -= V h: two passes and two all-reduces per step
  * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).
+ * key 4 = triangular solves of the ILU(0) preconditioners: 0 one launch per dependency level; 1 (default) one
+ * launch per solve, rows wait on the completion stamps of the rows they depend on (bitwise the same result).
  * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 

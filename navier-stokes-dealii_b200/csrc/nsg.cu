@@ -666,6 +666,26 @@ static AsmParams asm_params(const nsg_ctx *c) {
 static int launch_assembly(nsg_ctx *c) {
   const AsmParams P = asm_params(c);
   if (c->asm_variant == 4) {
+    // the pressure rows depend on the geometry only: they are integrated on a second stream beside the packet
+    // pre-pass and the velocity rows (NSG_ASM_CONCURRENT=0: one stream)
+    const bool fork = c->wl_p5.n_chunks > 0 && c->aux_stream && !(std::getenv("NSG_ASM_CONCURRENT") && std::atoi(std::getenv("NSG_ASM_CONCURRENT")) == 0);
+    cudaStream_t ps = fork ? c->aux_stream : c->stream;
+    if (fork) {
+      NSG_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      NSG_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    }
+    auto launch_p = [&]() -> int {
+      if (c->wl_p5.n_chunks > 0) {
+        k_assemble_p5<<<(unsigned)c->wl_p5.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p5.max_stage, ps>>>(
+            c->wl_p5, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
+        NSG_LAUNCH_CHECK(c);
+      }
+      return NSG_OK;
+    };
+    if (fork) {
+      NSG_TRY(launch_p());
+      NSG_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    }
     if (c->n_cells > 0) {
       k_cell_packets<<<grid_for(c->n_cells, 128, 1 << 30), 128, 0, c->stream>>>(c->n_cells, c->geom, c->cell_dofs, c->sol, c->sol_old,
                                                                                 P, c->cellpk);
@@ -685,11 +705,10 @@ static int launch_assembly(nsg_ctx *c) {
         k_assemble_u5<5><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
       NSG_LAUNCH_CHECK(c);
     }
-    if (c->wl_p5.n_chunks > 0) {
-      k_assemble_p5<<<(unsigned)c->wl_p5.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p5.max_stage, c->stream>>>(
-          c->wl_p5, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
-      NSG_LAUNCH_CHECK(c);
-    }
+    if (fork)
+      NSG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    else
+      NSG_TRY(launch_p());
   } else if (c->asm_variant >= 2) {
     if (c->n_cells > 0) {
       k_cell_packets<<<grid_for(c->n_cells, 128, 1 << 30), 128, 0, c->stream>>>(c->n_cells, c->geom, c->cell_dofs, c->sol, c->sol_old,
@@ -876,6 +895,9 @@ int nsg_create(int device, nsg_ctx **out) {
   }
   c->stream = c->own_stream;
   cudaEventCreate(&c->ev0);
+  cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&c->ev1);
   int rc = upload_tables();
   if (rc == NSG_OK) rc = dev_alloc(&c->partials, RED_MAX_BLOCKS);
@@ -919,6 +941,9 @@ void nsg_destroy(nsg_ctx *c) {
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1454,6 +1479,10 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       return NSG_OK;
     case 2:
       c->use_graphs = value != 0;
+      return NSG_OK;
+    case 4:
+      if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "ILU solve variant must be 0 (one launch per level) or 1 (single launch)");
+      c->ilu_variant = value;
       return NSG_OK;
     case 3:
       if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "orthogonalization must be 0 (modified) or 1 (classical Gram-Schmidt)");

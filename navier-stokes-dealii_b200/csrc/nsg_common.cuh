@@ -157,6 +157,12 @@ struct CsrBlock {  // a sub-matrix held separately (A, Mp, B of the block precon
   double *dinv = nullptr;
   int32_t *chunk_rows = nullptr;
   int64_t n_chunks = 0;
+  // single-launch ("sync-free") triangular solves: per-row completion stamps + ticket counter for the CTA order
+  ulonglong2 *done_l = nullptr, *done_u = nullptr;    // [n] {value, epoch stamp} of the forward / backward unknowns
+  unsigned long long *ticket = nullptr;               // [2] monotone counters (forward, backward)
+  unsigned long long epoch = 0;
+  unsigned long long tickets_l = 0, tickets_u = 0;    // host mirror: tickets handed out so far
+  int32_t *sf_error = nullptr;                        // set if a wait ran into its time limit
 };
 
 }  // namespace nsg
@@ -181,6 +187,7 @@ struct nsg_ctx {
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
   int spmv_variant = 0, asm_variant = 4;
+  int ilu_variant = 1;  // 0: one launch per dependency level; 1: single launch, rows wait on completion stamps
   bool use_graphs = true;
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;
@@ -243,4 +250,6 @@ struct nsg_ctx {
   int64_t launches = 0, h2d = 0, d2h = 0;
   double phase_ms[3] = {0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t aux_stream = nullptr;  // pressure-row assembly runs beside the velocity rows
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };

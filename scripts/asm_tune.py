@@ -17,10 +17,11 @@ for cap in caps:
     dev = pkg.DeviceProblem(part, 0)
     dev.set_params(neumann_id=neumann)
     dev.set_solution(sol); dev.set_solution_old(0.9 * sol)
-    for av, minb, pf in ((0, 0, 0), (2, 3, 0), (4, 3, 0), (4, 4, 0), (4, 5, 0), (4, 4, 592)):
+    for av, minb, pf in ((0, 0, 0), (4, 4, 0), (4, 4, -2)):
         if True:
             os.environ["NSG_ASM3_MINB"] = str(minb)
             os.environ.pop("NSG_ASM_PF", None)
+            os.environ["NSG_ASM_CONCURRENT"] = "0" if pf == -2 else "1"
             if pf >= 0:
                 os.environ["NSG_ASM_PF"] = str(pf)
             dev.set_tuning(1, av)

@@ -292,6 +292,20 @@ def test_ilu0_parity(pkg, which):
     dev.close()
 
 
+def test_ilu_single_launch_solves_bitwise(pkg):
+    """Tuning key 4: the single-launch triangular solves (rows wait on completion stamps) sum each row in the same
+    order as the level-scheduled ones: identical bits, also when applied repeatedly (epoch stamps)."""
+    d, part, dev, o = _precond_system(pkg)
+    for which, n in ((0, d.n_u), (1, d.n_p)):
+        x = np.random.default_rng(7 + which).standard_normal(n)
+        dev.set_tuning(4, 0)
+        ref = dev.ilu_apply(which, x)
+        dev.set_tuning(4, 1)
+        for _ in range(3):
+            assert np.array_equal(dev.ilu_apply(which, x), ref)
+    dev.close()
+
+
 @pytest.mark.parametrize("precond", [1, 2])
 def test_block_preconditioned_gmres_parity(pkg, precond):
     """hpp:520-639 behind solve_system: same outer step count, residual history and increment."""
