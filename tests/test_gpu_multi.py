@@ -19,4 +19,4 @@ def test_two_rank_parity():
            "--master-port", "29533", os.path.join(ROOT, "scripts", "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     fails = [l for l in out.stdout.splitlines() if "FAIL" in l]
-    assert "MGPU_CHECK PASS" in out.stdout, "\n".join(fails) + out.stderr[-1500:]
+    assert "MGPU_CHECK PASS" in out.stdout, "\n".join(fails) + "\n--- stdout tail ---\n" + out.stdout[-2500:] + "\n--- stderr tail ---\n" + out.stderr[-2500:]
