@@ -135,6 +135,8 @@ int nsg_set_solution(nsg_ctx *ctx, const double *host);
 int nsg_set_solution_old(nsg_ctx *ctx, const double *host);
 int nsg_set_delta(nsg_ctx *ctx, const double *host);
 int nsg_get_solution(nsg_ctx *ctx, double *host);
+/* the ghosted vector `solution` that output() reads (cpp:697-700): owned entries then the ghost layer, n_loc doubles */
+int nsg_get_solution_ghosted(nsg_ctx *ctx, double *host);
 int nsg_get_delta(nsg_ctx *ctx, double *host);
 int nsg_get_residual(nsg_ctx *ctx, double *host);
 int nsg_get_matrix_values(nsg_ctx *ctx, double *host /* nnz(J), CSR order */);

@@ -142,6 +142,7 @@ _NSG_SIGS = {
     "nsg_set_solution_old": (C.c_int, [vp, f64p]),
     "nsg_set_delta": (C.c_int, [vp, f64p]),
     "nsg_get_solution": (C.c_int, [vp, f64p]),
+    "nsg_get_solution_ghosted": (C.c_int, [vp, f64p]),
     "nsg_get_delta": (C.c_int, [vp, f64p]),
     "nsg_get_residual": (C.c_int, [vp, f64p]),
     "nsg_get_matrix_values": (C.c_int, [vp, f64p]),

@@ -1375,6 +1375,7 @@ int nsg_set_solution(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->s
 int nsg_set_solution_old(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->sol_old : nullptr, h, true); }
 int nsg_set_delta(nsg_ctx *c, const double *h) { return set_owned(c, c ? c->delta : nullptr, h, false); }
 int nsg_get_solution(nsg_ctx *c, double *h) { return get_owned(c, c ? c->sol : nullptr, h, c ? c->n_own : 0); }
+int nsg_get_solution_ghosted(nsg_ctx *c, double *h) { return get_owned(c, c ? c->sol : nullptr, h, c ? c->n_loc : 0); }
 int nsg_get_delta(nsg_ctx *c, double *h) { return get_owned(c, c ? c->delta : nullptr, h, c ? c->n_own : 0); }
 int nsg_get_residual(nsg_ctx *c, double *h) { return get_owned(c, c ? c->R : nullptr, h, c ? c->n_own : 0); }
 int nsg_get_matrix_values(nsg_ctx *c, double *h) { return get_owned(c, c ? c->vals : nullptr, h, c ? c->nnz : 0); }

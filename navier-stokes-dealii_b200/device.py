@@ -131,6 +131,10 @@ class DeviceProblem:
     def get_solution(self):
         return self._get(self._L.nsg_get_solution, self.n_own)
 
+    def get_solution_ghosted(self):
+        """Owned entries followed by the ghost layer (the vector `solution` of the reference, hpp:791)."""
+        return self._get(self._L.nsg_get_solution_ghosted, self.part.n_loc)
+
     def get_delta(self, out=None):
         """out: optional preallocated (e.g. page-locked) float64 array of n_own entries."""
         return self._get(self._L.nsg_get_delta, self.n_own, out)

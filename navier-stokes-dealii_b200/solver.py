@@ -67,7 +67,7 @@ class NavierStokesSolver:
     dim = 2  # hpp:411
 
     def __init__(self, degree_velocity, degree_pressure, T, deltat, params=None, device=0, rank=0, world_size=1,
-                 comm_unique_id=None, stream=None, verbose=True):
+                 comm_unique_id=None, stream=None, verbose=True, gather_objects=None):
         if (degree_velocity, degree_pressure) != (2, 1):
             raise ValueError("the B200 path implements the reference's P2-P1 Taylor-Hood pair (main.cpp:9-10)")
         self.T = float(T)
@@ -75,6 +75,9 @@ class NavierStokesSolver:
         self.prm = params or Parameters()
         self.device, self.rank, self.world_size = device, rank, world_size
         self._uid, self._stream = comm_unique_id, stream
+        # P > 1: callable(obj) -> [obj of rank 0, ..., obj of rank P-1] (e.g. torch.distributed.all_gather_object), used
+        # by output() so that rank 0 can describe every rank's heavy-data file in the one .xdmf
+        self._gather_objects = gather_objects
         self.verbose = verbose and rank == 0
         self.time = 0.0
         self.history = []        # (time_step, newton_iter, residual_norm, gmres_its)
@@ -218,7 +221,7 @@ class NavierStokesSolver:
             self.output(time_step, self.time)
             self.pcout("")
 
-    # ---- output (cpp:681-728): minimal raw writer; HDF5 is not in this image -----------------------
+    # ---- output (cpp:681-728): XDMF + raw binary heavy data (output.py; HDF5 is not in this image) + npz restart data ----
     def output(self, time_step, time):
         self.pcout("===============================================")
         if not self.prm.output_dir:
@@ -228,6 +231,15 @@ class NavierStokesSolver:
         sol = self.dev.get_solution()
         np.savez(os.path.join(self.prm.output_dir, f"{name}.rank{self.rank}.npz"), time=time, solution=sol,
                  l2g=self.part.l2g[: self.part.n_own], partitioning=self.rank)
+        # XDMF + raw binary heavy data, one patch per owned cell as DataOut::build_patches makes them (cpp:685-727)
+        from . import output as xout
+        patches = xout.cell_patches(self.part, self.dev.get_solution_ghosted(), self.rank)
+        layout = xout.write_rank_file(self.prm.output_dir, name, self.rank, patches)
+        layouts = {self.rank: layout}
+        if self.world_size > 1 and self._gather_objects is not None:
+            layouts = {r: lay for r, lay in enumerate(self._gather_objects(layout))}
+        if self.rank == 0:
+            xout.write_xdmf(self.prm.output_dir, name, time, layouts)
 
     # ---- N3: drag / lift on the cylinder (boundary id 13, cpp:368); not in the reference ----------------
     def drag_lift(self, boundary_id=13, u_mean=1.0, diameter=0.1):

@@ -126,6 +126,9 @@ class Oracle:
     def get_solution(self):
         return self._get(self._L.orc_get_solution, self.n)
 
+    def get_solution_ghosted(self):  # one rank: no ghost layer
+        return self.get_solution()
+
     def get_delta(self):
         return self._get(self._L.orc_get_delta, self.n)
 

@@ -98,3 +98,29 @@ def test_error_paths(pkg):
     its, res, rc = dev.solve(0, 1e-2, 100, 30, 0)
     assert (its, rc) == (0, 0) and res == 0.0 and not dev.get_delta().any()
     dev.close()
+
+
+def test_output_files_from_device_solution(pkg, tmp_path):
+    """N2: output() (cpp:681-728) after every time step: output-NNNN.xdmf + raw heavy data whose nodal values are the
+    device solution at the cell vertices."""
+    import importlib
+    xout = importlib.import_module("navier-stokes-dealii_b200.output")
+    prm = pkg.Parameters(mesh_path=mesh_path("square_h0.1.msh"), nu=0.05, H=1.0, inlet_time_mode="constant", neumann_id=1,
+                         inlet_id=0, wall_ids=(2, 3), clear_inlet_before_walls=True, preconditioner="identity", p_out=0.0,
+                         increment_bc="consistent", newton_max_iters=3, output_dir=str(tmp_path))
+    s = pkg.NavierStokesSolver(2, 1, 0.1, 0.05, prm, verbose=False)
+    s.setup()
+    s.solve()
+    import os
+    names = sorted(f for f in os.listdir(tmp_path) if f.endswith(".xdmf"))
+    assert names == ["output-0000.xdmf", "output-0001.xdmf", "output-0002.xdmf"]
+    t, grids = xout.read_back(str(tmp_path), names[-1])
+    assert abs(t - 0.1) < 1e-12
+    r = grids["rank0"]
+    sol = s.dev.get_solution()
+    cd = s.part.cell_dofs.reshape(-1, 15)
+    assert r["cells"].shape[0] == s.mesh.n_cells
+    assert np.array_equal(r["velocity"][:, 0], sol[cd[:, [0, 3, 6]].reshape(-1)])
+    assert np.array_equal(r["pressure"], sol[cd[:, [2, 5, 8]].reshape(-1)])
+    assert np.abs(r["velocity"][:, :2]).max() > 0.1
+    s.dev.close()

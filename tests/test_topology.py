@@ -174,3 +174,36 @@ def test_partition_and_local_problems(pkg, n_parts):
             recv = q.l2g[q.recv_idx[q.recv_ptr[b]:q.recv_ptr[b + 1]]]
             assert sent.tolist() == recv.tolist() and len(sent) > 0
         assert p.n_recv == p.n_ghost_u + p.n_ghost_p
+
+
+def test_output_writer_xdmf_roundtrip(pkg, tmp_path):
+    """N2: the XDMF + raw-binary writer (cpp:681-728 without HDF5): one 3-node patch per owned cell with velocity,
+    pressure and partitioning, two ranks described by one .xdmf; read back through the XML."""
+    import importlib
+    xout = importlib.import_module("navier-stokes-dealii_b200.output")
+    m = pkg.Mesh.read_msh(mesh_path("square_h0.1.msh"))
+    cp = m.partition_rcb(2)
+    d = pkg.Dofs(m, 2, cp)
+    xy = d.support_points()
+    g = np.zeros(d.n)
+    g[0:d.n_u:2] = 1.0 + xy[0:d.n_u:2, 0]           # u_x = 1 + x
+    g[1:d.n_u:2] = 2.0 * xy[1:d.n_u:2, 1]           # u_y = 2 y
+    g[d.n_u:] = xy[d.n_u:, 0] - xy[d.n_u:, 1]       # p = x - y
+    layouts, n_cells = {}, 0
+    for rank in (0, 1):
+        part = pkg.Part(d, rank)
+        patches = xout.cell_patches(part, g[part.l2g], rank)
+        layouts[rank] = xout.write_rank_file(str(tmp_path), "output-0003", rank, patches)
+        n_cells += int(part.cell_owned.sum())
+    assert n_cells == m.n_cells                      # every cell is written by exactly one rank
+    xout.write_xdmf(str(tmp_path), "output-0003", 0.15, layouts)
+    t, grids = xout.read_back(str(tmp_path), "output-0003.xdmf")
+    assert t == 0.15 and sorted(grids) == ["rank0", "rank1"]
+    for rank in (0, 1):
+        r = grids[f"rank{rank}"]
+        T = r["cells"].shape[0]
+        assert r["points"].shape == (3 * T, 2) and np.array_equal(r["cells"].reshape(-1), np.arange(3 * T))
+        x, y = r["points"][:, 0], r["points"][:, 1]
+        assert np.allclose(r["velocity"][:, 0], 1.0 + x, atol=1e-14) and np.allclose(r["velocity"][:, 1], 2.0 * y, atol=1e-14)
+        assert not r["velocity"][:, 2].any() and np.allclose(r["pressure"], x - y, atol=1e-14)
+        assert (r["partitioning"] == rank).all()
