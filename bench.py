@@ -174,7 +174,8 @@ def workload_config(args, d):
                        "P2-P1, state u=(sin(pi x)cos(pi y), -cos(pi x)sin(pi y)), p=xy, u_old=0.9u",
            "mesh": args.mesh, "levels": args.levels, "gmres_its_cap": args.gmres_its,
            "preconditioner": "identity (reference cpp:570)", "l2": "inputs larger than L2 (no flush needed)",
-           "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, NCCL halo + allreduce"}
+           "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, NCCL halo, Krylov all-reduce fused "
+                          "into the reduction kernels (NVLink peer memory)"}
     if d is not None:
         cfg.update({"cells": int(d.mesh.n_cells), "dofs": int(d.n)})
     return cfg
