@@ -82,6 +82,10 @@ int nsg_comm_init(nsg_ctx *ctx, int rank, int n_ranks, const void *unique_id128)
  * host all-gathers them in rank order, nsg_comm_set_peers maps them. Without it NCCL does the all-reduce. */
 int nsg_comm_ipc_handle(nsg_ctx *ctx, void *out64);
 int nsg_comm_set_peers(nsg_ctx *ctx, const void *handles /* n_ranks x 64 bytes, rank order */);
+/* Unmap the peers' mailboxes and go back to NCCL all-reduces. Every rank must call this and then synchronise with the
+ * others (barrier) BEFORE any rank destroys its context: CUDA IPC requires importers to close a mapping before the
+ * exporter frees the memory. */
+int nsg_comm_release_peers(nsg_ctx *ctx);
 
 /* The compile-time constants of the reference as run-time parameters; defaults are the
  * reference's values (hpp:703-709 nu,rho,p_out; main.cpp:13 deltat; hpp:438 g=0; cpp:320 id 10). */

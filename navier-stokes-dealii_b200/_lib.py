@@ -129,6 +129,7 @@ _NSG_SIGS = {
     "nsg_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
     "nsg_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),
     "nsg_comm_set_peers": (C.c_int, [vp, C.c_char_p]),
+    "nsg_comm_release_peers": (C.c_int, [vp]),
     "nsg_params_default": (None, [C.POINTER(NsgParams)]),
     "nsg_set_params": (C.c_int, [vp, C.POINTER(NsgParams)]),
     "nsg_assemble": (C.c_int, [vp]),

@@ -340,7 +340,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
       while (g < ng && g - ci.g0 < 255) {
         const int np = (int)(gptr[g + 1] - gptr[g]);
         if (np > 31) return fail(NSG_ERR_ARG, "a vertex has too many incident cells (more than 31)");
-        if (nt + np > NPC && g > ci.g0) break;
+        if (nt + np > NPC5 && g > ci.g0) break;
         if (g > ci.g0 && staged + stage_of(g) > stage_cap) break;
         staged += stage_of(g);
         nt += np;
@@ -350,7 +350,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
       ci.g1 = (int32_t)g;
       ci.n_threads = nt;
       ci.max_slots = mx;
-      ci.rec_base = rec;  // == chunk index * NPC: a lane finds its record without reading the chunk header
+      ci.rec_base = rec;  // == chunk index * NPC5: a lane finds its record without reading the chunk header
       if (kind == 0) {
         ci.rs = c->h_rowptr[2 * (int64_t)ci.g0];
         ci.cnt = (int32_t)(c->h_rowptr[2 * (int64_t)ci.g1] - ci.rs);
@@ -358,7 +358,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
         ci.rs = c->h_rowptr[nu + ci.g0], ci.ms = c->h_pm_rowptr[nu + ci.g0];
         ci.cnt = (int32_t)(c->h_rowptr[nu + ci.g1] - ci.rs), ci.mcnt = (int32_t)(c->h_pm_rowptr[nu + ci.g1] - ci.ms);
       }
-      rec += NPC;
+      rec += NPC5;
       chunks.push_back(ci);
     }
   }
@@ -366,7 +366,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
   PairRec no_work;
   std::memset(&no_work, 0, sizeof no_work);
   no_work.cell = -1;
-  std::vector<PairRec> recs((size_t)nchunks * NPC, no_work);
+  std::vector<PairRec> recs((size_t)nchunks * NPC5, no_work);
   int bad = 0;
   int64_t max_stage = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_stage) reduction(+ : bad)
@@ -376,7 +376,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
       int32_t round, cell, k, gl;
     };
     std::vector<Lane> lanes;
-    lanes.reserve(NPC);
+    lanes.reserve(NPC5);
     for (int64_t g = ci.g0; g < ci.g1; ++g)
       for (int64_t pi = gptr[g]; pi < gptr[g + 1]; ++pi) lanes.push_back({(int32_t)(pi - gptr[g]), pcell[pi], pk[pi], (int32_t)(g - ci.g0)});
     std::sort(lanes.begin(), lanes.end(), [](const Lane &a, const Lane &b2) {
@@ -384,7 +384,7 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
       if (a.cell != b2.cell) return a.cell < b2.cell;
       return a.k < b2.k;
     });
-    if ((int)lanes.size() != ci.n_threads || ci.n_threads > NPC) bad++;
+    if ((int)lanes.size() != ci.n_threads || ci.n_threads > NPC5) bad++;
     // first-touch bookkeeping per image entry
     const int64_t img = kind == 0 ? ci.cnt : (int64_t)ci.cnt + ci.mcnt;
     std::vector<uint8_t> touched((size_t)img, 0), rtouched((size_t)(ci.g1 - ci.g0), 0);
@@ -463,10 +463,10 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
   out->n_groups = ng;
   out->n_chunks = nchunks;
   out->n_pairs = npairs;
-  out->n_recs = nchunks * NPC;
+  out->n_recs = nchunks * NPC5;
   out->max_stage = max_stage + 2;
   NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
-  NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC));
+  NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC5));
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   return NSG_OK;
 }
@@ -676,7 +676,7 @@ static int launch_assembly(nsg_ctx *c) {
     }
     auto launch_p = [&]() -> int {
       if (c->wl_p5.n_chunks > 0) {
-        k_assemble_p5<<<(unsigned)c->wl_p5.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p5.max_stage, ps>>>(
+        k_assemble_p5<<<(unsigned)c->wl_p5.n_chunks, NPC5, sizeof(double) * (size_t)c->wl_p5.max_stage, ps>>>(
             c->wl_p5, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
         NSG_LAUNCH_CHECK(c);
       }
@@ -698,11 +698,11 @@ static int launch_assembly(nsg_ctx *c) {
       // a CTA pulls the records and packets of the CTA that will follow it on its SM slot towards L2
       const int pf = std::getenv("NSG_ASM_PF") ? std::atoi(std::getenv("NSG_ASM_PF")) : 0;  // measured: no gain (profiles/r01_summary.md)
       if (minb <= 3)
-        k_assemble_u5<3><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+        k_assemble_u5<3><<<grid, NPC5, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
       else if (minb == 4)
-        k_assemble_u5<4><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+        k_assemble_u5<4><<<grid, NPC5, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
       else
-        k_assemble_u5<5><<<grid, NPC, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
+        k_assemble_u5<5><<<grid, NPC5, smem, c->stream>>>(c->wl_u5, c->vals, c->R, c->cellpk, P, pf);
       NSG_LAUNCH_CHECK(c);
     }
     if (fork)
@@ -1197,6 +1197,19 @@ int nsg_comm_set_peers(nsg_ctx *c, const void *handles) {
   pc.seq_ctr = c->ar_seq;
   pc.n_ranks = c->n_ranks;  // switches the reductions to the fused all-reduce
   c->peer = pc;
+  return NSG_OK;
+}
+
+int nsg_comm_release_peers(nsg_ctx *c) {
+  if (!c) return fail(NSG_ERR_ARG, "null context");
+  NSG_CUDA(cudaSetDevice(c->device));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  c->peer.n_ranks = 1;  // reductions go back to NCCL
+  for (void *&m : c->peer_mapped)
+    if (m) {
+      cudaIpcCloseMemHandle(m);
+      m = nullptr;
+    }
   return NSG_OK;
 }
 

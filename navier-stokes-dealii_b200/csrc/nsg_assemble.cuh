@@ -1184,6 +1184,10 @@ k_assemble_u4(const WorkList wl, double *__restrict__ vals, double *__restrict__
   for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
 
+#ifndef NSG_NPC5
+#define NSG_NPC5 128
+#endif
+constexpr int NPC5 = NSG_NPC5;  // lanes (pairs) per CTA of variant 4
 // ---- variant 4: one pair per lane, lanes sorted by (commit round, cell), first-touch stores ----------------
 // ncu on variants 2/3: the LSU data pipe (l1tex__data_pipe_lsu_wavefronts) runs at 93 % of peak - the kernel
 // is bound by shared-memory / L1 WAVEFRONTS, two thirds of them from the warp-local commit rounds (3 rounds
@@ -1195,7 +1199,7 @@ k_assemble_u4(const WorkList wl, double *__restrict__ vals, double *__restrict__
 //   * lanes of a warp that share a cell are adjacent: one L1 wavefront serves them all;
 //   * the image leaves by one bulk async copy (TMA).
 template <int MINB>
-__global__ void __launch_bounds__(NPC, MINB)
+__global__ void __launch_bounds__(NPC5, (MINB * 128) / NPC5)
 k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
               const AsmParams P, const int pf_dist) {
   extern __shared__ __align__(16) double s_vals[];
@@ -1204,15 +1208,15 @@ k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__
   __shared__ double s_wpsi[7][6];
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
-  // the lane's record sits at a fixed place (chunk * NPC + lane): requested together with the chunk header
-  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC + t);
+  // the lane's record sits at a fixed place (chunk * NPC5 + lane): requested together with the chunk header
+  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC5 + t);
   const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
   const ChunkInfo ci = wl.chunks[b];
   // the CTA that follows this one on its SM slot: pull its header and records towards L2 now, its packets at the end
   const int64_t bn = b + pf_dist;
   int next_cell = -1;
   if (pf_dist > 0 && bn < wl.n_chunks) {
-    next_cell = __ldg(&wl.recs[bn * NPC + t].cell);
+    next_cell = __ldg(&wl.recs[bn * NPC5 + t].cell);
     if (t == 0) pf_l2(wl.chunks + bn);
   }
   const bool work = (int)ra.x >= 0;
@@ -1230,7 +1234,7 @@ k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__
   if (ci.pad) {  // the pattern has entries no cell contributes to: they must read zero
     const int n2 = (cnt + 2 * ng + 1) >> 1;
     double2 *z = reinterpret_cast<double2 *>(s_vals);
-    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
+    for (int i = t; i < n2; i += NPC5) z[i] = make_double2(0.0, 0.0);
   }
   if (t < 36) {
     const int k = t / 6, l = t % 6;
@@ -1239,10 +1243,7 @@ k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__
     e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
     (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
   }
-  if (t >= 64 && t < 64 + 42) {
-    const int q = (t - 64) / 6, k = (t - 64) % 6;
-    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
-  }
+  for (int i = t; i < 42; i += NPC5) s_wpsi[i / 6][i % 6] = c_fe.w[i / 6] * c_fe.psi[i / 6][i % 6];
   __syncthreads();
 
   const uint32_t kw = ra.y;
@@ -1333,9 +1334,9 @@ k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__
   if (((ci.rs | (int64_t)cnt) & 1) == 0) {
     if (t == 0 && cnt > 0) bulk_store_image(out, s_vals, (uint32_t)cnt * 8u);
   } else {
-    for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
+    for (int i = t; i < cnt; i += NPC5) __stcs(out + i, s_vals[i]);
   }
-  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
+  for (int i = t; i < 2 * ng; i += NPC5) R[2 * (int64_t)ci.g0 + i] = s_res[i];
   if (next_cell >= 0) {
     const char *pb = reinterpret_cast<const char *>(cellpk + PK * (int64_t)next_cell);
     pf_l2(pb), pf_l2(pb + 128), pf_l2(pb + 256), pf_l2(pb + 8 * PK - 8);
@@ -1343,7 +1344,7 @@ k_assemble_u5(const WorkList wl, double *__restrict__ vals, double *__restrict__
 }
 
 // pressure rows of variant 4 (B, the structurally present zero p-p block, pressure mass), same scheme
-__global__ void __launch_bounds__(NPC, 6)
+__global__ void __launch_bounds__(NPC5, (6 * 128) / NPC5)
 k_assemble_p5(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, double *__restrict__ pm_vals, double *__restrict__ R,
               const double *__restrict__ geom, const AsmParams P) {
   extern __shared__ __align__(16) double s_vals[];
@@ -1351,7 +1352,7 @@ k_assemble_p5(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, dou
   __shared__ double s_Mp[3][3];
   const int t = threadIdx.x;
   const int64_t b = blockIdx.x;
-  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC + t);
+  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC5 + t);
   const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
   const ChunkInfo ci = wl.chunks[b];
   const bool work = (int)ra.x >= 0;
@@ -1364,13 +1365,13 @@ k_assemble_p5(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, dou
   {
     const int n2 = (cnt + mcnt + 1) >> 1;
     double2 *z = reinterpret_cast<double2 *>(s_vals);
-    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
+    for (int i = t; i < n2; i += NPC5) z[i] = make_double2(0.0, 0.0);
   }
   if (t < 36) {
     const int l = t / 6, m = (t % 6) / 2, cc = t % 2;
     s_Bh[m][l][cc] = c_fe2.Bh[l][m][cc];
   }
-  if (t >= 64 && t < 73) (&s_Mp[0][0])[t - 64] = (&c_fe2.Mp[0][0])[t - 64];
+  if (t >= 48 && t < 57) (&s_Mp[0][0])[t - 48] = (&c_fe2.Mp[0][0])[t - 48];
   __syncthreads();
   const uint32_t kw = ra.y;
   const int m = (int)(kw & 7u), round = (int)((kw >> 3) & 31u);
@@ -1413,10 +1414,10 @@ k_assemble_p5(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, dou
     __syncthreads();
   }
   double *out = vals + ci.rs, *mout = pm_vals + ci.ms;
-  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
-  for (int i = t; i < mcnt; i += NPC) __stcs(mout + i, s_pm[i]);
+  for (int i = t; i < cnt; i += NPC5) __stcs(out + i, s_vals[i]);
+  for (int i = t; i < mcnt; i += NPC5) __stcs(mout + i, s_pm[i]);
   // no statement of the reference tests the pressure space: R_p == 0
-  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
+  for (int i = t; i < ng; i += NPC5) R[n_own_u + ci.g0 + i] = 0.0;
 }
 
 // ---- K2: Neumann faces (cpp:315-336), one thread per boundary P2 node, faces in list order ------

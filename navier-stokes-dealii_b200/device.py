@@ -62,6 +62,7 @@ class DeviceProblem:
         dist.all_gather_object(handles, self.comm_ipc_handle())
         self.comm_set_peers(handles)
         dist.barrier()
+        self._peer_dist = dist   # close() releases the peer mappings collectively before freeing the mailbox
         return True
 
     # -- parameters -----------------------------------------------------------------------------
@@ -191,12 +192,23 @@ class DeviceProblem:
         return {"assemble": out[0], "dirichlet": out[1], "solve": out[2]}
 
     def close(self):
+        """Collective when the fused all-reduce is on (every rank must call it): the peers' mailbox mappings are
+        closed on every rank, then a barrier, and only then is any mailbox freed (CUDA IPC rule)."""
         if getattr(self, "_h", None):
+            dist = getattr(self, "_peer_dist", None)
+            if dist is not None:
+                self._L.nsg_comm_release_peers(self._h)
+                self._peer_dist = None
+                try:
+                    dist.barrier()
+                except Exception:
+                    pass
             self._L.nsg_destroy(self._h)
             self._h = None
 
     def __del__(self):
         try:
+            self._peer_dist = None   # no collectives from a finaliser
             self.close()
         except Exception:
             pass

@@ -17,7 +17,7 @@ for cap in caps:
     dev = pkg.DeviceProblem(part, 0)
     dev.set_params(neumann_id=neumann)
     dev.set_solution(sol); dev.set_solution_old(0.9 * sol)
-    for av, minb, pf in ((0, 0, 0), (4, 4, 0), (4, 4, -2)):
+    for av, minb, pf in ((4, 3, 0), (4, 4, 0), (4, 5, 0)):
         if True:
             os.environ["NSG_ASM3_MINB"] = str(minb)
             os.environ.pop("NSG_ASM_PF", None)

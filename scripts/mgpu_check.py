@@ -4,6 +4,7 @@ oracle on the same mesh in the SAME (part-major) global numbering."""
 import importlib
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -57,7 +58,7 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
         err = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
         good = err <= tol
         state["ok"] &= good
-        print(f"[rank {rank}] {name}: {what:28s} rel err {err:.3e} {'ok' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}] {time.strftime('%H:%M:%S')} {name}: {what:28s} rel err {err:.3e} {'ok' if good else 'FAIL'}", flush=True)
 
     Jo = o.get_matrix_values()
     jo_rows = np.concatenate([_reorder(part, Jo, rp, col, gr) for gr in own])
@@ -102,6 +103,9 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
 
 
 def main():
+    # a stuck collective must not hang the GPU box: dump every thread's Python stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MGPU_WATCHDOG_S", "240")), exit=True)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -127,15 +131,12 @@ def _reorder(part, Jo, rp, col, gr):
     return Jo[rp[gr]:rp[gr + 1]][np.argsort(lcols, kind="stable")]
 
 
-_G2L = {}
-
-
 def _loc(part, gcols):
-    key = id(part)
-    if key not in _G2L:
+    # cached ON the part object (a cache keyed by id(part) handed a later case the map of a collected object)
+    g2l = getattr(part, "_g2l_map", None)
+    if g2l is None:
         g2l = {int(g): i for i, g in enumerate(part.l2g)}
-        _G2L[key] = g2l
-    g2l = _G2L[key]
+        part._g2l_map = g2l
     return np.array([g2l[int(c)] for c in gcols])
 
 
