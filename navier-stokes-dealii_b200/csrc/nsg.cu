@@ -1261,7 +1261,7 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
     if (!has_blk[b]) continue;
     const int64_t r0 = b == 0 ? 0 : c->n_own_u, r1 = b == 0 ? c->n_own_u : c->n_own;
     if (r1 > r0) {
-      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, 1 << 30), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
+      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, 148 * 8), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
       NSG_LAUNCH_CHECK(c);
     }
     k_first_nonzero_diag_value<<<1, 1, 0, c->stream>>>(c->diag_pos, c->vals, c->first_idx + b, c->scal + 8 + b);

@@ -1543,10 +1543,18 @@ __global__ void k_diag_pos(int64_t n, const int64_t *__restrict__ rowptr, const 
 // (the minimum is unique, so the result does not depend on the execution order), value afterwards
 __global__ void k_first_nonzero_diag_index(int64_t r0, int64_t r1, const int64_t *__restrict__ diag_pos,
                                            const double *__restrict__ vals, unsigned long long *first_idx) {
-  const int64_t i = r0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= r1 || (unsigned long long)i >= *first_idx) return;
-  const int64_t p = diag_pos[i];
-  if (p >= 0 && vals[p] != 0.0) atomicMin(first_idx, (unsigned long long)i);
+  // persistent blocks walk the rows in increasing chunks and stop as soon as a smaller index is known: the
+  // answer is almost always within the first rows, so the scan costs one chunk per block instead of one
+  // block per 256 rows of the whole block (2.5 ms of the 85 M-DoF bench step before)
+  for (int64_t base = r0 + (int64_t)blockIdx.x * blockDim.x; base < r1; base += (int64_t)gridDim.x * blockDim.x) {
+    if ((unsigned long long)base >= *(volatile unsigned long long *)first_idx) return;
+    const int64_t i = base + threadIdx.x;
+    if (i < r1) {
+      const int64_t p = diag_pos[i];
+      if (p >= 0 && vals[p] != 0.0) atomicMin(first_idx, (unsigned long long)i);
+    }
+    __syncthreads();  // the block's own find is visible to its next test
+  }
 }
 __global__ void k_first_nonzero_diag_value(const int64_t *__restrict__ diag_pos, const double *__restrict__ vals,
                                            const unsigned long long *first_idx, double *out) {

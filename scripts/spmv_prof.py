@@ -1,0 +1,19 @@
+"""ncu target: a few default-variant SpMVs on the bench workload (mesh, levels as in bench.py)."""
+import importlib, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+pkg = importlib.import_module("navier-stokes-dealii_b200")
+MESH = sys.argv[1] if len(sys.argv) > 1 else "mesh2d"
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+m, d, part, (ld, lv), neumann, sol = bench.build_problem(pkg, MESH, L, 1, 0)
+dev = pkg.DeviceProblem(part, 0)
+dev.set_params(neumann_id=neumann)
+dev.set_solution(sol); dev.set_solution_old(0.9 * sol)
+dev.assemble()
+dev.set_delta(np.random.default_rng(0).standard_normal(part.n_own))
+nb = 12 * part.nnz_jac + 8 * part.n_loc + 8 * part.n_own + 8 * (part.n_own + 1)
+ms = dev.time_kernel(1, 4)
+print("cells", m.n_cells, "N", d.n, "nnz", part.nnz_jac, "algorithmic bytes", nb, "ms", ms, "GB/s", nb / ms / 1e6)
+dev.close()
