@@ -305,7 +305,8 @@ def main():
         for rec in json.load(open(tpath)):
             if rec["mesh"] == args.mesh and rec["levels"] == args.levels and rec["n_gpus"] == world:
                 traffic = rec["dram_bytes_per_launch"]
-    rl = {"bound": "hbm", "kernel": "k_spmv_vec8u<persistent> (SpMV variant 4: CSR, 8 lanes/row, prefetched row extents)",
+    rl = {"bound": "hbm", "kernel": "k_spmv_rowpair<persistent> (SpMV variant 7: CSR, 8 lanes per velocity-node row PAIR sharing one column "
+                                   "index and one x gather, prefetched row extents)",
           "achieved": spmv_bytes / spmv_ms / 1e6, "peak": hbm, "unit": "GB/s",
           "frac": spmv_bytes / spmv_ms / 1e6 / hbm, "traffic": traffic, "peak_source": hbm_src,
           "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,

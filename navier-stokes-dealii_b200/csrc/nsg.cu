@@ -636,7 +636,19 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
   else if (c->spmv_variant == 3)
     k_spmv_vec8u<false><<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  else if (c->spmv_variant == 4)
+  else if (c->spmv_variant == 8) {
+    static int per_sm8 = 0;
+    if (!per_sm8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k_spmv_rowpair2<true>, SPMV_THREADS, 0);
+    const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
+    k_spmv_rowpair2<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm8, 1)),
+                            SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  } else if (c->spmv_variant == 7) {
+    static int per_sm7 = 0;
+    if (!per_sm7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm7, k_spmv_rowpair<true>, SPMV_THREADS, 0);
+    const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
+    k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm7, 1)),
+                           SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
+  } else if (c->spmv_variant == 4)
   {
     static int per_sm = 0;
     if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_vec8u<true>, SPMV_THREADS, 0);
@@ -1022,7 +1034,7 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
       NSG_TRY(upload(c, &c->gitems, items.data(), c->n_items));
       NSG_CUDA(cudaStreamSynchronize(c->stream));
     }
-    c->spmv_variant = 4;  // fastest measured so far (profiles/r01_spmv_variants.md)
+    c->spmv_variant = c->have_paired ? 7 : 4;  // fastest measured (profiles/r01_summary.md); 7 needs the node-pair row structure
   }
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
@@ -1485,8 +1497,8 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   switch (key) {
     case 0:
-      if (value < 0 || value > 6) return fail(NSG_ERR_ARG, "spmv variant must be 0..6");
-      if ((value == 2 || value == 6) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
+      if (value < 0 || value > 8) return fail(NSG_ERR_ARG, "spmv variant must be 0..8");
+      if ((value == 2 || value == 6 || value == 7 || value == 8) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
       c->spmv_variant = value;
       for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
       c->graphs.clear();  // captured segments embed the SpMV kernel

@@ -413,6 +413,181 @@ k_spmv_paired_p(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict
   }
 }
 
+// Variant 7 ("row pairs"): the two rows of a velocity node have the SAME column list (full coupling of the two
+// components), so 8 lanes serve both rows at once: one column index and one x gather feed two matrix entries.
+// Index bytes of the velocity rows halve (12 -> 10 B per non-zero read from HBM) and so do the gather
+// instructions - the L1 wavefronts the kernel is bound by (ncu: LSU data pipe 77 %, long_scoreboard).  Lane
+// mapping and reduction tree per row are those of k_spmv_vec8u: bitwise the same y.
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+               const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
+  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t s = 0, e = 0;
+  if (g < n_groups) {
+    const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
+    s = rowptr[r], e = rowptr[r + 1];
+  }
+  while (true) {
+    int64_t sn = 0, en = 0;
+    const int64_t gn = g + G;
+    if (PERSISTENT && gn < n_groups) {
+      const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
+      sn = rowptr[r], en = rowptr[r + 1];
+    }
+    const bool pair = g < n_ugroups;
+    const int64_t len = pair ? e - s : 0;  // the second row of the node starts where the first one ends
+    double v0[8], v1[8];
+    int32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t p = s + l8 + 8 * k;
+      const bool in = p < e;
+      v0[k] = in ? __ldcs(vals + p) : 0.0;
+      v1[k] = (in && pair) ? __ldcs(vals + p + len) : 0.0;
+      c[k] = in ? __ldcs(col + p) : -1;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c[k] >= 0) {
+        const double xv = __ldg(x + c[k]);
+        acc0 += v0[k] * xv;
+        acc1 += v1[k] * xv;
+      }
+    for (int64_t p = s + l8 + 64; p < e; p += 8) {
+      const double xv = __ldg(x + __ldcs(col + p));
+      acc0 += __ldcs(vals + p) * xv;
+      if (pair) acc1 += __ldcs(vals + p + len) * xv;
+    }
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+    if (g < n_groups && l8 == 0) {
+      if (pair) {
+        y[2 * g] = acc0;
+        y[2 * g + 1] = acc1;
+      } else {
+        y[g + n_ugroups] = acc0;
+      }
+    }
+    if (!PERSISTENT) break;
+    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
+    g = gn, s = sn, e = en;
+    if (g >= n_groups) s = e = 0;
+  }
+}
+
+// Variant 8: variant 7 with two adjacent entries per lane and step (64-bit index loads, 128-bit value loads of the
+// first row) and ONE 128-bit gather of x when the two columns are the (2m, 2m+1) pair of a velocity node - which
+// they are for all velocity columns, since a row starts at an even position and velocity columns come in pairs.
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_rowpair2(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
+  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t s = 0, e = 0;
+  if (g < n_groups) {
+    const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
+    s = rowptr[r], e = rowptr[r + 1];
+  }
+  while (true) {
+    int64_t sn = 0, en = 0;
+    const int64_t gn = g + G;
+    if (PERSISTENT && gn < n_groups) {
+      const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
+      sn = rowptr[r], en = rowptr[r + 1];
+    }
+    const bool pair = g < n_ugroups;
+    const int64_t len = pair ? e - s : 0;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (pair) {  // velocity node: the row starts at an even position -> aligned 2-entry accesses
+      int2 c[4];
+      double2 v0[4];
+      double v1a[4], v1b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t p = s + 2 * l8 + 16 * k;
+        const bool in0 = p < e, in1 = p + 1 < e;
+        c[k] = make_int2(-1, -1), v0[k] = make_double2(0.0, 0.0), v1a[k] = v1b[k] = 0.0;
+        if (in0) {
+          c[k] = __ldcs(reinterpret_cast<const int2 *>(col + p));
+          v0[k] = __ldcs(reinterpret_cast<const double2 *>(vals + p));
+          v1a[k] = __ldcs(vals + p + len);
+          if (in1) v1b[k] = __ldcs(vals + p + len + 1);
+          else c[k].y = -1, v0[k].y = 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c[k].x >= 0) {
+          double x0, x1 = 0.0;
+          if (c[k].y == c[k].x + 1 && !(c[k].x & 1)) {
+            const double2 xx = __ldg(reinterpret_cast<const double2 *>(x + c[k].x));
+            x0 = xx.x, x1 = xx.y;
+          } else {
+            x0 = __ldg(x + c[k].x);
+            if (c[k].y >= 0) x1 = __ldg(x + c[k].y);
+          }
+          acc0 += v0[k].x * x0;
+          acc0 += v0[k].y * x1;
+          acc1 += v1a[k] * x0;
+          acc1 += v1b[k] * x1;
+        }
+      for (int64_t p = s + l8 + 64; p < e; p += 8) {
+        const double xv = __ldg(x + __ldcs(col + p));
+        acc0 += __ldcs(vals + p) * xv;
+        acc1 += __ldcs(vals + p + len) * xv;
+      }
+    } else {
+      double v[8];
+      int32_t c[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int64_t p = s + l8 + 8 * k;
+        const bool in = p < e;
+        v[k] = in ? __ldcs(vals + p) : 0.0;
+        c[k] = in ? __ldcs(col + p) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c[k] >= 0) acc0 += v[k] * __ldg(x + c[k]);
+      for (int64_t p = s + l8 + 64; p < e; p += 8) acc0 += __ldcs(vals + p) * __ldg(x + __ldcs(col + p));
+    }
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+    if (g < n_groups && l8 == 0) {
+      if (pair) {
+        y[2 * g] = acc0;
+        y[2 * g + 1] = acc1;
+      } else {
+        y[g + n_ugroups] = acc0;
+      }
+    }
+    if (!PERSISTENT) break;
+    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
+    g = gn, s = sn, e = en;
+    if (g >= n_groups) s = e = 0;
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

@@ -118,7 +118,7 @@ def test_spmv_parity_and_linearity(pkg):
     lin = dev.spmv(2.0 * x - 0.5 * y)
     assert np.abs(lin - (2.0 * ax - 0.5 * ay)).max() <= 1e-12 * np.abs(lin).max()
     assert np.array_equal(dev.spmv(x), ax)        # run-to-run deterministic
-    for variant in (0, 1, 2, 3, 4, 5, 6):            # the SpMV kernels differ only in summation order
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):       # the SpMV kernels differ only in summation order
         dev.set_tuning(0, variant)
         got = dev.spmv(x)
         assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), variant
@@ -399,3 +399,61 @@ def test_classical_gram_schmidt_option(pkg):
     b = dev.get_residual()
     assert np.linalg.norm(J @ res[1][2] - b) <= 1.5e-8 * np.linalg.norm(b)
     dev.close()
+
+
+@pytest.mark.parametrize("variant", [0, 4])
+def test_assembly_pattern_wider_than_the_mesh(pkg, variant):
+    """Edge case of the write-once assembly: a sparsity pattern with entries NO cell contributes to (a caller may pass
+    a wider pattern than make_sparsity_pattern). Those entries must read exactly 0 after every assembly - variant 4 has
+    no zero-fill pass (first-touch stores), its work-list builder must detect the uncovered entries - and all the
+    others must be what the exact pattern gives."""
+    import copy
+    m, d, part, calls, neumann, inlet = build(pkg, "square")
+    sol = analytic_state(d, 0.03)
+
+    def assemble(p):
+        dev = pkg.DeviceProblem(p, 0)
+        dev.set_tuning(1, variant)
+        dev.set_params(nu=0.01, neumann_id=neumann)
+        dev.set_solution(sol)
+        dev.set_solution_old(0.9 * sol)
+        dev.assemble()
+        dev.assemble()      # twice: stale shared-memory images must not leak into the uncovered entries
+        out = dev.get_matrix_values(), dev.get_pm_values(), dev.get_residual()
+        dev.close()
+        return out
+
+    J0, M0, R0 = assemble(part)
+    # widen: give velocity node 0 (rows 0,1) the column pair of a far-away velocity node, and pressure row 0 one more
+    # velocity pair and one more pressure column
+    rp, col = part.jac_rowptr.copy(), part.jac_col.copy()
+    prp, pcol = part.pm_rowptr.copy(), part.pm_col.copy()
+    n_u, n = part.n_own_u, part.n_own
+
+    def widen(rp, col, rows, extra):
+        new_rp, new_col, is_new = [0], [], []
+        for r in range(len(rp) - 1):
+            c = list(col[rp[r]:rp[r + 1]])
+            add = [e for e in extra if e not in c] if r in rows else []
+            merged = sorted(c + add)
+            new_col += merged
+            is_new += [x in add for x in merged]
+            new_rp.append(len(new_col))
+        return np.array(new_rp, np.int64), np.array(new_col, np.int32), np.array(is_new, bool)
+
+    far = 2 * ((n_u // 2) - 1)                      # last velocity node: not coupled to node 0 on this mesh
+    assert far not in col[rp[0]:rp[1]]
+    rp1, col1, new1 = widen(rp, col, {0, 1}, [far, far + 1])
+    rp2, col2, new2 = widen(rp1, col1, {n_u}, [far, far + 1, n - 1])
+    new_j = np.zeros(len(col2), bool)
+    # map the flags of the first widening through the second one
+    keep2 = ~new2
+    new_j[keep2] = new1
+    new_j[new2] = True
+    prp2, pcol2, new_m = widen(prp, pcol, {n_u}, [n - 1])
+    wide = copy.copy(part)
+    wide.jac_rowptr, wide.jac_col, wide.nnz_jac = rp2, col2, len(col2)
+    wide.pm_rowptr, wide.pm_col, wide.nnz_pm = prp2, pcol2, len(pcol2)
+    J1, M1, R1 = assemble(wide)
+    assert new_j.sum() == 7 and not J1[new_j].any() and not M1[new_m].any()
+    assert np.array_equal(J1[~new_j], J0) and np.array_equal(M1[~new_m], M0) and np.array_equal(R1, R0)
