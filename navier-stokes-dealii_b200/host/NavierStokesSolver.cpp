@@ -330,34 +330,81 @@ std::vector<double> NavierStokesSolver::solution_owned_values() const {
 void NavierStokesSolver::output(const unsigned int &time_step, const double &t) const {
   pcout << "===============================================" << std::endl;
   if (output_dir.empty()) return;
-  std::vector<double> own = solution_owned_values();
   nst_part_info I;
   nst_part_get_info(part, &I);
-  std::ostringstream name;
-  name << output_dir << "/output-" << std::setw(4) << std::setfill('0') << time_step << ".rank" << mpi_rank << ".vtk";
-  std::ofstream f(name.str());
-  if (!f) fail("cannot write " + name.str());
+  // the ghosted `solution` DataOut reads (cpp:697-700): owned entries + ghost layer
+  std::vector<double> sol((size_t)std::max<int64_t>(I.n_own_u + I.n_own_p + I.n_ghost_u + I.n_ghost_p, 1));
+  NSG_CALL(nsg_get_solution_ghosted(dev, sol.data()));
   const int32_t *cv = nst_part_cell_vertices(part), *cd = nst_part_cell_dofs(part);
   const double *xy = nst_part_xy(part);
   const uint8_t *owned = nst_part_cell_owned(part);
   std::vector<int64_t> cells;
   for (int64_t c = 0; c < I.n_cells; ++c)
     if (owned[c]) cells.push_back(c);
-  f << "# vtk DataFile Version 3.0\nNavier-Stokes t=" << t << "\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS " << 3 * cells.size()
-    << " double\n";
-  for (int64_t c : cells)
-    for (int k = 0; k < 3; ++k) f << xy[2 * cv[3 * c + k]] << " " << xy[2 * cv[3 * c + k] + 1] << " 0\n";
-  f << "CELLS " << cells.size() << " " << 4 * cells.size() << "\n";
-  for (size_t i = 0; i < cells.size(); ++i) f << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << "\n";
-  f << "CELL_TYPES " << cells.size() << "\n";
-  for (size_t i = 0; i < cells.size(); ++i) f << "5\n";
-  auto val = [&](int32_t ldof) { return ldof < n_own ? own[ldof] : std::nan(""); };  // ghosts belong to another rank's file
-  f << "POINT_DATA " << 3 * cells.size() << "\nVECTORS velocity double\n";
-  for (int64_t c : cells)
-    for (int k = 0; k < 3; ++k) f << val(cd[15 * c + 3 * k]) << " " << val(cd[15 * c + 3 * k + 1]) << " 0\n";
+  const size_t T = cells.size();
+  std::ostringstream stem;
+  stem << "output-" << std::setw(4) << std::setfill('0') << time_step;
+  // one patch of three nodes per owned cell, as DataOut::build_patches with filter_duplicate_vertices = false
+  // (cpp:685-719): points, triangles, velocity (3-component), pressure, partitioning
+  std::vector<double> pts(6 * T), vel(9 * T, 0.0), pres(3 * T), partn(3 * T, (double)mpi_rank);
+  std::vector<int32_t> tri(3 * T);
+  for (size_t i = 0; i < T; ++i) {
+    const int64_t c = cells[i];
+    for (int k = 0; k < 3; ++k) {
+      pts[6 * i + 2 * k] = xy[2 * cv[3 * c + k]], pts[6 * i + 2 * k + 1] = xy[2 * cv[3 * c + k] + 1];
+      vel[9 * i + 3 * k] = sol[cd[15 * c + 3 * k]], vel[9 * i + 3 * k + 1] = sol[cd[15 * c + 3 * k + 1]];
+      pres[3 * i + k] = sol[cd[15 * c + 3 * k + 2]];
+      tri[3 * i + k] = (int32_t)(3 * i + k);
+    }
+  }
+  // (1) XDMF + raw little-endian heavy data (HDF5 is not available: Format="Binary" with Seek offsets); the layout is
+  //     the one navier-stokes-dealii_b200/output.py writes and reads back
+  {
+    const std::string bin = stem.str() + ".rank" + std::to_string(mpi_rank) + ".bin";
+    std::ofstream fb(output_dir + "/" + bin, std::ios::binary);
+    if (!fb) fail("cannot write " + output_dir + "/" + bin);
+    size_t off[5], o = 0;
+    auto put = [&](const void *ptr, size_t bytes, int slot) {
+      off[slot] = o;
+      fb.write((const char *)ptr, (std::streamsize)bytes);
+      o += bytes;
+    };
+    put(pts.data(), 8 * pts.size(), 0), put(tri.data(), 4 * tri.size(), 1), put(vel.data(), 8 * vel.size(), 2);
+    put(pres.data(), 8 * pres.size(), 3), put(partn.data(), 8 * partn.size(), 4);
+    const std::string xname = output_dir + "/" + stem.str() + (mpi_size > 1 ? ".rank" + std::to_string(mpi_rank) : std::string()) + ".xdmf";
+    std::ofstream fx(xname);
+    if (!fx) fail("cannot write " + xname);
+    auto item = [&](const std::string &dims, const char *type, int prec, int slot) {
+      std::ostringstream q;
+      q << "<DataItem Dimensions=\"" << dims << "\" NumberType=\"" << type << "\" Precision=\"" << prec
+        << "\" Format=\"Binary\" Endian=\"Little\" Seek=\"" << off[slot] << "\">" << bin << "</DataItem>";
+      return q.str();
+    };
+    const std::string n3 = std::to_string(3 * T);
+    fx << "<?xml version=\"1.0\" ?>\n<!DOCTYPE Xdmf SYSTEM \"Xdmf.dtd\" []>\n<Xdmf Version=\"3.0\">\n <Domain>\n"
+       << "  <Grid Name=\"CellTime\" GridType=\"Collection\" CollectionType=\"Temporal\">\n"
+       << "   <Grid Name=\"mesh\" GridType=\"Collection\" CollectionType=\"Spatial\">\n    <Time Value=\"" << std::setprecision(17) << t
+       << "\"/>\n    <Grid Name=\"rank" << mpi_rank << "\" GridType=\"Uniform\">\n"
+       << "     <Topology TopologyType=\"Triangle\" NumberOfElements=\"" << T << "\">" << item(std::to_string(T) + " 3", "Int", 4, 1)
+       << "</Topology>\n     <Geometry GeometryType=\"XY\">" << item(n3 + " 2", "Float", 8, 0) << "</Geometry>\n"
+       << "     <Attribute Name=\"velocity\" AttributeType=\"Vector\" Center=\"Node\">" << item(n3 + " 3", "Float", 8, 2) << "</Attribute>\n"
+       << "     <Attribute Name=\"pressure\" AttributeType=\"Scalar\" Center=\"Node\">" << item(n3, "Float", 8, 3) << "</Attribute>\n"
+       << "     <Attribute Name=\"partitioning\" AttributeType=\"Scalar\" Center=\"Node\">" << item(n3, "Float", 8, 4) << "</Attribute>\n"
+       << "    </Grid>\n   </Grid>\n  </Grid>\n </Domain>\n</Xdmf>\n";
+  }
+  // (2) the same patches as legacy VTK (one self-contained ASCII file per rank and step)
+  std::ofstream f(output_dir + "/" + stem.str() + ".rank" + std::to_string(mpi_rank) + ".vtk");
+  if (!f) fail("cannot write the .vtk file in " + output_dir);
+  f << "# vtk DataFile Version 3.0\nNavier-Stokes t=" << t << "\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS " << 3 * T << " double\n";
+  for (size_t i = 0; i < 3 * T; ++i) f << pts[2 * i] << " " << pts[2 * i + 1] << " 0\n";
+  f << "CELLS " << T << " " << 4 * T << "\n";
+  for (size_t i = 0; i < T; ++i) f << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << "\n";
+  f << "CELL_TYPES " << T << "\n";
+  for (size_t i = 0; i < T; ++i) f << "5\n";
+  f << "POINT_DATA " << 3 * T << "\nVECTORS velocity double\n";
+  for (size_t i = 0; i < 3 * T; ++i) f << vel[3 * i] << " " << vel[3 * i + 1] << " 0\n";
   f << "SCALARS pressure double 1\nLOOKUP_TABLE default\n";
-  for (int64_t c : cells)
-    for (int k = 0; k < 3; ++k) f << val(cd[15 * c + 3 * k + 2]) << "\n";
-  f << "CELL_DATA " << cells.size() << "\nSCALARS partitioning int 1\nLOOKUP_TABLE default\n";
-  for (size_t i = 0; i < cells.size(); ++i) f << mpi_rank << "\n";
+  for (size_t i = 0; i < 3 * T; ++i) f << pres[i] << "\n";
+  f << "CELL_DATA " << T << "\nSCALARS partitioning int 1\nLOOKUP_TABLE default\n";
+  for (size_t i = 0; i < T; ++i) f << mpi_rank << "\n";
 }

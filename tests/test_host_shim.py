@@ -58,13 +58,23 @@ def test_app_matches_python_driver(pkg):
 
 @pytest.mark.gpu
 def test_app_writes_output_files(tmp_path):
-    """N2: output() keeps the reference's one-file-per-step contract (cpp:681-728) with a minimal VTK writer."""
+    """N2: output() keeps the reference's one-file-per-step contract (cpp:681-728) as XDMF + raw binary heavy data and as legacy VTK."""
     env = dict(os.environ, NS_MESH=mesh_path("square_h0.1.msh"), NS_T="0.1", NS_NEUMANN_ID="1", NS_INLET_ID="0",
                NS_WALL_IDS="2,3", NS_OUTPUT_DIR=str(tmp_path))
     r = subprocess.run([os.path.join(HOST, "ns_app")], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     files = sorted(os.listdir(tmp_path))
-    assert files == ["output-0000.rank0.vtk", "output-0001.rank0.vtk", "output-0002.rank0.vtk"]
-    txt = open(os.path.join(tmp_path, files[-1])).read()
+    assert [f for f in files if f.endswith(".vtk")] == ["output-0000.rank0.vtk", "output-0001.rank0.vtk", "output-0002.rank0.vtk"]
+    assert [f for f in files if f.endswith(".xdmf")] == ["output-0000.xdmf", "output-0001.xdmf", "output-0002.xdmf"]
+    txt = open(os.path.join(tmp_path, "output-0002.rank0.vtk")).read()
     assert "CELLS 200 800" in txt and "VECTORS velocity double" in txt and "SCALARS pressure double 1" in txt
-    assert "SCALARS partitioning int 1" in txt
+    assert "SCALARS partitioning int 1" in txt and "nan" not in txt
+    # the XDMF + raw-binary files of the C++ host are the ones the Python mirror reads back
+    import importlib
+    import numpy as np
+    xout = importlib.import_module("navier-stokes-dealii_b200.output")
+    t, grids = xout.read_back(str(tmp_path), "output-0002.xdmf")
+    r = grids["rank0"]
+    assert abs(t - 0.1) < 1e-12 and r["cells"].shape == (200, 3) and r["points"].shape == (600, 2)
+    assert np.isfinite(r["velocity"]).all() and np.abs(r["velocity"][:, :2]).max() > 0 and not r["velocity"][:, 2].any()
+    assert (r["partitioning"] == 0).all()
