@@ -170,8 +170,8 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * 2 paired CSR (pair-compressed column index); 3 = 1 with all loads of a row in flight; 4 = 3
  * persistent with prefetched row extents; 5 bulk-async-copy (TMA) stream; 6 = 2 in the form of 4; 7 (default) = 4
  * serving the two rows of a velocity node together (they have the same column list: one index load and one x
- * gather feed two entries; bitwise the same result as 4); 8 = 7 with two entries per lane and step. Measured
- * rates: profiles/.
+ * gather feed two entries; bitwise the same result as 4); 8 = 7 with two entries per lane and step; 9 = 7 reading a
+ * compact copy of the column index (built on demand; fewer bytes, measured slower). Measured rates: profiles/.
  * key 1 = assembly kernel variant: 0 literal 7-point quadrature loop for every term, as the reference sums
  * them; 1 the same integrals with the quadrature sum factored into pre-integrated reference-cell tables;
  * 2 = 1 on per-cell packets (everything that depends on the cell only is computed once per cell by a streaming

@@ -636,7 +636,13 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
   else if (c->spmv_variant == 3)
     k_spmv_vec8u<false><<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  else if (c->spmv_variant == 8) {
+  else if (c->spmv_variant == 9) {
+    static int per_sm9 = 0;
+    if (!per_sm9) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, k_spmv_rowpair_c<true>, SPMV_THREADS, 0);
+    const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
+    k_spmv_rowpair_c<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm9, 1)),
+                             SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col7, c->vals, x_with_ghosts, y, state);
+  } else if (c->spmv_variant == 8) {
     static int per_sm8 = 0;
     if (!per_sm8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k_spmv_rowpair2<true>, SPMV_THREADS, 0);
     const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
@@ -941,7 +947,7 @@ void nsg_destroy(nsg_ctx *c) {
     if (m) cudaIpcCloseMemHandle(m);
   dev_free(c->mailbox), dev_free(c->ar_seq);
   if (c->comm) nccl_api().CommDestroy(c->comm);
-  dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
+  dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->col7), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p), free_worklist(c->wl_u5), free_worklist(c->wl_p5);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
@@ -1497,8 +1503,19 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   switch (key) {
     case 0:
-      if (value < 0 || value > 8) return fail(NSG_ERR_ARG, "spmv variant must be 0..8");
-      if ((value == 2 || value == 6 || value == 7 || value == 8) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
+      if (value < 0 || value > 9) return fail(NSG_ERR_ARG, "spmv variant must be 0..9");
+      if ((value == 2 || value == 6 || value == 7 || value == 8 || value == 9) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
+      if (value == 9 && !c->col7) {  // compact column index: the shared column list of a velocity node once (built on demand)
+        const int64_t n = c->n_own, nu = c->n_own_u;
+        const int64_t n7 = (c->h_rowptr[nu] >> 1) + (c->h_rowptr[n] - c->h_rowptr[nu]);
+        NSG_TRY(dev_alloc(&c->col7, n7 + 16));
+        NSG_CUDA(cudaMemsetAsync(c->col7, 0, 4 * (size_t)(n7 + 16), c->stream));
+        const int64_t n_groups = nu / 2 + c->n_own_p;
+        if (n_groups > 0) {
+          k_build_col7<<<grid_for(n_groups * 32, 256, 1 << 30), 256, 0, c->stream>>>(nu / 2, n, c->rowptr, c->col, c->col7);
+          NSG_LAUNCH_CHECK(c);
+        }
+      }
       c->spmv_variant = value;
       for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
       c->graphs.clear();  // captured segments embed the SpMV kernel

@@ -182,6 +182,7 @@ struct nsg_ctx {
   // device CSR
   int64_t *rowptr = nullptr, *pm_rowptr = nullptr;
   int32_t *col = nullptr, *pm_col = nullptr;
+  int32_t *col7 = nullptr;  // compact column index of SpMV variant 9 (one list per velocity node pair, then the pressure rows)
   double *vals = nullptr, *pm_vals = nullptr;
   int32_t *spmv_chunk_rows = nullptr;
   int64_t *diag_pos = nullptr;

@@ -486,6 +486,94 @@ k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ ro
   }
 }
 
+// Variant 9: variant 7 reading a COMPACT copy of the column index that stores the shared column list of a
+// velocity node once (col7: the first row of every node pair, then the pressure rows; built once by
+// k_build_col7).  Variant 7 skips the second row's indices but they sit in the same DRAM lines as the values
+// around them, so its DRAM traffic stays at 12 B per non-zero; with the compact copy the index really costs
+// 2 B per velocity non-zero.  The position of a group's list needs no pointer array: rows 2g and 2g+1 have equal
+// lengths, so list(g) starts at rowptr[2g]/2, and pressure row r at rowptr[n_u]/2 + rowptr[r] - rowptr[n_u].
+__global__ void k_build_col7(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                             int32_t *__restrict__ col7) {
+  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  const int64_t half = rowptr[2 * n_ugroups] >> 1;
+  const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
+  const int64_t s = rowptr[r], e = rowptr[r + 1];
+  const int64_t dst = g < n_ugroups ? (s >> 1) : half + (s - rowptr[2 * n_ugroups]);
+  for (int64_t i = lane; i < e - s; i += 32) col7[dst + i] = col[s + i];
+}
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_rowpair_c(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col7,
+                 const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                 const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
+  const int64_t nnz_u = rowptr[2 * n_ugroups], half = nnz_u >> 1;
+  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t s = 0, e = 0;
+  if (g < n_groups) {
+    const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
+    s = rowptr[r], e = rowptr[r + 1];
+  }
+  while (true) {
+    int64_t sn = 0, en = 0;
+    const int64_t gn = g + G;
+    if (PERSISTENT && gn < n_groups) {
+      const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
+      sn = rowptr[r], en = rowptr[r + 1];
+    }
+    const bool pair = g < n_ugroups;
+    const int64_t len = pair ? e - s : 0;
+    const int64_t coff = (pair ? (s >> 1) : half + (s - nnz_u)) - s;  // col7[coff + p] = column of entry p of the group's first row
+    double v0[8], v1[8];
+    int32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t p = s + l8 + 8 * k;
+      const bool in = p < e;
+      v0[k] = in ? __ldcs(vals + p) : 0.0;
+      v1[k] = (in && pair) ? __ldcs(vals + p + len) : 0.0;
+      c[k] = in ? __ldcs(col7 + coff + p) : -1;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c[k] >= 0) {
+        const double xv = __ldg(x + c[k]);
+        acc0 += v0[k] * xv;
+        acc1 += v1[k] * xv;
+      }
+    for (int64_t p = s + l8 + 64; p < e; p += 8) {
+      const double xv = __ldg(x + __ldcs(col7 + coff + p));
+      acc0 += __ldcs(vals + p) * xv;
+      if (pair) acc1 += __ldcs(vals + p + len) * xv;
+    }
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+    if (g < n_groups && l8 == 0) {
+      if (pair) {
+        y[2 * g] = acc0;
+        y[2 * g + 1] = acc1;
+      } else {
+        y[g + n_ugroups] = acc0;
+      }
+    }
+    if (!PERSISTENT) break;
+    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
+    g = gn, s = sn, e = en;
+    if (g >= n_groups) s = e = 0;
+  }
+}
+
 // Variant 8: variant 7 with two adjacent entries per lane and step (64-bit index loads, 128-bit value loads of the
 // first row) and ONE 128-bit gather of x when the two columns are the (2m, 2m+1) pair of a velocity node - which
 // they are for all velocity columns, since a row starts at an even position and velocity columns come in pairs.

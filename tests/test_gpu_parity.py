@@ -118,7 +118,7 @@ def test_spmv_parity_and_linearity(pkg):
     lin = dev.spmv(2.0 * x - 0.5 * y)
     assert np.abs(lin - (2.0 * ax - 0.5 * ay)).max() <= 1e-12 * np.abs(lin).max()
     assert np.array_equal(dev.spmv(x), ax)        # run-to-run deterministic
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):       # the SpMV kernels differ only in summation order
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):       # the SpMV kernels differ only in summation order
         dev.set_tuning(0, variant)
         got = dev.spmv(x)
         assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), variant
