@@ -67,7 +67,7 @@ class NavierStokesSolver:
     dim = 2  # hpp:411
 
     def __init__(self, degree_velocity, degree_pressure, T, deltat, params=None, device=0, rank=0, world_size=1,
-                 comm_unique_id=None, stream=None, verbose=True, gather_objects=None):
+                 comm_unique_id=None, stream=None, verbose=True, gather_objects=None, dist=None):
         if (degree_velocity, degree_pressure) != (2, 1):
             raise ValueError("the B200 path implements the reference's P2-P1 Taylor-Hood pair (main.cpp:9-10)")
         self.T = float(T)
@@ -78,6 +78,15 @@ class NavierStokesSolver:
         # P > 1: callable(obj) -> [obj of rank 0, ..., obj of rank P-1] (e.g. torch.distributed.all_gather_object), used
         # by output() so that rank 0 can describe every rank's heavy-data file in the one .xdmf
         self._gather_objects = gather_objects
+        # P > 1: an initialised torch.distributed module; switches the Krylov all-reduces to the fused NVLink path and
+        # provides the object gather of output()
+        self._dist = dist
+        if dist is not None and gather_objects is None:
+            def _gather(obj):
+                out = [None] * dist.get_world_size()
+                dist.all_gather_object(out, obj)
+                return out
+            self._gather_objects = _gather
         self.verbose = verbose and rank == 0
         self.time = 0.0
         self.history = []        # (time_step, newton_iter, residual_norm, gmres_its)
@@ -112,6 +121,8 @@ class NavierStokesSolver:
         self.dev = DeviceProblem(self.part, self.device, self._stream)
         if self.world_size > 1:
             self.dev.comm_init(self.rank, self.world_size, self._uid)
+            if self._dist is not None:
+                self.dev.enable_peer_allreduce(self._dist)
         self._push_params(stokes=False)
         return self
 
