@@ -182,6 +182,10 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).
  * key 4 = triangular solves of the ILU(0) preconditioners: 0 one launch per dependency level; 1 (default) one
  * launch per solve, rows wait on the completion stamps of the rows they depend on (bitwise the same result).
+ * key 5 = the whole identity-preconditioned GMRES solve as ONE cooperative kernel (vector entries in registers across
+ * the Gram-Schmidt chain, one stamped-slot exchange per inner product; one rank, modified Gram-Schmidt): 0 off, 1 (default) for systems
+ * of up to 65 536 unknowns (the meshes the reference ships: 2x faster there), 2 whenever the system fits (up to 148 x 256 x 8 unknowns). Same algorithm and scalars as
+ * the multi-kernel path; the inner-product sums are partitioned differently (agreement to rounding, not bitwise).
  * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 

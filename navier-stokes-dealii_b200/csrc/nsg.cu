@@ -875,6 +875,55 @@ static int get_vec(nsg_ctx *c, const double *dev, double *host, int64_t n) {
 
 #include "nsg_krylov.cuh"
 #include "nsg_precond.cuh"
+#include "nsg_gmres_fused.cuh"
+
+
+namespace nsg {
+// ---- whole identity-preconditioned GMRES solve as one cooperative kernel (small meshes; nsg_gmres_fused.cuh) ----
+static bool gmres_fused_applicable(const nsg_ctx *c, int32_t precond) {
+  if (c->gmres_fused == 0 || precond != NSG_PRECOND_IDENTITY || c->n_ranks != 1 || c->orthogonalization != 0) return false;
+  if (c->n_own <= 0) return false;
+  const int64_t limit = c->gmres_fused == 2 ? (int64_t)148 * GF_THREADS * GF_MAX_EPT : c->gmres_fused_max_n;
+  return c->n_own <= std::min<int64_t>(limit, (int64_t)148 * GF_THREADS * GF_MAX_EPT);
+}
+static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int n_tmp, int hist_cap, GmresResult *out) {
+  int64_t n = c->n_own;
+  const int grid = (int)std::min<int64_t>(148, (n + GF_THREADS - 1) / GF_THREADS);
+  const int64_t T = (int64_t)grid * GF_THREADS;
+  const int ept = (int)((n + T - 1) / T);
+  if (!c->gf_partials) {  // [2][148] {value, epoch} words + the epoch counter, zeroed once
+    NSG_TRY(dev_alloc(&c->gf_partials, 2 * (2 * 148) + 8));
+    NSG_CUDA(cudaMemsetAsync(c->gf_partials, 0, sizeof(double) * (2 * (2 * 148) + 8), c->stream));
+  }
+  // tolerance = rel_tol * ||R|| and the scalar state, exactly as gmres_core sets them up
+  NSG_TRY(dev_dot(c, n, c->R, c->R, &c->ctl->nrm2, nullptr));
+  k_gmres_init<<<1, 1, 0, c->stream>>>(c->ctl, rel_tol, max_steps, n_tmp, hist_cap);
+  NSG_LAUNCH_CHECK(c);
+  const int64_t *rowptr = c->rowptr;
+  const int32_t *col = c->col;
+  const double *vals = c->vals, *b = c->R;
+  double *basis = c->basis, *hist = c->hist;
+  ulonglong2 *slots = reinterpret_cast<ulonglong2 *>(c->gf_partials);
+  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->gf_partials + 2 * (2 * 148));
+  int64_t S = c->stride;
+  GmresCtl *ctl = c->ctl;
+  void *args[] = {&n, &rowptr, &col, &vals, &x, &b, &basis, &S, &n_tmp, &ctl, &hist, &slots, &epoch_ctr};
+  const void *fn = ept <= 1 ? (const void *)k_gmres_solve_fused<1>
+                 : ept <= 2 ? (const void *)k_gmres_solve_fused<2>
+                 : ept <= 4 ? (const void *)k_gmres_solve_fused<4>
+                            : (const void *)k_gmres_solve_fused<8>;
+  int per_sm = 0;
+  NSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, GF_THREADS, 0));
+  if (per_sm < 1) return fail(NSG_ERR_CUDA, "the fused GMRES kernel does not fit an SM");
+  NSG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GF_THREADS), args, 0, c->stream));
+  c->launches++;
+  NSG_TRY(read_ctl_header(c, c->ctl, c->h_ctl));
+  out->its = c->h_ctl->accumulated;
+  out->res = c->h_ctl->rho;
+  out->ok = (c->h_ctl->state & 0xff) == 1;
+  return NSG_OK;
+}
+}  // namespace nsg
 
 using namespace nsg;
 
@@ -945,7 +994,7 @@ void nsg_destroy(nsg_ctx *c) {
   c->graphs.clear();
   for (void *m : c->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
-  dev_free(c->mailbox), dev_free(c->ar_seq);
+  dev_free(c->mailbox), dev_free(c->ar_seq), dev_free(c->gf_partials);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->col7), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
@@ -1339,8 +1388,11 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   Op P = [c, precond](double *d, double *s, const int32_t *) { return precond_vmult(c, precond, d, s); };
   GmresResult r;
   c->inner_its = 0;
-  NSG_TRY(gmres_core(c, Range{0, c->n_own}, A, precond == NSG_PRECOND_IDENTITY ? nullptr : &P, x, c->R, c->R, rel_tol, max_it, n_tmp,
-                     c->basis, c->ctl, c->h_ctl, c->hist, (int)hist_cap, precond == NSG_PRECOND_IDENTITY, &r));
+  if (gmres_fused_applicable(c, precond))
+    NSG_TRY(gmres_fused(c, x, rel_tol, max_it, n_tmp, (int)hist_cap, &r));
+  else
+    NSG_TRY(gmres_core(c, Range{0, c->n_own}, A, precond == NSG_PRECOND_IDENTITY ? nullptr : &P, x, c->R, c->R, rel_tol, max_it, n_tmp,
+                       c->basis, c->ctl, c->h_ctl, c->hist, (int)hist_cap, precond == NSG_PRECOND_IDENTITY, &r));
   if (its_out) *its_out = r.its;
   if (res_out) *res_out = r.res;
   c->h_hist.resize(std::min<int64_t>(r.its, c->hist_cap));
@@ -1522,6 +1574,10 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       return NSG_OK;
     case 2:
       c->use_graphs = value != 0;
+      return NSG_OK;
+    case 5:
+      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "fused GMRES must be 0 (off), 1 (small systems) or 2 (whenever it fits)");
+      c->gmres_fused = value;
       return NSG_OK;
     case 4:
       if (value < 0 || value > 1) return fail(NSG_ERR_ARG, "ILU solve variant must be 0 (one launch per level) or 1 (single launch)");

@@ -934,7 +934,7 @@ __device__ inline int32_t gm_check(const GmresCtl *c, int step, double val) {
   return 0;
 }
 // cycle start: rho = ||v0||, check, gamma(0) = rho, 1/rho for the scaling kernel
-__global__ void k_gmres_cycle_start(GmresCtl *c) {
+__device__ inline void gm_cycle_start_dev(GmresCtl *c) {
   if (c->state != 0) return;
   const double rho = sqrt(c->nrm2);
   c->rho = rho;
@@ -944,8 +944,9 @@ __global__ void k_gmres_cycle_start(GmresCtl *c) {
   c->inv_s = 1.0 / rho;
   for (int i = 0; i < GM_MAX_TMP; ++i) c->h[i] = 0.0;
 }
+__global__ void k_gmres_cycle_start(GmresCtl *c) { gm_cycle_start_dev(c); }
 // after the orthogonalisation of inner step `inner`: h(inner+1) = s, Givens, residual estimate
-__global__ void k_gmres_step(GmresCtl *c, int inner, int reorth, double *hist) {
+__device__ inline void gm_step_dev(GmresCtl *c, int inner, int reorth, double *hist) {
   if (c->state != 0) return;
   const int ld = GM_MAX_TMP;
   c->accumulated += 1;
@@ -974,8 +975,9 @@ __global__ void k_gmres_step(GmresCtl *c, int inner, int reorth, double *hist) {
   c->state = gm_check(c, c->accumulated, rho);
   if (c->state != 0) c->state |= 0x100;  // finished inside this cycle: the update below must still run
 }
+__global__ void k_gmres_step(GmresCtl *c, int inner, int reorth, double *hist) { gm_step_dev(c, inner, reorth, hist); }
 // H1.backward(h, gamma)
-__global__ void k_gmres_backsolve(GmresCtl *c) {
+__device__ inline void gm_backsolve_dev(GmresCtl *c) {
   const int ld = GM_MAX_TMP;
   const int dim = c->dim;
   for (int i = dim - 1; i >= 0; --i) {
@@ -984,5 +986,6 @@ __global__ void k_gmres_backsolve(GmresCtl *c) {
     c->y[i] = s / c->H[i * ld + i];
   }
 }
+__global__ void k_gmres_backsolve(GmresCtl *c) { gm_backsolve_dev(c); }
 
 }  // namespace nsg
