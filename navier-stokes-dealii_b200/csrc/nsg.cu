@@ -892,8 +892,8 @@ static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int
   const int64_t T = (int64_t)grid * GF_THREADS;
   const int ept = (int)((n + T - 1) / T);
   if (!c->gf_partials) {  // [2][148] {value, epoch} words + the epoch counter, zeroed once
-    NSG_TRY(dev_alloc(&c->gf_partials, 2 * (2 * 148) + 8));
-    NSG_CUDA(cudaMemsetAsync(c->gf_partials, 0, sizeof(double) * (2 * (2 * 148) + 8), c->stream));
+    NSG_TRY(dev_alloc(&c->gf_partials, 2 * (2 * 148 + 1) + 8));
+    NSG_CUDA(cudaMemsetAsync(c->gf_partials, 0, sizeof(double) * (2 * (2 * 148 + 1) + 8), c->stream));
   }
   // tolerance = rel_tol * ||R|| and the scalar state, exactly as gmres_core sets them up
   NSG_TRY(dev_dot(c, n, c->R, c->R, &c->ctl->nrm2, nullptr));
@@ -904,7 +904,7 @@ static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int
   const double *vals = c->vals, *b = c->R;
   double *basis = c->basis, *hist = c->hist;
   ulonglong2 *slots = reinterpret_cast<ulonglong2 *>(c->gf_partials);
-  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->gf_partials + 2 * (2 * 148));
+  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->gf_partials + 2 * (2 * 148 + 1));
   int64_t S = c->stride;
   GmresCtl *ctl = c->ctl;
   void *args[] = {&n, &rowptr, &col, &vals, &x, &b, &basis, &S, &n_tmp, &ctl, &hist, &slots, &epoch_ctr};

@@ -37,6 +37,7 @@ __device__ __forceinline__ double gf_warp_allsum(double v) {  // every lane ends
 // alternate between two halves; a half is reused two reductions later, when every CTA is provably past reading it
 // (it had to publish the reduction in between).  Only scalars travel this way; whenever vector entries written by
 // other threads are read next, a real grid barrier follows.
+template <bool FENCE = false>
 __device__ __forceinline__ double gf_grid_sum(double v, ulonglong2 *slots, unsigned long long &epoch, double *s_red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   ++epoch;
@@ -49,6 +50,9 @@ __device__ __forceinline__ double gf_grid_sum(double v, ulonglong2 *slots, unsig
     double a = lane < GF_THREADS / 32 ? buf[lane] : 0.0;
     a = gf_warp_allsum(a);
     if (lane == 0) {
+      // FENCE: the exchange doubles as a grid barrier for VECTOR data (release the CTA's stores, which the
+      // __syncthreads above ordered before this thread; acquire below) - the scheme of cg::grid.sync()
+      if (FENCE) __threadfence();
       unsigned long long bits = (unsigned long long)__double_as_longlong(a);
       asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(half + blockIdx.x), "l"(bits), "l"(epoch) : "memory");
     }
@@ -71,10 +75,42 @@ __device__ __forceinline__ double gf_grid_sum(double v, ulonglong2 *slots, unsig
       t += __longlong_as_double((long long)w.x);
     }
     t = gf_warp_allsum(t);
+    if (FENCE) __threadfence();
     if (lane == 0) buf[GF_THREADS / 32] = t;
   }
   __syncthreads();
   return buf[GF_THREADS / 32];
+}
+
+// {inv_s, state} of the scalar bookkeeping, computed by thread 0 of CTA 0, reach the other CTAs as one stamped 16-byte
+// word (one L2 round trip) instead of through a grid barrier
+__device__ __forceinline__ void gf_bcast_publish(ulonglong2 *word, unsigned long long epoch, double inv, int32_t state) {
+  const unsigned long long lo = (unsigned long long)__double_as_longlong(inv), hi = (epoch << 16) | (unsigned long long)(state & 0xffff);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(word), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void gf_bcast_wait(const ulonglong2 *word, unsigned long long epoch, double *s_b, double &inv, int32_t &state) {
+  if (threadIdx.x == 0) {
+    ulonglong2 w;
+    unsigned spins = 0;
+    long long t0 = 0;
+    do {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(word) : "memory");
+      if ((w.y >> 16) == epoch) break;
+      if ((++spins & 4095u) == 0u) {
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 8000000000ll) {
+          w.x = 0x7ff8000000000000ull, w.y = 2;  // state 2 = failure
+          break;
+        }
+      }
+    } while (true);
+    s_b[0] = __longlong_as_double((long long)w.x);
+    s_b[1] = (double)(int)(w.y & 0xffffull);
+  }
+  __syncthreads();
+  inv = s_b[0];
+  state = (int32_t)s_b[1];
+  __syncthreads();
 }
 
 template <int EPT>
@@ -84,9 +120,13 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
                     ulonglong2 *slots, unsigned long long *epoch_ctr) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double s_red[2 * (GF_THREADS / 32 + 1)];
+  __shared__ double s_b[2];
+  ulonglong2 *bword = slots + 2 * 148;  // broadcast word at a fixed place behind the (at most 2 x 148) partial slots
   const int64_t T = (int64_t)gridDim.x * GF_THREADS, tid = (int64_t)blockIdx.x * GF_THREADS + threadIdx.x;
   const int m = n_tmp - 2;
-  unsigned long long epoch = *epoch_ctr;  // continues where the previous solve stopped: stale stamps never match
+  // both counters continue where the previous solve stopped: stale stamps never match.  Reductions and broadcasts
+  // count separately: the two halves of the partial slots must alternate strictly from one REDUCTION to the next.
+  unsigned long long epoch = epoch_ctr[0], bepoch = epoch_ctr[1];
   bool re_orth = false;
   const double sqrt_eps = sqrt(2.220446049250313e-16);
   double vv[EPT];
@@ -112,14 +152,15 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
       }
     }
     double tot = gf_grid_sum(acc, slots, epoch, s_red);
+    ++bepoch;
     if (tid == 0) {
       ctl->nrm2 = tot;
       gm_cycle_start_dev(ctl);
-      __threadfence();
+      gf_bcast_publish(bword, bepoch, ctl->inv_s, ctl->state);
     }
-    grid.sync();
-    int32_t state = *(volatile int32_t *)&ctl->state;
-    double inv = *(volatile double *)&ctl->inv_s;
+    int32_t state;
+    double inv;
+    gf_bcast_wait(bword, bepoch, s_b, inv, state);
     if (state == 0) {
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
@@ -199,13 +240,12 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
           }
         }
       }
+      ++bepoch;
       if (tid == 0) {
         gm_step_dev(ctl, inner, re_orth ? 1 : 0, hist);
-        __threadfence();
+        gf_bcast_publish(bword, bepoch, ctl->inv_s, ctl->state);
       }
-      grid.sync();
-      state = *(volatile int32_t *)&ctl->state;
-      inv = *(volatile double *)&ctl->inv_s;
+      gf_bcast_wait(bword, bepoch, s_b, inv, state);
       // the multi-kernel path scales only while state == 0 (k_scale_dev skips once the solver has decided)
       if (state == 0) {
 #pragma unroll
@@ -214,7 +254,7 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
           if (i < n) V(inner + 1)[i] = isfinite(inv) ? vv[k] * inv : vv[k];
         }
       }
-      grid.sync();
+      (void)gf_grid_sum<true>(0.0, slots, epoch, s_red);  // grid barrier for the stored basis vector (next: SpMV gathers)
     }
     // ---- cycle end: x += sum_k y_k v_k
     if (tid == 0) {
@@ -235,7 +275,7 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
     grid.sync();
     if (state != 0) break;
   }
-  if (tid == 0) *epoch_ctr = epoch;  // every thread counted the same reductions
+  if (tid == 0) epoch_ctr[0] = epoch, epoch_ctr[1] = bepoch;  // every thread counted the same exchanges
 }
 
 }  // namespace nsg
