@@ -130,7 +130,7 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
   bool re_orth = false;
   const double sqrt_eps = sqrt(2.220446049250313e-16);
   double vv[EPT];
-  // row i of A times v, entries in CSR order (the order the oracle and SpMV variant 0 use)
+  // row i of A times v, entries in CSR order (the order SpMV variant 0 uses)
   auto row_times = [&](int64_t i, const double *v) {
     double a = 0.0;
     for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) a += vals[p] * v[col[p]];

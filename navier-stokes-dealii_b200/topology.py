@@ -163,6 +163,31 @@ class Dofs:
             pass
 
 
+class _PartHandle:
+    """Owns one nst_part; freed when the last Part (or shallow copy of it) that views its buffers goes away."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def __del__(self):
+        try:
+            if self._h:
+                nst().nst_part_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype):
+    """Read-only zero-copy view of a library-owned buffer (empty array for n == 0)."""
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(int(n),))
+    assert a.dtype == np.dtype(dtype), (a.dtype, dtype)
+    a.flags.writeable = False
+    return a
+
+
 class Part:
     """One rank's local problem: owned rows + one ghost layer (cpp:19-21, 75-91)."""
 
@@ -179,16 +204,20 @@ class Part:
         self.n_own = self.n_own_u + self.n_own_p
         self.n_loc = self.n_own + self.n_ghost_u + self.n_ghost_p
         L = nst()
-        self.l2g = as_array(L.nst_part_l2g(h), self.n_loc, np.int64)
-        self.cell_ids = as_array(L.nst_part_cell_ids(h), self.n_cells, np.int32)
-        self.cell_dofs = as_array(L.nst_part_cell_dofs(h), 15 * self.n_cells, np.int32)
-        self.cell_vertices = as_array(L.nst_part_cell_vertices(h), 3 * self.n_cells, np.int32)
-        self.xy = as_array(L.nst_part_xy(h), 2 * self.n_vertices, np.float64)
-        self.cell_owned = as_array(L.nst_part_cell_owned(h), self.n_cells, np.uint8)
-        self.jac_rowptr = as_array(L.nst_part_jac_rowptr(h), self.n_own + 1, np.int64)
-        self.jac_col = as_array(L.nst_part_jac_col(h), self.nnz_jac, np.int32)
-        self.pm_rowptr = as_array(L.nst_part_pm_rowptr(h), self.n_own + 1, np.int64)
-        self.pm_col = as_array(L.nst_part_pm_col(h), self.nnz_pm, np.int32)
+        # the big arrays are VIEWS of the library-owned buffers (no second copy of hundreds of millions of pattern
+        # entries); the holder keeps the nst_part alive for as long as any (shallow copy of this) Part refers to it
+        self._keep = _PartHandle(h)
+        view = _view
+        self.l2g = view(L.nst_part_l2g(h), self.n_loc, np.int64)
+        self.cell_ids = view(L.nst_part_cell_ids(h), self.n_cells, np.int32)
+        self.cell_dofs = view(L.nst_part_cell_dofs(h), 15 * self.n_cells, np.int32)
+        self.cell_vertices = view(L.nst_part_cell_vertices(h), 3 * self.n_cells, np.int32)
+        self.xy = view(L.nst_part_xy(h), 2 * self.n_vertices, np.float64)
+        self.cell_owned = view(L.nst_part_cell_owned(h), self.n_cells, np.uint8)
+        self.jac_rowptr = view(L.nst_part_jac_rowptr(h), self.n_own + 1, np.int64)
+        self.jac_col = view(L.nst_part_jac_col(h), self.nnz_jac, np.int32)
+        self.pm_rowptr = view(L.nst_part_pm_rowptr(h), self.n_own + 1, np.int64)
+        self.pm_col = view(L.nst_part_pm_col(h), self.nnz_pm, np.int32)
         self.neighbors = as_array(L.nst_part_neighbors(h), self.n_neighbors, np.int32)
         self.send_ptr = as_array(L.nst_part_send_ptr(h), self.n_neighbors + 1, np.int64)
         self.send_idx = as_array(L.nst_part_send_idx(h), self.n_send, np.int32)
@@ -198,7 +227,6 @@ class Part:
         self.bface_cell = as_array(L.nst_part_bface_cell(h), nb, np.int32)
         self.bface_face = as_array(L.nst_part_bface_face(h), nb, np.int32)
         self.bface_tag = as_array(L.nst_part_bface_tag(h), nb, np.int32)
-        L.nst_part_free(h)
         self._h = None
         # global -> local map of the owned rows (for the Dirichlet list)
         self.own_global = self.l2g[: self.n_own]
