@@ -174,7 +174,7 @@ _nsg = None
 def nst():
     global _nst
     if _nst is None:
-        path = os.path.join(_HERE, "libnst.so")
+        path = os.environ.get("NST_LIB", os.path.join(_HERE, "libnst.so"))  # NST_LIB: A/B builds of the same ABI
         if not os.path.exists(path):
             raise NstError(f"{path} is missing: run `make` (or __graft_entry__.build()) first")
         _nst = _bind(C.CDLL(path), _NST_SIGS)

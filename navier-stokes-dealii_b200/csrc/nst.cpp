@@ -726,31 +726,39 @@ void build_pattern(int64_t n_rows, int64_t n_cells, const int32_t *cell_dofs, in
         if (g < n_rows) dcell[pos[g]++] = (int32_t)c;
       }
   }
-  auto row_cols = [&](int64_t r, int32_t *buf) -> int {
+  // The two dofs of a velocity node are consecutive ids everywhere (global, owned-local and ghost-local numbering), so a
+  // row is assembled from KEYS - the x-dof of every velocity node and every pressure dof of the patch (9 per cell
+  // instead of 15 dofs) - which are sorted, made unique and then expanded (x-dof -> x-dof, y-dof).
+  static const int UX[6] = {0, 3, 6, 9, 11, 13}, PD[3] = {2, 5, 8};
+  auto row_cols = [&](int64_t r, int32_t *buf, int32_t *keys) -> int {
     const bool rp = is_p((int32_t)r);
-    int n = 0;
     if (kind == 2 && !rp) return 0;  // the pressure-mass pattern has entries in pressure rows only
+    int nk = 0;
     for (int64_t q = dptr[r]; q < dptr[r + 1]; ++q) {
       const int32_t *cd = cell_dofs + 15 * (int64_t)dcell[q];
-      for (int k = 0; k < 15; ++k) {
-        const bool cp = is_p(cd[k]);
-        const bool pp = rp && cp;
-        if ((kind == 1 && pp) || (kind == 2 && !pp)) continue;
-        buf[n++] = cd[k];
-      }
+      if (kind != 2)
+        for (int k = 0; k < 6; ++k) keys[nk++] = cd[UX[k]];
+      if (!(kind == 1 && rp) && !(kind == 2 && !rp))
+        for (int k = 0; k < 3; ++k) keys[nk++] = cd[PD[k]];
     }
-    std::sort(buf, buf + n);
-    return (int)(std::unique(buf, buf + n) - buf);
+    std::sort(keys, keys + nk);
+    nk = (int)(std::unique(keys, keys + nk) - keys);
+    int n = 0;
+    for (int j = 0; j < nk; ++j) {
+      buf[n++] = keys[j];
+      if (!is_p(keys[j])) buf[n++] = keys[j] + 1;
+    }
+    return n;
   };
   rowptr.assign(n_rows + 1, 0);
 #pragma omp parallel
   {
-    std::vector<int32_t> buf(15 * 64);
+    std::vector<int32_t> buf(15 * 64), keys(9 * 64);
 #pragma omp for schedule(dynamic, 8192)
     for (int64_t r = 0; r < n_rows; ++r) {
       const size_t need = 15 * (size_t)(dptr[r + 1] - dptr[r]);
-      if (buf.size() < need) buf.resize(need);
-      rowptr[r + 1] = row_cols(r, buf.data());
+      if (buf.size() < need) buf.resize(need), keys.resize(need);
+      rowptr[r + 1] = row_cols(r, buf.data(), keys.data());
     }
   }
   for (int64_t r = 0; r < n_rows; ++r) rowptr[r + 1] += rowptr[r];
@@ -758,12 +766,12 @@ void build_pattern(int64_t n_rows, int64_t n_cells, const int32_t *cell_dofs, in
   col->resize(rowptr[n_rows]);
 #pragma omp parallel
   {
-    std::vector<int32_t> buf(15 * 64);
+    std::vector<int32_t> buf(15 * 64), keys(9 * 64);
 #pragma omp for schedule(dynamic, 8192)
     for (int64_t r = 0; r < n_rows; ++r) {
       const size_t need = 15 * (size_t)(dptr[r + 1] - dptr[r]);
-      if (buf.size() < need) buf.resize(need);
-      const int n = row_cols(r, buf.data());
+      if (buf.size() < need) buf.resize(need), keys.resize(need);
+      const int n = row_cols(r, buf.data(), keys.data());
       std::copy(buf.data(), buf.data() + n, col->data() + rowptr[r]);
     }
   }
