@@ -707,25 +707,48 @@ const int64_t *nst_dofs_part_n_p(const nst_dofs *d) { return d->part_n_p.data();
 
 namespace {
 
+// dof -> cells CSR restricted to rows < n_rows (the order of the cells of a dof is irrelevant to its users)
+struct DofCells {
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> cell;
+};
+static void dof_to_cells(int64_t n_rows, int64_t n_cells, const int32_t *cell_dofs, DofCells &dc) {
+  std::vector<int64_t> &dptr = dc.ptr;
+  dptr.assign(n_rows + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < 15 * n_cells; ++i)
+    if (cell_dofs[i] < n_rows) {
+#pragma omp atomic
+      dptr[cell_dofs[i] + 1]++;
+    }
+  for (int64_t r = 0; r < n_rows; ++r) dptr[r + 1] += dptr[r];
+  dc.cell.resize(dptr[n_rows]);
+  std::vector<int64_t> pos(dptr.begin(), dptr.end() - 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < n_cells; ++c)
+    for (int k = 0; k < 15; ++k) {
+      const int32_t g = cell_dofs[15 * c + k];
+      if (g < n_rows) {
+        int64_t at;
+#pragma omp atomic capture
+        at = pos[g]++;
+        dc.cell[at] = (int32_t)c;
+      }
+    }
+}
+
 // Generic CSR pattern of the rows [0,n_rows) from 15-dof cell lists; `is_p(id)` tells the block
 // of a (local) dof id. kind 0: all couplings; 1: all but p-p; 2: p-p only. Columns ascending.
 template <class IsP>
 void build_pattern(int64_t n_rows, int64_t n_cells, const int32_t *cell_dofs, int kind, IsP is_p,
-                   std::vector<int64_t> &rowptr, ColVec *col) {
-  // dof -> cells CSR restricted to rows < n_rows
-  std::vector<int64_t> dptr(n_rows + 1, 0);
-  for (int64_t i = 0; i < 15 * n_cells; ++i)
-    if (cell_dofs[i] < n_rows) dptr[cell_dofs[i] + 1]++;
-  for (int64_t r = 0; r < n_rows; ++r) dptr[r + 1] += dptr[r];
-  std::vector<int32_t> dcell(dptr[n_rows]);
-  {
-    std::vector<int64_t> pos(dptr.begin(), dptr.end() - 1);
-    for (int64_t c = 0; c < n_cells; ++c)
-      for (int k = 0; k < 15; ++k) {
-        const int32_t g = cell_dofs[15 * c + k];
-        if (g < n_rows) dcell[pos[g]++] = (int32_t)c;
-      }
+                   std::vector<int64_t> &rowptr, ColVec *col, const DofCells *shared = nullptr) {
+  DofCells own;
+  if (!shared) {
+    dof_to_cells(n_rows, n_cells, cell_dofs, own);
+    shared = &own;
   }
+  const std::vector<int64_t> &dptr = shared->ptr;
+  const std::vector<int32_t> &dcell = shared->cell;
   // The two dofs of a velocity node are consecutive ids everywhere (global, owned-local and ghost-local numbering), so a
   // row is assembled from KEYS - the x-dof of every velocity node and every pressure dof of the patch (9 per cell
   // instead of 15 dofs) - which are sorted, made unique and then expanded (x-dof -> x-dof, y-dof).
@@ -951,8 +974,12 @@ int nst_part_build(const nst_mesh *m, const nst_dofs *d, int n_parts, const int3
   // local patterns of the owned rows (columns ascending in local ids: owned first, then ghosts)
   const int32_t a0 = (int32_t)n_own_u, a1 = (int32_t)n_own, a2 = (int32_t)(n_own + n_gu);
   auto is_p = [a0, a1, a2](int32_t l) { return (l >= a0 && l < a1) || l >= a2; };
-  build_pattern(n_own, nc, P->cell_dofs.data(), 0, is_p, P->jac_rowptr, &P->jac_col);
-  build_pattern(n_own, nc, P->cell_dofs.data(), 2, is_p, P->pm_rowptr, &P->pm_col);
+  {
+    DofCells dc;  // shared by the two patterns
+    dof_to_cells(n_own, nc, P->cell_dofs.data(), dc);
+    build_pattern(n_own, nc, P->cell_dofs.data(), 0, is_p, P->jac_rowptr, &P->jac_col, &dc);
+    build_pattern(n_own, nc, P->cell_dofs.data(), 2, is_p, P->pm_rowptr, &P->pm_col, &dc);
+  }
   // halo plan
   std::vector<std::vector<int32_t>> recv(n_parts), send(n_parts);
   for (int64_t i = 0; i < n_gu; ++i) recv[owner_of(gu[i])].push_back((int32_t)(n_own + i));
