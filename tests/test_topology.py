@@ -207,3 +207,23 @@ def test_output_writer_xdmf_roundtrip(pkg, tmp_path):
         assert np.allclose(r["velocity"][:, 0], 1.0 + x, atol=1e-14) and np.allclose(r["velocity"][:, 1], 2.0 * y, atol=1e-14)
         assert not r["velocity"][:, 2].any() and np.allclose(r["pressure"], x - y, atol=1e-14)
         assert (r["partitioning"] == rank).all()
+
+
+def test_part_arrays_are_views_kept_alive_by_copies(pkg):
+    """The big Part arrays are read-only zero-copy views of library-owned buffers; a shallow copy of a Part (used by the
+    tests to swap in modified patterns) must keep those buffers alive after the original is gone."""
+    import copy
+    import gc
+    m = pkg.Mesh.read_msh(mesh_path("square_h0.1.msh"))
+    d = pkg.Dofs(m)
+    part = pkg.Part(d, 0)
+    ref_col, ref_dofs = part.jac_col.copy(), part.cell_dofs.copy()
+    assert not part.jac_col.flags.writeable and not part.cell_dofs.flags.writeable
+    with pytest.raises(ValueError):
+        part.jac_col[0] = 7
+    clone = copy.copy(part)
+    del part
+    gc.collect()
+    junk = [np.ones(1 << 16) for _ in range(64)]      # churn the allocator: freed memory would be overwritten
+    assert np.array_equal(clone.jac_col, ref_col) and np.array_equal(clone.cell_dofs, ref_dofs)
+    del junk
