@@ -55,3 +55,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f in ("nst.cpp",) and "not the oracle" in txt, (dirpath, f)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, timed on the host cores) must print ONE
+    JSON line with the keys the driver reads; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--mesh", "cmy", "--cpu-level", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "jacobian_assembly_mdofs" and j["unit"] == "MDoF/s"
+    assert j["value"] > 0 and j["higher_is_better"] is True and j["dtype"] == "f64"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "MDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"]
