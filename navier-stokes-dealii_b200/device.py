@@ -58,9 +58,26 @@ class DeviceProblem:
         import os
         if os.environ.get("NSG_NO_PEER_AR", "0") == "1" or dist.get_world_size() <= 1:
             return False
-        handles = [None] * dist.get_world_size()
-        dist.all_gather_object(handles, self.comm_ipc_handle())
-        self.comm_set_peers(handles)
+        # a rank that cannot export or map a mailbox (no peer access between the devices) must not leave the others
+        # spinning on it: the decision to switch is taken collectively, otherwise everybody stays on NCCL
+        world = dist.get_world_size()
+        try:
+            mine, err = self.comm_ipc_handle(), None
+        except Exception as e:  # noqa: BLE001
+            mine, err = b"\0" * 64, str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, (mine, err))
+        if all(e is None for _, e in handles):
+            try:
+                self.comm_set_peers([h for h, _ in handles])
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        ok = [None] * world
+        dist.all_gather_object(ok, err is None and all(e is None for _, e in handles))
+        if not all(ok):
+            self._L.nsg_comm_release_peers(self._h)   # closes whatever was mapped; reductions stay on NCCL
+            dist.barrier()
+            return False
         dist.barrier()
         self._peer_dist = dist   # close() releases the peer mappings collectively before freeing the mailbox
         return True

@@ -80,3 +80,62 @@ def test_two_rank_halo_and_spmv_gloo():
     assert len(res) == 2
     for rank, ok_halo, ok_rows, ok_spmv, ok_dot, nn in res:
         assert ok_halo and ok_rows and ok_spmv and ok_dot and nn == 1, res
+
+
+class _FakeLib:
+    def __init__(self, log):
+        self.log = log
+
+    def nsg_comm_release_peers(self, h):
+        self.log.append("release")
+        return 0
+
+
+def _peer_worker(rank, world, port, q, failing_rank):
+    """Host logic of DeviceProblem.enable_peer_allreduce on a stub (no GPU): the switch to the fused all-reduce is a
+    COLLECTIVE decision - if any rank cannot export/map a mailbox, every rank stays on NCCL and releases its mappings."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import importlib
+    device = importlib.import_module("navier-stokes-dealii_b200.device")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        log = []
+
+        class Stub:
+            _L, _h = _FakeLib(log), object()
+
+            def comm_ipc_handle(self):
+                return bytes([rank]) * 64
+
+            def comm_set_peers(self, handles):
+                log.append(("set", [h[0] for h in handles]))
+                if rank == failing_rank:
+                    raise RuntimeError("cudaIpcOpenMemHandle: peer access is not supported between these two devices")
+
+        stub = Stub()
+        os.environ.pop("NSG_NO_PEER_AR", None)
+        got = device.DeviceProblem.enable_peer_allreduce(stub, dist)
+        q.put((rank, got, log, getattr(stub, "_peer_dist", None) is not None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("failing_rank", [-1, 1])
+def test_peer_allreduce_switch_is_collective_gloo(failing_rank):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + 7 * (failing_rank + 2)) % 90
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q, failing_rank)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+    for rank, got, log, has_dist in res:
+        assert ("set", [0, 1]) in log                          # handles arrive in rank order on every rank
+        if failing_rank < 0:
+            assert got is True and has_dist and "release" not in log
+        else:
+            assert got is False and not has_dist and "release" in log, res
