@@ -186,7 +186,13 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * the Gram-Schmidt chain, one stamped-slot exchange per inner product; one rank, modified Gram-Schmidt): 0 off, 1 (default) for systems
  * of up to 65 536 unknowns (the meshes the reference ships: 2x faster there), 2 whenever the system fits (up to 148 x 256 x 8 unknowns). Same algorithm and scalars as
  * the multi-kernel path; the inner-product sums are partitioned differently (agreement to rounding, not bitwise).
- * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off. */
+ * key 2 = CUDA graphs for the launch segments of the identity-preconditioned GMRES cycle: 1 (default) on, 0 off.
+ * key 1 = 5 (default since round 2): the "fan" scheme - one (owner, cell) pair per lane integrated in a rotated local
+ * frame (owner = local vertex 0 / edge 0: all tables are immediates), the lanes of an owner in one warp in fan order,
+ * shared-edge contributions combined by warp shuffles, every entry stored exactly once (no read-modify-write, no
+ * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically.
+ * key 6 = how variant 5 brings the per-cell packets to its lanes: 0 global loads, 1 (default) cp.async staging in shared
+ * memory, 2 one bulk copy (TMA engine) per cell. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

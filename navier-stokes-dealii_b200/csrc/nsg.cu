@@ -9,6 +9,7 @@
 #include <numeric>
 
 #include "nsg_assemble.cuh"
+#include "nsg_assemble_fan.cuh"
 #include "nsg_common.cuh"
 #include "nsg_linalg.cuh"
 
@@ -115,6 +116,29 @@ static int upload_tables() {
       for (int c = 0; c < 2; ++c) f.ga[l][c] = g0[l][c], f.gb[l][c] = gx[l][c] - g0[l][c], f.gc[l][c] = gy[l][c] - g0[l][c];
   }
   NSG_CUDA(cudaMemcpyToSymbol(c_fe2, &f, sizeof f));
+  // rows of the tables for the owner's local index in the rotated frame of the fan scheme (K = 0 vertex, K = 3 edge midpoint)
+  FanTab ft[2];
+  std::memset(ft, 0, sizeof ft);
+  for (int i = 0; i < 2; ++i) {
+    const int K = i == 0 ? 0 : 3;
+    for (int q = 0; q < 7; ++q)
+      for (int l = 0; l < 6; ++l) {
+        const double m = t.w[q] * t.psi[q][K] * t.psi[q][l];
+        ft[i].M[l] += m;
+        for (int j = 0; j < 3; ++j) ft[i].T[j][l] += m * t.chi[q][j];
+        ft[i].K00[l] += t.w[q] * t.dpsi[q][K][0] * t.dpsi[q][l][0];
+        ft[i].K01s[l] += t.w[q] * (t.dpsi[q][K][0] * t.dpsi[q][l][1] + t.dpsi[q][K][1] * t.dpsi[q][l][0]);
+        ft[i].K11[l] += t.w[q] * t.dpsi[q][K][1] * t.dpsi[q][l][1];
+      }
+    for (int m = 0; m < 3; ++m)
+      for (int cc = 0; cc < 2; ++cc) ft[i].Bh[m][cc] = f.Bh[K][m][cc];
+  }
+  NSG_CUDA(cudaMemcpyToSymbol(c_fan, ft, sizeof ft));
+  FanTabP fp;
+  for (int l = 0; l < 6; ++l)
+    for (int cc = 0; cc < 2; ++cc) fp.Bp[l][cc] = f.Bh[l][0][cc];
+  for (int n = 0; n < 3; ++n) fp.Mp[n] = f.Mp[0][n];
+  NSG_CUDA(cudaMemcpyToSymbol(c_fanp, &fp, sizeof fp));
   return NSG_OK;
 }
 
@@ -471,8 +495,11 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
   return NSG_OK;
 }
 
+#include "nsg_fanlist.inl"
+
 static void free_worklist(WorkList &w) {
   dev_free(w.chunks);
+  dev_free(w.cells);
   dev_free(w.tdesc);
   dev_free(w.tdesc3);
   dev_free(w.recs);
@@ -681,9 +708,56 @@ static AsmParams asm_params(const nsg_ctx *c) {
   return P;
 }
 
+template <int STAGE>
+static int launch_u6(nsg_ctx *c, const AsmParams &P) {
+  const unsigned grid = (unsigned)c->wl_u6.n_chunks;
+  const size_t smem = sizeof(double) * (size_t)c->wl_u6.max_stage;
+  k_assemble_u6<4, STAGE><<<grid, NPC6, smem, c->stream>>>(c->wl_u6, c->vals, c->R, c->cellpk, P);
+  NSG_LAUNCH_CHECK(c);
+  return NSG_OK;
+}
+
 static int launch_assembly(nsg_ctx *c) {
   const AsmParams P = asm_params(c);
-  if (c->asm_variant == 4) {
+  if (c->asm_variant == 5) {
+    // fan scheme.  The pressure rows depend on the geometry only: they run on a second stream beside the packet
+    // pre-pass and the velocity rows (NSG_ASM_CONCURRENT=0: one stream)
+    const bool fork = c->wl_p6.n_chunks > 0 && c->aux_stream && !(std::getenv("NSG_ASM_CONCURRENT") && std::atoi(std::getenv("NSG_ASM_CONCURRENT")) == 0);
+    cudaStream_t ps = fork ? c->aux_stream : c->stream;
+    if (fork) {
+      NSG_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      NSG_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    }
+    auto launch_p = [&]() -> int {
+      if (c->wl_p6.n_chunks > 0) {
+        k_assemble_p6<<<(unsigned)c->wl_p6.n_chunks, NPC6, sizeof(double) * (size_t)c->wl_p6.max_stage, ps>>>(
+            c->wl_p6, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom8, P);
+        NSG_LAUNCH_CHECK(c);
+      }
+      return NSG_OK;
+    };
+    if (fork) {
+      NSG_TRY(launch_p());
+      NSG_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    }
+    if (c->n_cells > 0) {
+      k_cell_packets6<<<(unsigned)((c->n_cells + 127) / 128), 128, 0, c->stream>>>(c->n_cells, c->geom8, c->cell_dofs, c->sol, c->sol_old, P,
+                                                                                  c->cellpk);
+      NSG_LAUNCH_CHECK(c);
+    }
+    if (c->wl_u6.n_chunks > 0) {
+      if (c->asm_stage == 0)
+        NSG_TRY(launch_u6<0>(c, P));
+      else if (c->asm_stage == 2)
+        NSG_TRY(launch_u6<2>(c, P));
+      else
+        NSG_TRY(launch_u6<1>(c, P));
+    }
+    if (fork)
+      NSG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    else
+      NSG_TRY(launch_p());
+  } else if (c->asm_variant == 4) {
     // the pressure rows depend on the geometry only: they are integrated on a second stream beside the packet
     // pre-pass and the velocity rows (NSG_ASM_CONCURRENT=0: one stream)
     const bool fork = c->wl_p5.n_chunks > 0 && c->aux_stream && !(std::getenv("NSG_ASM_CONCURRENT") && std::atoi(std::getenv("NSG_ASM_CONCURRENT")) == 0);
@@ -826,6 +900,37 @@ static int ensure_slot_worklists(nsg_ctx *c) {
   return NSG_OK;
 }
 
+// Work lists of assembly variant 4 (round-sorted lanes): built when it is selected or when the fan scheme cannot serve the mesh.
+static int ensure_round_worklists(nsg_ctx *c, const int32_t *cell_dofs_host) {
+  if (c->wl_u5.chunks || c->wl_p5.chunks || !c->have_mesh) return NSG_OK;
+  std::vector<int32_t> cell_dofs_h;
+  if (!cell_dofs_host) {
+    cell_dofs_h.resize((size_t)(15 * c->n_cells));
+    NSG_CUDA(cudaMemcpy(cell_dofs_h.data(), c->cell_dofs, sizeof(int32_t) * cell_dofs_h.size(), cudaMemcpyDeviceToHost));
+    cell_dofs_host = cell_dofs_h.data();
+  }
+  const bool fetch_cols = c->h_col.empty() && c->nnz > 0;
+  if (fetch_cols) {
+    c->h_col.resize((size_t)c->nnz), c->h_pm_col.resize((size_t)c->pm_nnz);
+    NSG_CUDA(cudaMemcpy(c->h_col.data(), c->col, sizeof(int32_t) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
+    NSG_CUDA(cudaMemcpy(c->h_pm_col.data(), c->pm_col, sizeof(int32_t) * (size_t)c->pm_nnz, cudaMemcpyDeviceToHost));
+  }
+  NSG_TRY(build_worklist5(c, 0, cell_dofs_host, &c->wl_u5));
+  NSG_TRY(build_worklist5(c, 1, cell_dofs_host, &c->wl_p5));
+  const size_t s5u = 8 * (size_t)c->wl_u5.max_stage, s5p = 8 * (size_t)c->wl_p5.max_stage;
+  if (s5u > 200 * 1024 || s5p > 200 * 1024)
+    return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
+  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5p, 1024)));
+  if (fetch_cols) {
+    c->h_col.clear(), c->h_col.shrink_to_fit();
+    c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
+  }
+  return NSG_OK;
+}
+
 static int ensure_pinned(nsg_ctx *c, int64_t n) {
   if (c->h_pinned_cap >= n) return NSG_OK;
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -954,7 +1059,8 @@ int nsg_create(int device, nsg_ctx **out) {
   auto *c = new nsg_ctx;
   c->device = device;
   c->peer.n_ranks = 1;
-  if (const char *v = std::getenv("NSG_ASM_VARIANT")) c->asm_variant = std::min(std::max(std::atoi(v), 0), 4);
+  if (const char *v = std::getenv("NSG_ASM_VARIANT")) c->asm_variant = std::min(std::max(std::atoi(v), 0), 5);
+  if (const char *v = std::getenv("NSG_ASM_STAGE")) c->asm_stage = std::min(std::max(std::atoi(v), 0), 2);
   nsg_params_default(&c->prm);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -999,6 +1105,8 @@ void nsg_destroy(nsg_ctx *c) {
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->col7), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p), free_worklist(c->wl_u5), free_worklist(c->wl_p5);
+  free_worklist(c->wl_u6), free_worklist(c->wl_p6);
+  dev_free(c->geom8);
   dev_free(c->bnode_dof), dev_free(c->bnode_ptr), dev_free(c->bnode_face), dev_free(c->bnode_pos);
   dev_free(c->bface_cell), dev_free(c->bface_face), dev_free(c->bface_tag);
   dev_free(c->sol), dev_free(c->sol_old), dev_free(c->delta), dev_free(c->R), dev_free(c->basis), dev_free(c->work);
@@ -1126,18 +1234,29 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     k_cell_geometry<<<grid_for(n_cells, 256, 1 << 30), 256, 0, c->stream>>>(n_cells, c->xy, c->cell_vertices, c->geom);
     NSG_LAUNCH_CHECK(c);
   }
-  // the work lists of the older assembly variants (0..3) are built on demand (nsg_set_tuning key 1)
+  NSG_TRY(dev_alloc(&c->geom8, 8 * n_cells));
+  if (n_cells > 0) {
+    k_cell_geometry8<<<grid_for(n_cells, 256, 1 << 30), 256, 0, c->stream>>>(n_cells, c->xy, c->cell_vertices, c->geom8);
+    NSG_LAUNCH_CHECK(c);
+  }
   NSG_TRY(dev_alloc(&c->cellpk, PK * n_cells + 2));
-  NSG_TRY(build_worklist5(c, 0, cell_dofs, &c->wl_u5));
-  NSG_TRY(build_worklist5(c, 1, cell_dofs, &c->wl_p5));
+  // default: the fan scheme (variant 5); its lists exist only for oriented manifold triangulations.  The work lists of
+  // the other variants are built on demand (nsg_set_tuning key 1) or when the fan scheme cannot serve the mesh.
   {
-    const size_t s5u = 8 * (size_t)c->wl_u5.max_stage, s5p = 8 * (size_t)c->wl_p5.max_stage;
-    if (s5u > 200 * 1024 || s5p > 200 * 1024)
-      return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
-    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
-    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
-    NSG_CUDA(cudaFuncSetAttribute(k_assemble_u5<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5u, 1024)));
-    NSG_CUDA(cudaFuncSetAttribute(k_assemble_p5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s5p, 1024)));
+    bool ok_u = false, ok_p = false;
+    NSG_TRY(build_fanlist(c, 0, cell_dofs, &c->wl_u6, &ok_u));
+    if (ok_u) NSG_TRY(build_fanlist(c, 1, cell_dofs, &c->wl_p6, &ok_p));
+    const size_t s6u = 8 * (size_t)c->wl_u6.max_stage, s6p = 8 * (size_t)c->wl_p6.max_stage;
+    c->fan_ok = ok_u && ok_p && s6u <= 200 * 1024 && s6p <= 200 * 1024;
+    if (c->fan_ok) {
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_p6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6p, 1024)));
+    } else {
+      free_worklist(c->wl_u6), free_worklist(c->wl_p6);
+      if (c->asm_variant == 5) c->asm_variant = 4;
+    }
   }
   // Neumann: owned boundary P2 nodes -> (face, position on the face)
   {
@@ -1173,10 +1292,14 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     NSG_TRY(upload(c, &c->bnode_pos, npos.data(), (int64_t)npos.size()));
     NSG_CUDA(cudaStreamSynchronize(c->stream));
   }
+  c->have_mesh = true;
+  if (c->asm_variant == 4) {
+    NSG_TRY(ensure_round_worklists(c, cell_dofs));
+  } else if (c->asm_variant < 4) {
+    NSG_TRY(ensure_slot_worklists(c));
+  }
   c->h_col.clear(), c->h_col.shrink_to_fit();
   c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
-  c->have_mesh = true;
-  if (c->asm_variant < 4) NSG_TRY(ensure_slot_worklists(c));
   return NSG_OK;
 }
 
@@ -1590,9 +1713,16 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       c->graphs.clear();
       return NSG_OK;
     case 1:
-      if (value < 0 || value > 4) return fail(NSG_ERR_ARG, "assembly variant must be 0..4 (see nsg.h)");
+      if (value < 0 || value > 5) return fail(NSG_ERR_ARG, "assembly variant must be 0..5 (see nsg.h)");
+      if (value == 5 && c->have_mesh && !c->fan_ok)
+        return fail(NSG_ERR_STATE, "the fan scheme (variant 5) cannot serve this mesh (not an oriented manifold triangulation)");
       if (value < 4) NSG_TRY(ensure_slot_worklists(c));
+      if (value == 4) NSG_TRY(ensure_round_worklists(c, nullptr));
       c->asm_variant = value;
+      return NSG_OK;
+    case 6:
+      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "packet staging must be 0 (global loads), 1 (cp.async) or 2 (bulk copies)");
+      c->asm_stage = value;
       return NSG_OK;
     default: return fail(NSG_ERR_ARG, "unknown tuning key");
   }

@@ -76,6 +76,7 @@ struct WorkList {
                                  // J-row offset | mass-row offset << 16); y = row length | slot << 16 | owner << 24;
                                  // y = 0xffffffff marks a padding lane
   PairRec *recs = nullptr;       // [n_recs]; cell = -1 marks "no work"
+  int32_t *cells = nullptr;      // [n_chunks*NPC6] fan scheme: the cells whose packets a chunk stages (ChunkInfo::n_threads of them)
   int64_t max_stage = 0;         // max number of staged matrix entries of a chunk
 };
 
@@ -187,7 +188,7 @@ struct nsg_ctx {
   int32_t *spmv_chunk_rows = nullptr;
   int64_t *diag_pos = nullptr;
   unsigned long long *first_idx = nullptr;
-  int spmv_variant = 0, asm_variant = 4;
+  int spmv_variant = 0, asm_variant = 5;
   int gmres_fused = 1;  // tuning key 5: 0 off, 1 systems up to gmres_fused_max_n unknowns, 2 whenever the vectors fit the grid's registers
   int64_t gmres_fused_max_n = 65536;  // measured: 2.0x faster at 29 646 unknowns, 1.08x at 117 324, 0.86x at 232 003
   double *gf_partials = nullptr;
@@ -203,11 +204,15 @@ struct nsg_ctx {
   int64_t spmv_n_chunks = 0;
   // mesh
   double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|
+  double *geom8 = nullptr;  // [8T] grad lambda_0..2, |det J|, 0 (assembly variant 5)
   double *cellpk = nullptr;  // [44T] per-cell packets of assembly variant 2 (rewritten by every nsg_assemble)
   double *xy = nullptr;
   int32_t *cell_vertices = nullptr, *cell_dofs = nullptr;
   nsg::WorkList wl_u, wl_p;
   nsg::WorkList wl_u5, wl_p5;  // assembly variant 4: one pair per lane, lanes sorted by (round, cell)
+  nsg::WorkList wl_u6, wl_p6;  // assembly variant 5 ("fan"): the lanes of an owner in one warp, every entry stored once
+  bool fan_ok = false;         // the mesh is an oriented manifold triangulation the fan scheme can serve
+  int asm_stage = 1;           // variant 5: 0 lanes read the packets from global memory, 1 cp.async staging, 2 bulk-copy (TMA) staging
   // Neumann: boundary nodes -> faces
   int64_t n_bnodes = 0;
   int32_t *bnode_dof = nullptr, *bnode_ptr = nullptr, *bnode_face = nullptr, *bnode_pos = nullptr;
