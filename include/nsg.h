@@ -96,7 +96,11 @@ typedef struct {
   int32_t neumann_id;  /* boundary id of the Neumann (p_out) faces */
   int32_t use_mass;    /* 1 = implicit Euler terms (cpp:249-251, 288-290); 0 = steady */
   int32_t stokes;      /* 1 = assemble_stokes_system (cpp:380-531) into the same objects */
-  int32_t reserved;
+  int32_t dirichlet_diag; /* diagonal of a constrained row after nsg_apply_dirichlet (cpp:375-376):
+                           0 (default) = TrilinosWrappers rule: ALWAYS replaced by d = |first non-zero diagonal entry of
+                           the block's locally owned rows|, rhs_i = g_i d (MatrixTools::apply_boundary_values for Trilinos
+                           matrices: clear_rows(rows, d)); 1 = deal.II's native-SparseMatrix rule: a non-zero diagonal
+                           is kept (d only where it is zero), rhs_i = g_i J_ii */
 } nsg_params;
 void nsg_params_default(nsg_params *p);
 int nsg_set_params(nsg_ctx *ctx, const nsg_params *p);
@@ -126,6 +130,12 @@ int nsg_solve(nsg_ctx *ctx, int32_t precond, double rel_tol, int32_t max_it, int
               int32_t target, int32_t *its_out, double *res_out);
 /* residual estimate after every GMRES step of the last nsg_solve (returns how many exist). */
 int64_t nsg_gmres_history(nsg_ctx *ctx, double *out, int64_t cap);
+/* Which code path the last nsg_solve took (so that a test can assert that the knob it set was the one exercised):
+ * out4[0] = 1 the whole solve ran as the ONE cooperative kernel (tuning key 5), 0 the multi-kernel solver;
+ * out4[1] = number of CUDA-graph replays of restart-cycle segments (tuning key 2; 0 = plain launches);
+ * out4[2] = SpMV kernel variant used by the operator (tuning key 0; -1 for the cooperative kernel, which has its own);
+ * out4[3] = Gram-Schmidt variant (tuning key 3). */
+int nsg_last_solve_info(nsg_ctx *ctx, int32_t *out4);
 
 /* solution_owned += delta_owned; solution = solution_owned (cpp:616-618). */
 int nsg_update_solution(nsg_ctx *ctx);
@@ -162,7 +172,9 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
 
 /* Repeat a kernel `reps` times on device-resident data and return the mean time per
  * launch in milliseconds (CUDA events on the context's stream). what: 0 = assembly (cells +
- * Neumann, no Dirichlet), 1 = SpMV J*delta, 2 = add_and_dot, 3 = dot, 4 = one halo exchange. */
+ * Neumann, no Dirichlet), 1 = SpMV J*delta, 2 = add_and_dot, 3 = dot, 4 = one halo exchange, 5 = FP64 pipe
+ * micro-benchmark (SM count x 16 CTAs x 256 threads x 8 chains x 2048 dependent DFMA = SMs x 67 108 864 DFMA per launch,
+ * 2 flop each: the measured FP64 peak the assembly's FP64-pipe share is quoted against). */
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
 /* Tuning knobs that do not change what is computed (only the summation order inside a row):

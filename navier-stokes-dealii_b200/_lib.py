@@ -43,7 +43,7 @@ class PartInfo(C.Structure):
 class NsgParams(C.Structure):
     _fields_ = [("nu", C.c_double), ("rho", C.c_double), ("p_out", C.c_double), ("deltat", C.c_double),
                 ("forcing", C.c_double * 2), ("neumann_id", i32), ("use_mass", i32), ("stokes", i32),
-                ("reserved", i32)]
+                ("dirichlet_diag", i32)]
 
 
 def _opt(ptr_type):
@@ -137,6 +137,7 @@ _NSG_SIGS = {
     "nsg_residual_norm": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "nsg_solve": (C.c_int, [vp, i32, C.c_double, i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_double)]),
     "nsg_gmres_history": (i64, [vp, _opt(f64p), i64]),
+    "nsg_last_solve_info": (C.c_int, [vp, i32p]),
     "nsg_update_solution": (C.c_int, [vp]),
     "nsg_push_time_level": (C.c_int, [vp]),
     "nsg_set_solution": (C.c_int, [vp, f64p]),

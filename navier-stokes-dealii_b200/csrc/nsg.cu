@@ -1045,7 +1045,7 @@ void nsg_params_default(nsg_params *p) {
   p->deltat = 0.05;                              // main.cpp:13
   p->forcing[0] = 0.0, p->forcing[1] = -0.0;     // hpp:438: g = 0
   p->neumann_id = 10;                            // cpp:320
-  p->use_mass = 1, p->stokes = 0, p->reserved = 0;
+  p->use_mass = 1, p->stokes = 0, p->dirichlet_diag = 0;
 }
 
 int nsg_create(int device, nsg_ctx **out) {
@@ -1406,6 +1406,7 @@ int nsg_comm_release_peers(nsg_ctx *c) {
 int nsg_set_params(nsg_ctx *c, const nsg_params *p) {
   if (!c || !p) return fail(NSG_ERR_ARG, "null argument");
   if (!(p->nu > 0) || (p->use_mass && !(p->deltat > 0))) return fail(NSG_ERR_ARG, "nu and deltat must be positive");
+  if (p->dirichlet_diag < 0 || p->dirichlet_diag > 1) return fail(NSG_ERR_ARG, "dirichlet_diag must be 0 (Trilinos rule) or 1 (keep a non-zero diagonal)");
   c->prm = *p;
   return NSG_OK;
 }
@@ -1461,7 +1462,7 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
   // solve never reads (it iterates on solution_owned) and overwrites afterwards -> no vector write here.
   double *x = into_solution ? nullptr : c->delta;
   k_apply_dirichlet<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(n, c->dir_dofs, c->dir_vals, c->n_own_u, c->rowptr,
-                                                                             c->diag_pos, c->vals, x, c->R, c->scal + 8);
+                                                                             c->diag_pos, c->vals, x, c->R, c->scal + 8, c->prm.dirichlet_diag);
   NSG_LAUNCH_CHECK(c);
   NSG_CUDA(cudaEventRecord(c->ev1, c->stream));
   NSG_CUDA(cudaEventSynchronize(c->ev1));  // dofs/values are caller-owned: the copies must have completed
@@ -1511,7 +1512,9 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   Op P = [c, precond](double *d, double *s, const int32_t *) { return precond_vmult(c, precond, d, s); };
   GmresResult r;
   c->inner_its = 0;
-  if (gmres_fused_applicable(c, precond))
+  const bool fused = gmres_fused_applicable(c, precond);
+  c->last_solve[0] = fused ? 1 : 0, c->last_solve[1] = 0, c->last_solve[2] = fused ? -1 : c->spmv_variant, c->last_solve[3] = c->orthogonalization;
+  if (fused)
     NSG_TRY(gmres_fused(c, x, rel_tol, max_it, n_tmp, (int)hist_cap, &r));
   else
     NSG_TRY(gmres_core(c, Range{0, c->n_own}, A, precond == NSG_PRECOND_IDENTITY ? nullptr : &P, x, c->R, c->R, rel_tol, max_it, n_tmp,
@@ -1535,6 +1538,12 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
     snprintf(buf, sizeof buf, "GMRES did not converge: %d steps, last residual %.6e", r.its, r.res);
     return fail(NSG_ERR_NO_CONVERGENCE, buf);
   }
+  return NSG_OK;
+}
+
+int nsg_last_solve_info(nsg_ctx *c, int32_t *out4) {
+  if (!c || !out4) return fail(NSG_ERR_ARG, "null argument");
+  for (int i = 0; i < 4; ++i) out4[i] = c->last_solve[i];
   return NSG_OK;
 }
 
@@ -1662,6 +1671,13 @@ int nsg_time_kernel(nsg_ctx *c, int32_t what, int32_t reps, double *ms_per_launc
       case 2: NSG_TRY(dev_add_and_dot(c, n, a, c->scal, 1.0, b, w, c->scal + 1, nullptr)); break;
       case 3: NSG_TRY(dev_dot(c, n, a, b, c->scal + 1, nullptr)); break;
       case 4: NSG_TRY(halo_exchange(c, c->delta)); break;
+      case 5: {  // FP64 pipe peak: sm_count x 16 CTAs x 256 threads x 8 chains x 2048 DFMA
+        int sms = 0;
+        NSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        k_dfma_peak<<<sms * 16, DFMA_THREADS, 0, c->stream>>>(c->scal + 2, 0.999999, 1e-9);
+        NSG_LAUNCH_CHECK(c);
+        break;
+      }
       default: return fail(NSG_ERR_ARG, "unknown kernel id");
     }
   }

@@ -1562,12 +1562,14 @@ __global__ void k_first_nonzero_diag_value(const int64_t *__restrict__ diag_pos,
   *out = (i == ~0ull) ? 1.0 : fabs(vals[diag_pos[i]]);
 }
 
-// one warp per constrained row: clear the row in every block, keep a non-zero diagonal (else the
-// block's first non-zero diagonal), set the solution entry and rhs_i = g_i * diag_i
+// one warp per constrained row: clear the row in every block and set the diagonal, the solution entry and the right-hand
+// side.  keep_diag == 0 (TrilinosWrappers rule, the reference's path): the diagonal is ALWAYS replaced by d = the block's
+// first non-zero diagonal and rhs_i = g_i d; keep_diag == 1 (deal.II's native SparseMatrix rule): a non-zero diagonal is
+// kept (d only where it is zero) and rhs_i = g_i J_ii.
 __global__ void k_apply_dirichlet(int64_t n, const int32_t *__restrict__ dofs, const double *__restrict__ g,
                                   int64_t n_own_u, const int64_t *__restrict__ rowptr, const int64_t *__restrict__ diag_pos,
                                   double *__restrict__ vals, double *__restrict__ x, double *__restrict__ R,
-                                  const double *__restrict__ first_nz) {
+                                  const double *__restrict__ first_nz, const int keep_diag) {
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
@@ -1576,11 +1578,13 @@ __global__ void k_apply_dirichlet(int64_t n, const int32_t *__restrict__ dofs, c
   for (int64_t p = rowptr[i] + lane; p < rowptr[i + 1]; p += 32)
     if (p != pd) vals[p] = 0.0;
   if (lane == 0) {
-    double diag = pd >= 0 ? vals[pd] : 0.0;
-    if (pd >= 0 && diag == 0.0) {
-      diag = first_nz[i < n_own_u ? 0 : 1];
-      vals[pd] = diag;
+    const double d = first_nz[i < n_own_u ? 0 : 1];
+    double diag = d;
+    if (keep_diag) {
+      diag = pd >= 0 ? vals[pd] : 0.0;
+      if (diag == 0.0) diag = d;
     }
+    if (pd >= 0) vals[pd] = diag;
     if (x) x[i] = g[w];
     R[i] = g[w] * diag;
   }

@@ -371,7 +371,9 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
     }
   }
   double A[6][4], Bt[3][2];
-  const bool edge_owner = kc >= 3;  // uniform over the warp (the host packs vertex owners and edge owners into different warps)
+  // uniform over the warp: the host packs vertex owners and edge owners into different warps (idle padding lanes have no
+  // type of their own and must take the branch of their warp: the shuffles below are full-mask)
+  const bool edge_owner = __any_sync(0xffffffffu, work && kc >= 3);
   if (!edge_owner)
     fan_rows<0>(n1, n2, dd.x, u, ns, mdt, nurho, P.rho, A, Bt);
   else

@@ -196,6 +196,7 @@ struct nsg_ctx {
   bool use_graphs = true;
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;
+  int32_t last_solve[4] = {0, 0, 0, 0};  // nsg_last_solve_info
   nsg::GroupMeta *gmeta = nullptr;
   int32_t *row_perm = nullptr, *group_perm = nullptr;
   int32_t *gitems = nullptr;

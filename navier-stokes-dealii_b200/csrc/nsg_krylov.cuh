@@ -139,6 +139,7 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
       if (e.key == key) {
         NSG_CUDA(cudaGraphLaunch(e.exec, c->stream));
         c->launches += e.launches;
+        c->last_solve[1]++;
         return NSG_OK;
       }
     const int64_t l0 = c->launches;
@@ -153,6 +154,7 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
     cudaGraphDestroy(g);
     c->graphs.push_back(GraphEntry{key, ex, c->launches - l0});
     NSG_CUDA(cudaGraphLaunch(ex, c->stream));
+    c->last_solve[1]++;
     return NSG_OK;
   };
 

@@ -927,6 +927,25 @@ __global__ void k_scatter(int64_t n, const int32_t *__restrict__ idx, const doub
   if (i < n) dst[idx[i]] = src[i];
 }
 
+// FP64 pipe micro-benchmark ("the builder must measure the DFMA peak before quoting FP64 utilisation"):
+// every thread runs 8 independent chains of DFMA_ITERS fused multiply-adds; 2 flop each.
+constexpr int DFMA_ITERS = 2048, DFMA_CHAINS = 8, DFMA_THREADS = 256;
+__global__ void __launch_bounds__(DFMA_THREADS)
+k_dfma_peak(double *out, double a, double b) {
+  double x[DFMA_CHAINS];
+#pragma unroll
+  for (int j = 0; j < DFMA_CHAINS; ++j) x[j] = a + j + threadIdx.x;
+#pragma unroll 4
+  for (int i = 0; i < DFMA_ITERS; ++i) {
+#pragma unroll
+    for (int j = 0; j < DFMA_CHAINS; ++j) x[j] = fma(x[j], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < DFMA_CHAINS; ++j) s += x[j];
+  if (s == 123.456) out[0] = s;  // never true for the arguments used: keeps the chains alive
+}
+
 // ---- GMRES scalar bookkeeping on the device (single thread) ------------------------------------
 __device__ inline int32_t gm_check(const GmresCtl *c, int step, double val) {
   if (val <= c->tol) return 1;

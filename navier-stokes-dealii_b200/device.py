@@ -119,6 +119,12 @@ class DeviceProblem:
         self._L.nsg_gmres_history(self._h, out, n)
         return out[:n]
 
+    def last_solve_info(self):
+        """Which path the last solve() took: dict(fused, graph_replays, spmv_variant, orthogonalization)."""
+        out = np.zeros(4, np.int32)
+        nsg_check(self._L.nsg_last_solve_info(self._h, out))
+        return {"fused": bool(out[0]), "graph_replays": int(out[1]), "spmv_variant": int(out[2]), "orthogonalization": int(out[3])}
+
     def update_solution(self):
         nsg_check(self._L.nsg_update_solution(self._h))
 

@@ -182,6 +182,7 @@ void NavierStokesSolver::push_params(bool stokes) {
   P.neumann_id = stokes ? env_int("NS_STOKES_NEUMANN_ID", nullptr, 1) : neumann_id;
   P.use_mass = env_int("NS_USE_MASS", nullptr, 1);
   P.stokes = stokes ? 1 : 0;
+  P.dirichlet_diag = env_int("NS_DIRICHLET_DIAG", nullptr, 0);  // 0: TrilinosWrappers rule (reference path), 1: keep a non-zero diagonal
   NSG_CALL(nsg_set_params(dev, &P));
 }
 

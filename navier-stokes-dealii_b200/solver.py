@@ -59,6 +59,7 @@ class Parameters:
     stokes_max_iters: int = 2000
     stokes_rel_tol: float = 1e-6
     output_dir: str = ""                             # "" = no files (cpp:681-728 writes XDMF/HDF5)
+    dirichlet_diag: int = 0                          # include/nsg.h nsg_params: 0 TrilinosWrappers rule, 1 keep a non-zero diagonal
     force_boundary_id: int = -1                      # >= 0: record drag/lift on this boundary after every time step (N3)
     extra: dict = field(default_factory=dict)
 
@@ -130,7 +131,7 @@ class NavierStokesSolver:
         p = self.prm
         self.dev.set_params(nu=p.nu, rho=p.rho, p_out=p.p_out, deltat=self.deltat, forcing=(0.0, -p.g),
                             neumann_id=p.stokes_neumann_id if stokes else p.neumann_id,
-                            use_mass=1 if p.use_mass else 0, stokes=1 if stokes else 0)
+                            use_mass=1 if p.use_mass else 0, stokes=1 if stokes else 0, dirichlet_diag=p.dirichlet_diag)
 
     def _inlet(self):
         mode = self.prm.inlet_time_mode

@@ -90,7 +90,7 @@ struct Params {
   int32_t neumann_id;
   int32_t use_mass;  // 1: implicit-Euler mass terms as in cpp:249-251,288; 0: steady
   int32_t stokes;    // 1: assemble_stokes_system (cpp:380-531): viscous + B/Bt only, rhs = forcing + Neumann
-  int32_t pad;
+  int32_t dirichlet_diag;  // 0: Trilinos rule (diagonal always replaced by the block's first non-zero diagonal); 1: keep a non-zero diagonal
 };
 
 struct Ctx {
@@ -287,9 +287,13 @@ void assemble(Ctx &c) {
   }
 }
 
-// MatrixTools::apply_boundary_values, Trilinos block version, eliminate_columns=false
-// (cpp:375-376; SURVEY §9-7, with clear_row's "a non-zero diagonal is preserved" rule and
-// rhs_i = g_i * diag_i).  `sol` is delta_owned (Newton) or solution (Stokes).
+// MatrixTools::apply_boundary_values, Trilinos block version, eliminate_columns=false (cpp:375-376):
+// per diagonal block, d = |first non-zero diagonal entry in the local row range|; constrained rows are cleared in
+// every block of the block row (clear_rows(rows, d) on the diagonal block: the diagonal is ALWAYS set to d - the
+// Trilinos version does not look at the old diagonal), solution_i = g_i, rhs_i = g_i * d.
+// prm.dirichlet_diag == 1 gives deal.II's rule for its native SparseMatrix instead (a non-zero diagonal is kept,
+// rhs_i = g_i * J_ii) - the two cannot be told apart without a deal.II run (recalled semantics).
+// `sol` is delta_owned (Newton) or solution (Stokes).
 void apply_dirichlet(Ctx &c, int64_t n, const int32_t *dofs, const double *vals, std::vector<double> &sol) {
   for (int block = 0; block < 2; ++block) {
     const int64_t r0 = block == 0 ? 0 : c.n_u, r1 = block == 0 ? c.n_u : c.N;
@@ -310,9 +314,11 @@ void apply_dirichlet(Ctx &c, int64_t n, const int32_t *dofs, const double *vals,
       const int64_t pd = find_col(c, c.rowptr, c.col, i, (int32_t)i);
       for (int64_t p = c.rowptr[i]; p < c.rowptr[i + 1]; ++p)
         if (p != pd) c.J[p] = 0;  // clears the row in the diagonal and the off-diagonal blocks
-      if (pd >= 0 && c.J[pd] == 0) c.J[pd] = first_nz;
+      double diag = first_nz;
+      if (c.prm.dirichlet_diag == 1 && pd >= 0 && c.J[pd] != 0) diag = c.J[pd];
+      if (pd >= 0) c.J[pd] = diag;
       sol[i] = vals[k];
-      c.R[i] = vals[k] * c.J[pd];
+      c.R[i] = vals[k] * diag;
     }
   }
 }
@@ -643,8 +649,8 @@ void *orc_create(int64_t n_u, int64_t n_p, const int64_t *rowptr, const int32_t 
 void orc_destroy(void *h) { delete (Ctx *)h; }
 
 void orc_set_params(void *h, double nu, double rho, double p_out, double deltat, double fx, double fy,
-                    int32_t neumann_id, int32_t use_mass, int32_t stokes) {
-  ((Ctx *)h)->prm = Params{nu, rho, p_out, deltat, {fx, fy}, neumann_id, use_mass, stokes, 0};
+                    int32_t neumann_id, int32_t use_mass, int32_t stokes, int32_t dirichlet_diag) {
+  ((Ctx *)h)->prm = Params{nu, rho, p_out, deltat, {fx, fy}, neumann_id, use_mass, stokes, dirichlet_diag};
 }
 void orc_set_block_jacobi(void *h, int n_parts, const int64_t *u_off, const int64_t *p_off) {
   Ctx *c = (Ctx *)h;

@@ -24,7 +24,7 @@ def lib():
         L.orc_create.restype = vp
         L.orc_create.argtypes = [i64, i64, i64p, i32p, i64p, i32p, i64, i64, f64p, i32p, i32p, i64, i32p, i32p, i32p]
         L.orc_destroy.argtypes = [vp]
-        L.orc_set_params.argtypes = [vp, dbl, dbl, dbl, dbl, dbl, dbl, i32, i32, i32]
+        L.orc_set_params.argtypes = [vp, dbl, dbl, dbl, dbl, dbl, dbl, i32, i32, i32, i32]
         L.orc_set_block_jacobi.argtypes = [vp, C.c_int, i64p, i64p]
         L.orc_assemble.argtypes = [vp]
         L.orc_apply_dirichlet.argtypes = [vp, i64, i32p, f64p, i32]
@@ -68,8 +68,9 @@ class Oracle:
                                _nz(part.bface_tag))
 
     def set_params(self, nu=0.001, rho=1.0, p_out=10.0, deltat=0.05, forcing=(0.0, 0.0), neumann_id=10, use_mass=1,
-                   stokes=0):
-        self._L.orc_set_params(self._h, nu, rho, p_out, deltat, forcing[0], forcing[1], neumann_id, use_mass, stokes)
+                   stokes=0, dirichlet_diag=0):
+        self._L.orc_set_params(self._h, nu, rho, p_out, deltat, forcing[0], forcing[1], neumann_id, use_mass, stokes,
+                               dirichlet_diag)
 
     def set_block_jacobi(self, u_off, p_off):
         u_off = np.ascontiguousarray(u_off, np.int64)

@@ -56,6 +56,9 @@ dev = pkg.DeviceProblem(part, 0)
 print(f"device setup {time.perf_counter() - t0:.1f} s", flush=True)
 dev.set_params(neumann_id=neumann)
 dev.set_solution(sol); dev.set_solution_old(0.9 * sol)
+ms = dev.time_kernel(5, 3)
+sms = 148
+print(f"FP64 pipe micro-benchmark: {ms:.3f} ms per launch -> {sms * 67108864 * 2 / ms / 1e9:.1f} TFLOP/s (if {sms} SMs)", flush=True)
 ref = None
 for variant, stage, conc in ((4, 0, 1), (5, 0, 1), (5, 1, 1), (5, 2, 1), (5, 1, 0), (5, 2, 0)):
     os.environ["NSG_ASM_CONCURRENT"] = str(conc)

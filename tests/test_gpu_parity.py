@@ -76,6 +76,36 @@ def test_assembly_parity(pkg, case, mode, variant):
     dev.close()
 
 
+@pytest.mark.parametrize("rule", [0, 1])
+def test_dirichlet_diagonal_rules(pkg, rule):
+    """nsg_params.dirichlet_diag: the TrilinosWrappers rule (0, default: the diagonal of a constrained row is ALWAYS the
+    block's first non-zero diagonal d, rhs = g d) and deal.II's native rule (1: a non-zero diagonal is kept, rhs = g J_ii),
+    device against oracle (bitwise on the constrained rows) and against the rule restated in numpy, non-zero inlet data."""
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy")
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
+    assert np.abs(gv).max() > 1
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    out = []
+    for obj in (dev, o):
+        obj.set_params(dirichlet_diag=rule)
+        obj.set_solution(analytic_state(d, 0.1))
+        obj.assemble()
+        J0 = sp.csr_matrix((obj.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(d.n, d.n)).diagonal()
+        obj.apply_dirichlet(gd, gv)
+        J = sp.csr_matrix((obj.get_matrix_values(), part.jac_col, part.jac_rowptr), shape=(d.n, d.n))
+        out.append((J0, J, obj.get_residual(), obj.get_delta()))
+    (d0, Jd, Rd, xd), (o0, Jo, Ro, xo) = out
+    first = abs(d0[:d.n_u][np.flatnonzero(d0[:d.n_u])[0]])
+    want = np.full(len(gd), first) if rule == 0 else np.where(d0[gd] != 0, d0[gd], first)
+    assert np.array_equal(Jd.diagonal()[gd], want) and np.array_equal(Rd[gd], gv * want) and np.array_equal(xd[gd], gv)
+    rows = Jd[gd].tocoo()
+    assert np.abs(rows.data[rows.col != gd[rows.row]]).max() == 0
+    assert np.abs(Jd.diagonal()[gd] - Jo.diagonal()[gd]).max() <= 1e-12 * first
+    assert np.abs(Rd - Ro).max() <= 1e-12 * np.abs(Ro).max()
+    assert abs(dev.residual_norm() - o.residual_norm()) <= 1e-12 * o.residual_norm()
+    dev.close()
+
+
 def test_exact_cell_on_device(pkg, golden):
     """The sympy known-answer vector straight against the CUDA kernels (one cell)."""
     import os
@@ -125,6 +155,29 @@ def test_spmv_parity_and_linearity(pkg):
     dev.close()
 
 
+# The identity-preconditioned solve has three code paths (include/nsg.h, tuning keys 5 and 2): the whole solve as ONE
+# cooperative kernel (default up to 65 536 unknowns), the multi-kernel solver replaying CUDA graphs of the restart-cycle
+# segments (default above that: the path bench.py times), and the same with plain launches.  Every GMRES parity test
+# runs on all three and asserts through nsg_last_solve_info that the path it asked for is the one that ran.
+PATHS = {"fused": {5: 1}, "graphs": {5: 0, 2: 1}, "plain": {5: 0, 2: 0}}
+
+
+def set_path(dev, path):
+    for key, value in PATHS[path].items():
+        dev.set_tuning(key, value)
+
+
+def check_path(dev, path, spmv=None):
+    info = dev.last_solve_info()
+    assert info["fused"] == (path == "fused"), (path, info)
+    if path == "graphs":
+        assert info["graph_replays"] > 0, info
+    if path == "plain":
+        assert info["graph_replays"] == 0, info
+    if path != "fused" and spmv is not None:
+        assert info["spmv_variant"] == spmv, info
+
+
 def newton_trajectory(obj, part_or_none, gd, gv, n_steps, n, precond=0):
     """The reference's time loop (cpp:658-678) + solve_newton (cpp:590-627) on either backend."""
     hist = []
@@ -146,9 +199,30 @@ def newton_trajectory(obj, part_or_none, gd, gv, n_steps, n, precond=0):
     return hist, obj.get_solution()
 
 
-def test_reference_run_cmy(pkg):
+_CMY_ORACLE = {}
+
+
+def _cmy_oracle(pkg):
+    """The oracle side of test_reference_run_cmy, computed once for the three device paths."""
+    if not _CMY_ORACLE:
+        m, d, part, calls, neumann, inlet = build(pkg, "cmy")
+        gd, gv = d.dirichlet_values(calls, dict(time_factor=0.0, **inlet))
+        o = Oracle(part)
+        o.set_params()
+        o.set_solution(np.zeros(d.n))
+        o.push_time_level()
+        o.assemble()
+        o.apply_dirichlet(gd, gv)
+        _CMY_ORACLE["norm"] = o.residual_norm()
+        _CMY_ORACLE["first"] = (o.solve(0, 1e-2, 100000, 30, 0), o.gmres_history(), o.get_delta())
+        _CMY_ORACLE["traj"] = newton_trajectory(o, None, gd, gv, 2, d.n)
+    return _CMY_ORACLE
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_reference_run_cmy(pkg, path):
     """Config 1 on the mesh the reference opens (cpp:15) with its shipped parameters: 2 time steps of
-    Newton + GMRES(28, identity).
+    Newton + GMRES(28, identity), on each of the three solver paths.
 
     The first solve (153 steps, 5 restarts) must agree step for step to 1e-8.  Later solves take
     thousands of restarted steps at the reference's loose 1e-2 tolerance: two IEEE-correct
@@ -158,27 +232,33 @@ def test_reference_run_cmy(pkg):
     final iterate within 1e-2 (the accuracy the 1e-2 stopping test leaves in the iterate)."""
     m, d, part, calls, neumann, inlet = build(pkg, "cmy")
     gd, gv = d.dirichlet_values(calls, dict(time_factor=0.0, **inlet))
-    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    ref = _cmy_oracle(pkg)
+    dev = pkg.DeviceProblem(part, 0)
     dev.set_params()
-    o.set_params()
-    dev.set_tuning(0, 0)   # SpMV variant 0 sums each row in CSR order like the oracle: strict comparison
+    set_path(dev, path)
     # --- first Newton solve of the first time step: strict parity
-    for obj in (dev, o):
-        obj.set_solution(np.zeros(d.n))
-        obj.push_time_level()
-        obj.assemble()
-        obj.apply_dirichlet(gd, gv)
-    assert abs(dev.residual_norm() - o.residual_norm()) <= 1e-12 * o.residual_norm()
-    rd, ro = dev.solve(0, 1e-2, 100000, 30, 0), o.solve(0, 1e-2, 100000, 30, 0)
-    assert rd[0] == ro[0] == 153 and rd[2] == ro[2] == 0
-    h1, h2 = dev.gmres_history(), o.gmres_history()
-    assert np.abs(h1 / h2 - 1).max() <= 1e-8
-    xd, xo = dev.get_delta(), o.get_delta()
-    assert np.abs(xd - xo).max() <= 1e-8 * np.abs(xo).max()
-    # --- the whole trajectory, with the default (fastest) SpMV variant
-    dev.set_tuning(0, 1)
+    dev.set_solution(np.zeros(d.n))
+    dev.push_time_level()
+    dev.assemble()
+    dev.apply_dirichlet(gd, gv)
+    assert abs(dev.residual_norm() - ref["norm"]) <= 1e-12 * ref["norm"]
+    ro, h2, xo = ref["first"]
+    spmvs = (None,) if path == "fused" else (0, 7)     # 0 sums each row in CSR order like the oracle, 7 is the default
+    for spmv in spmvs:
+        if spmv is not None:
+            dev.set_tuning(0, spmv)
+        dev.set_delta(np.zeros(d.n))
+        rd = dev.solve(0, 1e-2, 100000, 30, 0)
+        check_path(dev, path, spmv)
+        assert rd[0] == ro[0] > 28 and rd[2] == ro[2] == 0
+        h1 = dev.gmres_history()
+        assert np.abs(h1 / h2 - 1).max() <= 1e-8
+        xd = dev.get_delta()
+        assert np.abs(xd - xo).max() <= 1e-8 * np.abs(xo).max()
+    # --- the whole trajectory on this path (default SpMV kernel)
     hd, sd = newton_trajectory(dev, part, gd, gv, 2, d.n)
-    ho, so = newton_trajectory(o, None, gd, gv, 2, d.n)
+    check_path(dev, path, 7)
+    ho, so = ref["traj"]
     assert [(a, b, c2 is None) for a, b, _, c2 in hd] == [(a, b, c2 is None) for a, b, _, c2 in ho]
     for (_, _, r1, i1), (_, _, r2, i2) in zip(hd, ho):
         assert abs(r1 - r2) <= 2e-2 * max(r2, 1e-2)
@@ -188,7 +268,46 @@ def test_reference_run_cmy(pkg):
     dev.close()
 
 
-def test_gmres_history_parity_live_inlet(pkg):
+def test_multikernel_gmres_above_the_fused_limit(pkg):
+    """The path bench.py times: more than 65 536 unknowns (cylinder_cmy.msh refined once, 117 324 DoFs), default tuning
+    = multi-kernel GMRES, SpMV variant 7, CUDA-graph replay of the cycle segments.  Against the oracle: residual history
+    of the first restart cycle to 1e-9, of three cycles (84 steps) to 1e-8, and the iterate after exactly 84 steps to
+    1e-8 (a fixed step count instead of a stopping test: both sides do the same number of steps by construction)."""
+    m, d, part, calls, neumann, inlet = build(pkg, "cmy", levels=1)
+    assert d.n > 65536
+    gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
+    dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
+    for obj in (dev, o):
+        obj.set_params(nu=0.01)
+        obj.set_solution(analytic_state(d, 0.05))
+        obj.set_solution_old(analytic_state(d, 0.045))
+        obj.assemble()
+        obj.apply_dirichlet(gd, gv)
+    x0 = dev.get_delta()
+    o.set_delta(x0)
+    ro = o.solve(0, 1e-10, 84, 30, 0)
+    h2, xo = o.gmres_history(), o.get_delta()
+    assert ro[0] == 84 and ro[2] != 0
+    for path in ("graphs", "plain"):
+        if path == "plain":
+            dev.set_tuning(2, 0)
+        for rep in range(2):       # the second solve replays the graphs captured by the first
+            dev.set_delta(x0)
+            rd = dev.solve(0, 1e-10, 84, 30, 0, check=False)
+            info = dev.last_solve_info()
+            assert not info["fused"] and info["spmv_variant"] == 7 and info["orthogonalization"] == 0, info
+            assert (info["graph_replays"] > 0) == (path == "graphs"), info
+            assert rd[0] == 84 and rd[2] == -3
+            h1 = dev.gmres_history()
+            assert np.abs(h1[:28] / h2[:28] - 1).max() <= 1e-9, (path, rep)
+            assert np.abs(h1 / h2 - 1).max() <= 1e-8, (path, rep)
+            xd = dev.get_delta()
+            assert np.abs(xd - xo).max() <= 1e-8 * np.abs(xo).max(), (path, rep)
+    dev.close()
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_gmres_history_parity_live_inlet(pkg, path):
     """Non-trivial data: inlet switched on (time factor 1), small convecting state, restarts exercised."""
     m, d, part, calls, neumann, inlet = build(pkg, "square")
     gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
@@ -202,12 +321,16 @@ def test_gmres_history_parity_live_inlet(pkg):
     x0 = dev.get_delta()
     ro = o.solve(0, 1e-6, 100000, 30, 0)
     h2, xo = o.gmres_history(), o.get_delta()
+    set_path(dev, path)
     # the first restart cycle agrees to 1e-9; along the several hundred restarted steps the 1e-16
     # differences in summation order are amplified by the loss of orthogonality -> 1e-4 at the end
-    for variant, tol in ((0, 1e-4), (1, 1e-4), (2, 1e-4)):
-        dev.set_tuning(0, variant)
+    # (the cooperative kernel has its own SpMV: the SpMV knob applies to the multi-kernel paths only)
+    for variant, tol in ((None, 1e-4),) if path == "fused" else ((0, 1e-4), (4, 1e-4), (7, 1e-4)):
+        if variant is not None:
+            dev.set_tuning(0, variant)
         dev.set_delta(x0)
         rd = dev.solve(0, 1e-6, 100000, 30, 0)
+        check_path(dev, path, variant)
         assert rd[2] == ro[2] == 0 and rd[0] > 28 and abs(rd[0] - ro[0]) <= 2
         h1 = dev.gmres_history()
         k = min(len(h1), len(h2))
