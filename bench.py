@@ -97,6 +97,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs of the NUMA node the GPU
+    hangs off: with 8 ranks on a two-socket host the H2D copies of the e2e step otherwise cross the socket link.
+    Returns a short description for the JSON line; a no-op when sysfs does not tell."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"numa node {node}: no allowed cpu"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -104,14 +130,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline_assembly(pkg, mesh, level, workers):
+def cpu_baseline_assembly(pkg, mesh, level, workers, start="fork"):
     """Oracle (CPU port of the reference loops) assembling `workers` independent replicas of the
     level-`level` mesh, one per process: the perfect-scaling upper bound of `mpirun -np workers`."""
     if workers == 1:
         r = _oracle_worker((mesh, level))
         return r[0], r[1], r[2], r[3]
     import multiprocessing as mp
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context(start)   # "spawn" from a process that holds a CUDA context (the GPU arm)
     with ctx.Pool(workers) as pool:
         res = pool.map(_oracle_worker, [(mesh, level)] * workers)
     n = res[0][0]
@@ -160,8 +186,9 @@ def run_reference(args):
               f"{args.mesh} mesh refined {level}x ({cells} cells, {n} DoFs each); assembly + Dirichlet timed")
     line = {"impl": "reference", "metric": "jacobian_assembly_mdofs", "value": v, "unit": "MDoF/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(1e3 * n * workers / (v * 1e6)),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, None),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, None), levels=level, full_workload_levels=args.levels, cells=int(cells),
+                           dofs=int(n), sample=sample),
             "gmres_ms_per_iteration_per_replica_dof": None,
             "cpu_baseline": {"value": v, "unit": "MDoF/s", "cores": workers, "kind": "port", "sample": sample,
                              "gmres_s_per_iteration_at_sample_size": float(np.mean(its)) * workers},
@@ -172,7 +199,7 @@ def run_reference(args):
 def workload_config(args, d):
     cfg = {"workload": f"synthetic uniformly refined cylinder mesh: {MESHES[args.mesh][0]} red-refined {args.levels}x, "
                        "P2-P1, state u=(sin(pi x)cos(pi y), -cos(pi x)sin(pi y)), p=xy, u_old=0.9u",
-           "mesh": args.mesh, "levels": args.levels, "gmres_its_cap": args.gmres_its,
+           "mesh": args.mesh, "levels": args.levels, "gmres_its_cap": args.gmres_its, "nu": args.nu, "deltat": args.deltat,
            "preconditioner": "identity (reference cpp:570)", "l2": "inputs larger than L2 (no flush needed)",
            "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, NCCL halo, Krylov all-reduce fused "
                           "into the reduction kernels (NVLink peer memory)"}
@@ -193,10 +220,17 @@ def main():
     ap.add_argument("--levels", type=int, default=8)
     ap.add_argument("--gmres-its", type=int, default=56)
     ap.add_argument("--cpu-level", type=int, default=None, help="refinement level of the CPU-baseline sample")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="weak (BASELINE.json configs[4]): --levels is the 1-GPU level, N GPUs refine floor(log4 N) more")
+    ap.add_argument("--nu", type=float, default=0.001, help="viscosity (reference hpp:703; configs[4]: 5e-4 = Re 200)")
+    ap.add_argument("--deltat", type=float, default=0.05, help="time step (reference main.cpp:13; configs[4]: small)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.cpu_level is None:
         args.cpu_level = {"cmy": 2, "mesh2d": 4}[args.mesh]
+    if args.scaling == "weak":      # cells per GPU: 1x, 1/2x, 1x, 1/2x of the 1-GPU mesh at N = 1, 2, 4, 8
+        args.base_levels = args.levels
+        args.levels = args.levels + int(np.floor(np.log(max(args.gpus, 1)) / np.log(4) + 1e-9))
     # torchrun exports OMP_NUM_THREADS=1; the host topology code (libnst.so) is OpenMP-parallel
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl != "reference":
@@ -212,6 +246,7 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("navier-stokes-dealii_b200")
@@ -224,7 +259,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(rank, world, uid[0])
         peer_ar = dev.enable_peer_allreduce(dist)
-    dev.set_params(neumann_id=neumann)
+    dev.set_params(neumann_id=neumann, nu=args.nu, deltat=args.deltat)
     dev.set_solution(sol)
     dev.set_solution_old(0.9 * sol)
     t_setup = time.perf_counter() - t_setup
@@ -298,6 +333,7 @@ def main():
     g_its = int(its_seen[-1])
     mgs_passes = sum(min(i % 28, 27) + 1 for i in range(g_its))   # add_and_dot launches of the MGS sweeps
     asm_k_ms = dev.time_kernel(0, reps)
+    fp64_tf = torch.cuda.get_device_properties(local).multi_processor_count * 67108864 * 2 / dev.time_kernel(5, 3) / 1e9
     asm_bytes = (8 * nnz + 8 * part.nnz_pm + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
     traffic = None   # dram__bytes_read+write per launch of the same kernel on the same workload, from profiles/
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
@@ -317,12 +353,12 @@ def main():
                           "frac": 32 * n_rows / aad_ms / 1e6 / hbm, "ms_per_launch": aad_ms,
                           "launches_per_step": int(mgs_passes), "share_of_step": mgs_passes * aad_ms / t_step_ms,
                           "note": "modified Gram-Schmidt chain: the largest share of a step; 32 B/DoF per pass"},
-        "assembly(k_cell_packets+k_assemble_u5+k_assemble_p5+k_neumann)": {
+        "assembly(k_cell_packets6+k_assemble_u6+k_assemble_p6+k_neumann)": {
             "bound": "hbm", "achieved": asm_bytes / asm_k_ms / 1e6, "peak": hbm, "unit": "GB/s",
             "frac": asm_bytes / asm_k_ms / 1e6 / hbm, "ms_per_launch": asm_k_ms, "algorithmic_bytes_per_launch": asm_bytes,
             "mdofs": part.n_own / asm_k_ms / 1e3,
-            "note": "variant 4; ncu: bound by L1/shared-memory wavefronts (LSU data pipe 72 %) and CTA barriers, FP64 pipe 21 % "
-                    "(profiles/r01_summary.md)"}}
+            "fp64_peak_tflops_measured": fp64_tf,
+            "note": "variant 5 (fan scheme); ncu summary and the FP64-pipe share: profiles/r02_summary.md"}}
 
     # the same GMRES steps with classical Gram-Schmidt (tuning key 3; NOT the reference default): reported beside
     dev.set_tuning(3, 1)
@@ -357,8 +393,9 @@ def main():
 
     if rank == 0:
         line = {"metric": "jacobian_assembly_mdofs", "value": value, "unit": "MDoF/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong",
+                "warmup": args.warmup, "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, d),
+                "host_binding": numa,
                 "assembly_ms": t_asm_ms, "gmres_ms_per_newton_step": t_sol_ms, "gmres_its": int(its_seen[-1]),
                 "gmres_ms_per_iteration": t_sol_ms / max(1, its_seen[-1]), "setup_s": t_setup,
                 "gmres_ms_per_newton_step_classical_gs": cgs_ms,
@@ -367,16 +404,19 @@ def main():
                 "gpu_launches": int(c1["launches"] - c0["launches"]), "clocks": clocks, "roofline": rl,
                 "roofline_other": rl_other,
                 "e2e": {"value": N / e2e_asm_s / 1e6, "unit": "MDoF/s",
-                        "h2d_bytes_per_step": int(8 * part.n_own + 12 * len(ld)), "d2h_bytes_per_step": int(8 + 8 * part.n_own),
-                        "newton_step_ms": 1e3 * e2e_step_s,
-                        "what": "set_solution(host) + assemble + Dirichlet + residual norm to host; newton_step_ms adds "
-                                "GMRES and get_delta(host)"}}
+                        "h2d_bytes_per_step": int(8 * part.n_own + 12 * len(ld)), "d2h_bytes_per_step": 8,
+                        "newton_step_ms": 1e3 * e2e_step_s, "newton_step_d2h_bytes": int(8 + 8 * part.n_own),
+                        "what": "value: set_solution(host, pinned) + assemble + Dirichlet + residual norm to host (8 bytes back); "
+                                "newton_step_ms adds GMRES and get_delta(host), whose bytes are newton_step_d2h_bytes"}}
         if not args.no_cpu_baseline and world == 1:
-            workers = 1
-            n_s, t_a, t_it, cells = cpu_baseline_assembly(pkg, args.mesh, args.cpu_level + 1, workers)
-            line["cpu_baseline"] = {"value": n_s / t_a / 1e6, "unit": "MDoF/s", "cores": workers, "kind": "port",
-                                    "sample": f"oracle (scalar C++ port of cpp:178-378) on the {args.mesh} mesh refined "
-                                              f"{args.cpu_level + 1}x: {cells} cells, {n_s} DoFs, one assembly + Dirichlet",
+            # the SAME measurement the reference arm (--impl reference) reports: all host cores, one replica per core
+            os.environ["OMP_NUM_THREADS"] = "1"
+            workers = os.cpu_count() or 1
+            n_s, t_a, t_it, cells = cpu_baseline_assembly(pkg, args.mesh, args.cpu_level, workers, start="spawn")
+            line["cpu_baseline"] = {"value": workers * n_s / t_a / 1e6, "unit": "MDoF/s", "cores": workers, "kind": "port",
+                                    "sample": f"{workers} independent replicas (one per core, perfect-scaling bound of mpirun -np "
+                                              f"{workers}) of the oracle (C++ port of cpp:178-378) on the {args.mesh} mesh refined "
+                                              f"{args.cpu_level}x ({cells} cells, {n_s} DoFs each): one assembly + Dirichlet",
                                     "gmres_s_per_iteration_at_sample_size": t_it}
         print(json.dumps(line))
     dev.close()

@@ -178,17 +178,15 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
 /* Tuning knobs that do not change what is computed (only the summation order inside a row):
- * key 0 = SpMV kernel variant: 0 CSR-stream through shared memory; 1 CSR-vector, 8 lanes per row;
- * 2 paired CSR (pair-compressed column index); 3 = 1 with all loads of a row in flight; 4 = 3
- * persistent with prefetched row extents; 5 bulk-async-copy (TMA) stream; 6 = 2 in the form of 4; 7 (default) = 4
- * serving the two rows of a velocity node together (they have the same column list: one index load and one x
- * gather feed two entries; bitwise the same result as 4); 8 = 7 with two entries per lane and step; 9 = 7 reading a
- * compact copy of the column index (built on demand; fewer bytes, measured slower). Measured rates: profiles/.
- * key 1 = assembly kernel variant: 0 literal 7-point quadrature loop for every term, as the reference sums
- * them; 1 the same integrals with the quadrature sum factored into pre-integrated reference-cell tables;
- * 2 = 1 on per-cell packets (everything that depends on the cell only is computed once per cell by a streaming
- * pre-pass); 3 = 2 integrating the rows in two column halves; 4 (default) = 2 with one (owner, cell) pair per
- * lane, lanes sorted by commit round, first-touch stores and a TMA bulk write-out. Measured: profiles/.
+ * key 0 = SpMV kernel variant: 0 CSR-stream through shared memory (every row summed in CSR order, as the reference's
+ * Epetra loop: the strict-parity kernel); 1 CSR-vector, 8 lanes per row; 4 = 1 with all loads of a row in flight,
+ * persistent, prefetched row extents; 7 (default) = 4 serving the two rows of a velocity node together (they have the
+ * same column list: one index load and one x gather feed two entries; bitwise the same result as 4). The six other
+ * variants measured in round 1 (profiles/r01_summary.md) were slower and have been removed.
+ * key 1 = assembly kernel variant: 0 literal 7-point quadrature loop for every term, contributions added in ascending
+ * cell order as the reference's loop adds them (strict-parity kernel); 4 per-cell packets from a streaming pre-pass, one
+ * (owner, cell) pair per lane, lanes sorted by commit round, first-touch stores, TMA bulk write-out (round-1 default,
+ * serves any mesh); 5 (default) the "fan" scheme, see below. Variants 1-3 of round 1 were slower and have been removed.
  * key 3 = Gram-Schmidt variant of SolverGMRES: 0 (default) modified, the chain of add_and_dot that deal.II
  * <= 9.4 runs; 1 classical (h = V^T w, w -= V h: two passes and two all-reduces per step
  * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).
@@ -202,9 +200,7 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * key 1 = 5 (default since round 2): the "fan" scheme - one (owner, cell) pair per lane integrated in a rotated local
  * frame (owner = local vertex 0 / edge 0: all tables are immediates), the lanes of an owner in one warp in fan order,
  * shared-edge contributions combined by warp shuffles, every entry stored exactly once (no read-modify-write, no
- * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically.
- * key 6 = how variant 5 brings the per-cell packets to its lanes: 0 global loads, 1 (default) cp.async staging in shared
- * memory, 2 one bulk copy (TMA engine) per cell. */
+ * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically. */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

@@ -39,7 +39,17 @@ void dev_free(T *&p) {
   p = nullptr;
 }
 
-inline int grid_for(int64_t n, int threads, int cap = 148 * 16) {
+// number of SMs of the current device (148 on a B200; a MIG/MPS slice has fewer): every persistent grid is sized from it
+inline int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+inline int grid_for(int64_t n, int threads, int cap = 0) {
+  if (cap <= 0) cap = sm_count() * 16;
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, cap));
 }
 inline int red_grid(int64_t n) {
@@ -499,7 +509,6 @@ static int build_worklist5(nsg_ctx *c, int kind, const int32_t *cd, WorkList *ou
 
 static void free_worklist(WorkList &w) {
   dev_free(w.chunks);
-  dev_free(w.cells);
   dev_free(w.tdesc);
   dev_free(w.tdesc3);
   dev_free(w.recs);
@@ -518,74 +527,18 @@ static void make_spmv_chunks(const int64_t *rowptr, int64_t n, std::vector<int32
   }
 }
 
-// Permutation that sorts rows (or groups) by length inside windows of `window` entries, so that the
-// 8-lane groups of one warp iterate the same number of times while x/y locality is kept.
-static void length_sorted_perm(int64_t n, int64_t window, const std::vector<int64_t> &len, std::vector<int32_t> &perm) {
-  perm.resize(n);
-#pragma omp parallel for schedule(static)
-  for (int64_t w0 = 0; w0 < n; w0 += window) {
-    const int64_t w1 = std::min(n, w0 + window);
-    for (int64_t i = w0; i < w1; ++i) perm[i] = (int32_t)i;
-    std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int32_t a, int32_t b) { return len[a] > len[b]; });
-  }
-}
-
-// pair-compressed column index (SpMV variant 2); returns false if the pattern does not have the
-// node-pair structure (then the plain CSR kernels are used)
-static bool build_paired_index(const nsg_ctx *c, const int64_t *rowptr, const int32_t *col, std::vector<GroupMeta> &meta,
-                               std::vector<int32_t> &items) {
-  const int64_t nu = c->n_own_u, nown = c->n_own, gu0 = nown, gu1 = nown + c->n_ghost_u;
-  const int64_t n_ug = nu / 2, G = n_ug + c->n_own_p;
-  meta.assign(G, GroupMeta{});
-  std::vector<int64_t> cnt(G + 1, 0);
-  auto is_pair_start = [&](int64_t cc, int64_t next) {
-    if (cc < nu) return (cc % 2 == 0) && next == cc + 1;
-    if (cc >= gu0 && cc < gu1) return ((cc - gu0) % 2 == 0) && next == cc + 1;
-    return false;
-  };
-  auto is_u = [&](int64_t cc) { return cc < nu || (cc >= gu0 && cc < gu1); };
+// SpMV variant 7 serves the two rows of a velocity node together: true if rows 2g and 2g+1 have the same column list
+// for every owned velocity node (full coupling of the two components, cpp:107-110)
+static bool rows_come_in_pairs(const nsg_ctx *c, const int64_t *rowptr, const int32_t *col) {
+  const int64_t n_ug = c->n_own_u / 2;
+  if (c->n_own_u % 2) return false;
   int bad = 0;
 #pragma omp parallel for schedule(static) reduction(+ : bad)
-  for (int64_t g = 0; g < G; ++g) {
-    const int64_t row = g < n_ug ? 2 * g : nu + (g - n_ug);
-    const int64_t s = rowptr[row], e = rowptr[row + 1];
-    if (g < n_ug) {
-      if (rowptr[row + 2] - e != e - s || std::memcmp(col + s, col + e, 4 * (size_t)(e - s)) != 0) bad++;
-    }
-    int seg = 0, n[4] = {0, 0, 0, 0};
-    for (int64_t p = s; p < e;) {
-      const int64_t cc = col[p];
-      const bool pr = is_pair_start(cc, p + 1 < e ? col[p + 1] : -1);
-      if (!pr && is_u(cc)) bad++;  // an unpaired velocity column
-      const int want = cc < nu ? 0 : (cc < nown ? 1 : (cc < gu1 ? 2 : 3));
-      if (want < seg) bad++;
-      seg = want;
-      n[seg]++;
-      p += pr ? 2 : 1;
-    }
-    for (int q = 0; q < 4; ++q)
-      if (n[q] > 65535) bad++;
-    meta[g].val_start = s;
-    meta[g].np1 = (uint16_t)n[0], meta[g].ns1 = (uint16_t)n[1], meta[g].np2 = (uint16_t)n[2], meta[g].ns2 = (uint16_t)n[3];
-    cnt[g + 1] = n[0] + n[1] + n[2] + n[3];
+  for (int64_t g = 0; g < n_ug; ++g) {
+    const int64_t s = rowptr[2 * g], e = rowptr[2 * g + 1];
+    if (rowptr[2 * g + 2] - e != e - s || std::memcmp(col + s, col + e, 4 * (size_t)(e - s)) != 0) bad++;
   }
-  if (bad) return false;
-  for (int64_t g = 0; g < G; ++g) cnt[g + 1] += cnt[g];
-  if (cnt[G] >= (int64_t)UINT32_MAX) return false;
-  items.resize(cnt[G]);
-#pragma omp parallel for schedule(static)
-  for (int64_t g = 0; g < G; ++g) {
-    const int64_t row = g < n_ug ? 2 * g : nu + (g - n_ug);
-    const int64_t s = rowptr[row], e = rowptr[row + 1];
-    meta[g].item_start = (uint32_t)cnt[g];
-    int64_t w = cnt[g];
-    for (int64_t p = s; p < e;) {
-      const int64_t cc = col[p];
-      items[w++] = (int32_t)cc;
-      p += is_pair_start(cc, p + 1 < e ? col[p + 1] : -1) ? 2 : 1;
-    }
-  }
-  return true;
+  return bad == 0;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -649,46 +602,18 @@ static int dev_multi_axpy_norm(nsg_ctx *c, int64_t n, double *w, const double *b
 
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
   NSG_TRY(halo_exchange(c, x_with_ghosts));
-  if (c->spmv_variant == 2 && c->have_paired)
-    k_spmv_paired<<<(unsigned)((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
-  else if (c->spmv_variant == 6 && c->have_paired) {
-    static int per_sm = 0;
-    if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_paired_p, SPMV_THREADS, 0);
-    k_spmv_paired_p<<<(unsigned)std::min<int64_t>((c->n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm, 1)),
-                      SPMV_THREADS, 0, c->stream>>>(c->n_groups, c->n_ugroups, c->gmeta, c->gitems, c->vals, x_with_ghosts, y, state);
-  } else if (c->spmv_variant == 5)
-    k_spmv_tma<<<(unsigned)std::min<int64_t>(c->spmv_n_chunks, 148 * 2), SPMV_THREADS, sizeof(TmaStage) * TMA_STAGES, c->stream>>>(
-        c->spmv_n_chunks, c->spmv_chunk_rows, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  else if (c->spmv_variant == 3)
-    k_spmv_vec8u<false><<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-        c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  else if (c->spmv_variant == 9) {
-    static int per_sm9 = 0;
-    if (!per_sm9) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, k_spmv_rowpair_c<true>, SPMV_THREADS, 0);
-    const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
-    k_spmv_rowpair_c<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm9, 1)),
-                             SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col7, c->vals, x_with_ghosts, y, state);
-  } else if (c->spmv_variant == 8) {
-    static int per_sm8 = 0;
-    if (!per_sm8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k_spmv_rowpair2<true>, SPMV_THREADS, 0);
-    const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
-    k_spmv_rowpair2<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm8, 1)),
-                            SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  } else if (c->spmv_variant == 7) {
+  if (c->spmv_variant == 7) {
     static int per_sm7 = 0;
     if (!per_sm7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm7, k_spmv_rowpair<true>, SPMV_THREADS, 0);
     const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
-    k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm7, 1)),
+    k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm7, 1)),
                            SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  } else if (c->spmv_variant == 4)
-  {
+  } else if (c->spmv_variant == 4) {
     static int per_sm = 0;
     if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_vec8u<true>, SPMV_THREADS, 0);
-    k_spmv_vec8u<true><<<(unsigned)std::min<int64_t>((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS, 148 * std::max(per_sm, 1)),
+    k_spmv_vec8u<true><<<(unsigned)std::min<int64_t>((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm, 1)),
                          SPMV_THREADS, 0, c->stream>>>(c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  }
-  else if (c->spmv_variant >= 1)
+  } else if (c->spmv_variant == 1)
     k_spmv_vec8<<<(unsigned)((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
         c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
   else
@@ -706,15 +631,6 @@ static AsmParams asm_params(const nsg_ctx *c) {
   P.use_mass = c->prm.use_mass, P.stokes = c->prm.stokes, P.neumann_id = c->prm.neumann_id;
   P.debug = std::getenv("NSG_ASM_DEBUG") ? std::atoi(std::getenv("NSG_ASM_DEBUG")) : 0;
   return P;
-}
-
-template <int STAGE>
-static int launch_u6(nsg_ctx *c, const AsmParams &P) {
-  const unsigned grid = (unsigned)c->wl_u6.n_chunks;
-  const size_t smem = sizeof(double) * (size_t)c->wl_u6.max_stage;
-  k_assemble_u6<4, STAGE><<<grid, NPC6, smem, c->stream>>>(c->wl_u6, c->vals, c->R, c->cellpk, P);
-  NSG_LAUNCH_CHECK(c);
-  return NSG_OK;
 }
 
 static int launch_assembly(nsg_ctx *c) {
@@ -746,12 +662,9 @@ static int launch_assembly(nsg_ctx *c) {
       NSG_LAUNCH_CHECK(c);
     }
     if (c->wl_u6.n_chunks > 0) {
-      if (c->asm_stage == 0)
-        NSG_TRY(launch_u6<0>(c, P));
-      else if (c->asm_stage == 2)
-        NSG_TRY(launch_u6<2>(c, P));
-      else
-        NSG_TRY(launch_u6<1>(c, P));
+      k_assemble_u6<4><<<(unsigned)c->wl_u6.n_chunks, NPC6, sizeof(double) * (size_t)c->wl_u6.max_stage, c->stream>>>(
+          c->wl_u6, c->vals, c->R, c->cellpk, c->geom8, P);
+      NSG_LAUNCH_CHECK(c);
     }
     if (fork)
       NSG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -801,48 +714,6 @@ static int launch_assembly(nsg_ctx *c) {
       NSG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     else
       NSG_TRY(launch_p());
-  } else if (c->asm_variant >= 2) {
-    if (c->n_cells > 0) {
-      k_cell_packets<<<grid_for(c->n_cells, 128, 1 << 30), 128, 0, c->stream>>>(c->n_cells, c->geom, c->cell_dofs, c->sol, c->sol_old,
-                                                                                P, c->cellpk);
-      NSG_LAUNCH_CHECK(c);
-    }
-    if (c->wl_u.n_chunks > 0) {
-      const unsigned grid = (unsigned)c->wl_u.n_chunks;
-      const size_t smem = sizeof(double) * (size_t)c->wl_u.max_stage;
-      // resident CTAs per SM the register allocation is sized for (env NSG_ASM3_MINB: 3, 4 or 5)
-      const int minb = std::getenv("NSG_ASM3_MINB") ? std::atoi(std::getenv("NSG_ASM3_MINB")) : 4;
-      if (c->asm_variant == 3) {
-        if (minb <= 3)
-          k_assemble_u4<3><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-        else if (minb == 4)
-          k_assemble_u4<4><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-        else
-          k_assemble_u4<5><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-      } else if (minb <= 3)
-        k_assemble_u3<3><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-      else if (minb == 4)
-        k_assemble_u3<4><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-      else
-        k_assemble_u3<5><<<grid, NPC, smem, c->stream>>>(c->wl_u, c->vals, c->R, c->cellpk, P);
-      NSG_LAUNCH_CHECK(c);
-    }
-    if (c->wl_p.n_chunks > 0) {
-      k_assemble_p3<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
-          c->wl_p, c->n_own_u, c->vals, c->pm_vals, c->R, c->geom, P);
-      NSG_LAUNCH_CHECK(c);
-    }
-  } else if (c->asm_variant == 1) {
-    if (c->wl_u.n_chunks > 0) {
-      k_assemble_u2<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
-          c->wl_u, c->rowptr, c->vals, c->R, c->geom, c->cell_dofs, c->sol, c->sol_old, P);
-      NSG_LAUNCH_CHECK(c);
-    }
-    if (c->wl_p.n_chunks > 0) {
-      k_assemble_p2<<<(unsigned)c->wl_p.n_chunks, NPC, sizeof(double) * (size_t)c->wl_p.max_stage, c->stream>>>(
-          c->wl_p, c->n_own_u, c->rowptr, c->vals, c->pm_rowptr, c->pm_vals, c->R, c->geom, P);
-      NSG_LAUNCH_CHECK(c);
-    }
   } else {
   if (c->wl_u.n_chunks > 0) {
     k_assemble_u<<<(unsigned)c->wl_u.n_chunks, NPC, sizeof(double) * (size_t)c->wl_u.max_stage, c->stream>>>(
@@ -884,15 +755,6 @@ static int ensure_slot_worklists(nsg_ctx *c) {
     return fail(NSG_ERR_ARG, "a chunk of matrix rows does not fit in shared memory (vertex valence too high)");
   NSG_CUDA(cudaFuncSetAttribute(k_assemble_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
   NSG_CUDA(cudaFuncSetAttribute(k_assemble_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_u4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_u, 1024)));
-  NSG_CUDA(cudaFuncSetAttribute(k_assemble_p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_p, 1024)));
   if (fetch_cols) {
     c->h_col.clear(), c->h_col.shrink_to_fit();
     c->h_pm_col.clear(), c->h_pm_col.shrink_to_fit();
@@ -1059,8 +921,7 @@ int nsg_create(int device, nsg_ctx **out) {
   auto *c = new nsg_ctx;
   c->device = device;
   c->peer.n_ranks = 1;
-  if (const char *v = std::getenv("NSG_ASM_VARIANT")) c->asm_variant = std::min(std::max(std::atoi(v), 0), 5);
-  if (const char *v = std::getenv("NSG_ASM_STAGE")) c->asm_stage = std::min(std::max(std::atoi(v), 0), 2);
+  if (const char *v = std::getenv("NSG_ASM_VARIANT")) c->asm_variant = (std::atoi(v) == 0 || std::atoi(v) == 4) ? std::atoi(v) : 5;
   nsg_params_default(&c->prm);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -1102,8 +963,8 @@ void nsg_destroy(nsg_ctx *c) {
     if (m) cudaIpcCloseMemHandle(m);
   dev_free(c->mailbox), dev_free(c->ar_seq), dev_free(c->gf_partials);
   if (c->comm) nccl_api().CommDestroy(c->comm);
-  dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->col7), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
-  dev_free(c->gmeta), dev_free(c->gitems), dev_free(c->row_perm), dev_free(c->group_perm), dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
+  dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
+  dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
   free_worklist(c->wl_u), free_worklist(c->wl_p), free_worklist(c->wl_u5), free_worklist(c->wl_p5);
   free_worklist(c->wl_u6), free_worklist(c->wl_p6);
   dev_free(c->geom8);
@@ -1161,7 +1022,6 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   NSG_TRY(upload(c, &c->pm_rowptr, pm_rowptr, n + 1));
   NSG_TRY(upload(c, &c->pm_col, pm_col, c->pm_nnz));
   NSG_TRY(dev_alloc(&c->vals, c->nnz + 16));
-  NSG_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TmaStage) * TMA_STAGES)));
   NSG_TRY(dev_alloc(&c->pm_vals, c->pm_nnz));
   NSG_CUDA(cudaMemsetAsync(c->vals, 0, 8 * (size_t)std::max<int64_t>(c->nnz, 1), c->stream));
   NSG_CUDA(cudaMemsetAsync(c->pm_vals, 0, 8 * (size_t)std::max<int64_t>(c->pm_nnz, 1), c->stream));
@@ -1175,30 +1035,8 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   make_spmv_chunks(jac_rowptr, n, chunks);
   c->spmv_n_chunks = (int64_t)chunks.size() - 1;
   NSG_TRY(upload(c, &c->spmv_chunk_rows, chunks.data(), (int64_t)chunks.size()));
-  {
-    std::vector<GroupMeta> meta;
-    std::vector<int32_t> items;
-    c->have_paired = build_paired_index(c, jac_rowptr, jac_col, meta, items);
-    if (c->have_paired) {
-      std::vector<int64_t> len(meta.size());
-      std::vector<int32_t> perm;
-      for (size_t g = 0; g < meta.size(); ++g) len[g] = 2 * meta[g].np1 + meta[g].ns1 + 2 * meta[g].np2 + meta[g].ns2;
-      length_sorted_perm((int64_t)meta.size(), 1024, len, perm);
-      std::vector<GroupMeta> sorted(meta.size());
-      for (size_t i = 0; i < meta.size(); ++i) {
-        sorted[i] = meta[perm[i]];
-        sorted[i].pad = (uint32_t)perm[i];
-      }
-      meta.swap(sorted);
-      c->n_ugroups = n_own_u / 2;
-      c->n_groups = (int64_t)meta.size();
-      c->n_items = (int64_t)items.size();
-      NSG_TRY(upload(c, &c->gmeta, meta.data(), c->n_groups));
-      NSG_TRY(upload(c, &c->gitems, items.data(), c->n_items));
-      NSG_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    c->spmv_variant = c->have_paired ? 7 : 4;  // fastest measured (profiles/r01_summary.md); 7 needs the node-pair row structure
-  }
+  c->have_paired = rows_come_in_pairs(c, jac_rowptr, jac_col);
+  c->spmv_variant = c->have_paired ? 7 : 4;  // fastest measured (profiles/r01_summary.md); 7 needs the node-pair row structure
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
     NSG_CUDA(cudaMemsetAsync(*v, 0, 8 * (size_t)c->stride, c->stream));
@@ -1249,9 +1087,7 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     const size_t s6u = 8 * (size_t)c->wl_u6.max_stage, s6p = 8 * (size_t)c->wl_p6.max_stage;
     c->fan_ok = ok_u && ok_p && s6u <= 200 * 1024 && s6p <= 200 * 1024;
     if (c->fan_ok) {
-      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
-      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
-      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
       NSG_CUDA(cudaFuncSetAttribute(k_assemble_p6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6p, 1024)));
     } else {
       free_worklist(c->wl_u6), free_worklist(c->wl_p6);
@@ -1452,7 +1288,7 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
     if (!has_blk[b]) continue;
     const int64_t r0 = b == 0 ? 0 : c->n_own_u, r1 = b == 0 ? c->n_own_u : c->n_own;
     if (r1 > r0) {
-      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, 148 * 8), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
+      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, sm_count() * 8), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
       NSG_LAUNCH_CHECK(c);
     }
     k_first_nonzero_diag_value<<<1, 1, 0, c->stream>>>(c->diag_pos, c->vals, c->first_idx + b, c->scal + 8 + b);
@@ -1694,19 +1530,8 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   switch (key) {
     case 0:
-      if (value < 0 || value > 9) return fail(NSG_ERR_ARG, "spmv variant must be 0..9");
-      if ((value == 2 || value == 6 || value == 7 || value == 8 || value == 9) && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
-      if (value == 9 && !c->col7) {  // compact column index: the shared column list of a velocity node once (built on demand)
-        const int64_t n = c->n_own, nu = c->n_own_u;
-        const int64_t n7 = (c->h_rowptr[nu] >> 1) + (c->h_rowptr[n] - c->h_rowptr[nu]);
-        NSG_TRY(dev_alloc(&c->col7, n7 + 16));
-        NSG_CUDA(cudaMemsetAsync(c->col7, 0, 4 * (size_t)(n7 + 16), c->stream));
-        const int64_t n_groups = nu / 2 + c->n_own_p;
-        if (n_groups > 0) {
-          k_build_col7<<<grid_for(n_groups * 32, 256, 1 << 30), 256, 0, c->stream>>>(nu / 2, n, c->rowptr, c->col, c->col7);
-          NSG_LAUNCH_CHECK(c);
-        }
-      }
+      if (value != 0 && value != 1 && value != 4 && value != 7) return fail(NSG_ERR_ARG, "spmv variant must be 0, 1, 4 or 7 (see nsg.h)");
+      if (value == 7 && !c->have_paired) return fail(NSG_ERR_STATE, "the pattern has no node-pair structure");
       c->spmv_variant = value;
       for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
       c->graphs.clear();  // captured segments embed the SpMV kernel
@@ -1729,16 +1554,12 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       c->graphs.clear();
       return NSG_OK;
     case 1:
-      if (value < 0 || value > 5) return fail(NSG_ERR_ARG, "assembly variant must be 0..5 (see nsg.h)");
+      if (value != 0 && value != 4 && value != 5) return fail(NSG_ERR_ARG, "assembly variant must be 0, 4 or 5 (see nsg.h)");
       if (value == 5 && c->have_mesh && !c->fan_ok)
         return fail(NSG_ERR_STATE, "the fan scheme (variant 5) cannot serve this mesh (not an oriented manifold triangulation)");
       if (value < 4) NSG_TRY(ensure_slot_worklists(c));
       if (value == 4) NSG_TRY(ensure_round_worklists(c, nullptr));
       c->asm_variant = value;
-      return NSG_OK;
-    case 6:
-      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "packet staging must be 0 (global loads), 1 (cp.async) or 2 (bulk copies)");
-      c->asm_stage = value;
       return NSG_OK;
     default: return fail(NSG_ERR_ARG, "unknown tuning key");
   }

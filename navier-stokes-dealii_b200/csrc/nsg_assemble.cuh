@@ -322,300 +322,8 @@ k_assemble_p(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ row
   for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
 }
 
-// ---- variant 1 ("factored"): the same integrals with the q-sum taken out where the integrand factors ----
-// On an affine cell  g = A ghat (A = J^-T, d = |det J|):  mass and stiffness rows are geometry x table;
-// grad u^k is affine in (xi,eta) so the first Frechet term is three table rows; only the second Frechet
-// term and the convective residual keep a quadrature loop, and that loop runs in reference space (no
-// per-point J^-T products).  ~0.45x the fp64 instructions of variant 0, same results to rounding.
-#ifndef NSG_ASM2_MINB
-#define NSG_ASM2_MINB 3
-#endif
-__global__ void __launch_bounds__(NPC, NSG_ASM2_MINB)
-k_assemble_u2(const WorkList wl, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
-              double *__restrict__ R, const double *__restrict__ geom, const int32_t *__restrict__ cell_dofs,
-              const double *__restrict__ sol, const double *__restrict__ sol_old, const AsmParams P) {
-  extern __shared__ double s_vals[];
-  // tables indexed by the owner's (per-thread) local index k live in shared memory
-  __shared__ double s_psi[7][6], s_Mh[6][6], s_Mx[6][6], s_My[6][6], s_K00[6][6], s_K01s[6][6], s_K11[6][6], s_Bh[6][3][2],
-      s_mh[6];
-  const int t = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const ChunkInfo ci = wl.chunks[b];
-  const int ng = ci.g1 - ci.g0;
-  const int64_t rs = rowptr[2 * (int64_t)ci.g0], re = rowptr[2 * (int64_t)ci.g1];
-  const int cnt = (int)(re - rs);
-  double *s_res = s_vals + cnt;
-  for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
-  for (int i = t; i < 42; i += NPC) (&s_psi[0][0])[i] = (&c_fe.psi[0][0])[i];
-  for (int i = t; i < 36; i += NPC) {
-    (&s_Mh[0][0])[i] = (&c_fe2.Mh[0][0])[i];
-    (&s_Mx[0][0])[i] = (&c_fe2.Mx[0][0])[i];
-    (&s_My[0][0])[i] = (&c_fe2.My[0][0])[i];
-    (&s_K00[0][0])[i] = (&c_fe2.K00[0][0])[i];
-    (&s_K01s[0][0])[i] = (&c_fe2.K01s[0][0])[i];
-    (&s_K11[0][0])[i] = (&c_fe2.K11[0][0])[i];
-    (&s_Bh[0][0][0])[i] = (&c_fe2.Bh[0][0][0])[i];
-  }
-  for (int i = t; i < 6; i += NPC) s_mh[i] = c_fe2.mh[i];
-  __syncthreads();
-
-  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
-  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
-  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
-  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
-  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
-  const int64_t node = ci.g0 + gl;
-  const int64_t r0 = rowptr[2 * node];
-  const int len = (int)(rowptr[2 * node + 1] - r0);
-  double *row0 = s_vals + (r0 - rs), *row1 = row0 + len;
-  const double nurho = P.nu * P.rho;
-  const bool ns = !P.stokes;
-
-  for (int j = 0; j < ASM_PPT; ++j) {
-    uint4 ra = make_uint4(0xffffffffu, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (have) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
-      ra = __ldcs(rp);
-      rb = __ldcs(rp + 1);
-    }
-    const bool work = (int)ra.x >= 0;
-    double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
-    double res0 = 0.0, res1 = 0.0;
-#pragma unroll
-    for (int l = 0; l < 6; ++l) A00[l] = A01[l] = A10[l] = A11[l] = 0.0;
-#pragma unroll
-    for (int m = 0; m < 3; ++m) B0[m] = B1[m] = 0.0;
-    if (work) {
-      const int64_t c = (int)ra.x;
-      const int k = (int)ra.y;
-      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
-                   a11 = __ldg(geom + 5 * c + 3), d = __ldg(geom + 5 * c + 4);
-      const int32_t *cd = cell_dofs + 15 * c;
-      double u[6][2];
-      double G0[2][2] = {{0, 0}, {0, 0}}, Gx[2][2] = {{0, 0}, {0, 0}}, Gy[2][2] = {{0, 0}, {0, 0}};
-      double H[2][6][2];
-      double cr0 = 0.0, cr1 = 0.0;
-      if (ns) {
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          const int32_t d0 = __ldg(cd + uidx(l));
-          u[l][0] = sol[d0];
-          u[l][1] = sol[d0 + 1];
-        }
-        // reference gradient of u^k is affine: Ghat(xi,eta) = Gh0 + Ghx xi + Ghy eta; physical G_ab = sum_c A_bc Ghat_ac
-        double h0[2][2] = {{0, 0}, {0, 0}}, hx[2][2] = {{0, 0}, {0, 0}}, hy[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll
-        for (int l = 0; l < 6; ++l)
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              h0[a][cc] += u[l][a] * c_fe2.ga[l][cc];
-              hx[a][cc] += u[l][a] * c_fe2.gb[l][cc];
-              hy[a][cc] += u[l][a] * c_fe2.gc[l][cc];
-            }
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          G0[a][0] = a00 * h0[a][0] + a01 * h0[a][1], G0[a][1] = a10 * h0[a][0] + a11 * h0[a][1];
-          Gx[a][0] = a00 * hx[a][0] + a01 * hx[a][1], Gx[a][1] = a10 * hx[a][0] + a11 * hx[a][1];
-          Gy[a][0] = a00 * hy[a][0] + a01 * hy[a][1], Gy[a][1] = a10 * hy[a][0] + a11 * hy[a][1];
-        }
-#pragma unroll
-        for (int l = 0; l < 6; ++l) H[0][l][0] = H[0][l][1] = H[1][l][0] = H[1][l][1] = 0.0;
-        // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l, and the convective residual
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          double U0 = 0, U1 = 0;
-#pragma unroll
-          for (int l = 0; l < 6; ++l) {
-            U0 += u[l][0] * c_fe.psi[q][l];
-            U1 += u[l][1] * c_fe.psi[q][l];
-          }
-          const double wk = c_fe.w[q] * s_psi[q][k];
-          const double c0 = wk * U0, c1 = wk * U1;
-#pragma unroll
-          for (int l = 0; l < 6; ++l) {
-            H[0][l][0] += c0 * c_fe.dpsi[q][l][0];
-            H[0][l][1] += c0 * c_fe.dpsi[q][l][1];
-            H[1][l][0] += c1 * c_fe.dpsi[q][l][0];
-            H[1][l][1] += c1 * c_fe.dpsi[q][l][1];
-          }
-          const double g00 = G0[0][0] + Gx[0][0] * c_fe2.qx[q] + Gy[0][0] * c_fe2.qy[q];
-          const double g01 = G0[0][1] + Gx[0][1] * c_fe2.qx[q] + Gy[0][1] * c_fe2.qy[q];
-          const double g10 = G0[1][0] + Gx[1][0] * c_fe2.qx[q] + Gy[1][0] * c_fe2.qy[q];
-          const double g11 = G0[1][1] + Gx[1][1] * c_fe2.qx[q] + Gy[1][1] * c_fe2.qy[q];
-          cr0 += wk * (U0 * g00 + U1 * g10);
-          cr1 += wk * (U0 * g01 + U1 * g11);
-        }
-      }
-      // S = A^T A: g_k . g_l = ghat_k^T S ghat_l
-      const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
-      const double rd = P.rho * d, md = (P.use_mass && ns) ? P.dt_inv * d : 0.0, vd = nurho * d;
-      double rv0 = 0.0, rv1 = 0.0;
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double Mkl = s_Mh[k][l];
-        const double Kkl = S00 * s_K00[k][l] + S01 * s_K01s[k][l] + S11 * s_K11[k][l];  // (1/d) sum_q w g_k.g_l
-        const double D = md * Mkl + vd * Kkl;
-        A00[l] = D;
-        A11[l] = D;
-        if (ns) {
-          const double Mx = s_Mx[k][l], My = s_My[k][l];
-          // rho w G_ab psi_k psi_l  (cpp:259-263)
-          A00[l] += rd * (G0[0][0] * Mkl + Gx[0][0] * Mx + Gy[0][0] * My);
-          A01[l] += rd * (G0[0][1] * Mkl + Gx[0][1] * Mx + Gy[0][1] * My);
-          A10[l] += rd * (G0[1][0] * Mkl + Gx[1][0] * Mx + Gy[1][0] * My);
-          A11[l] += rd * (G0[1][1] * Mkl + Gx[1][1] * Mx + Gy[1][1] * My);
-          // rho w psi_k U_b (g_l)_a  (cpp:265-269): (g_l)_a = sum_c A_ac dhat_c psi_l
-          A00[l] += rd * (a00 * H[0][l][0] + a01 * H[0][l][1]);
-          A01[l] += rd * (a00 * H[1][l][0] + a01 * H[1][l][1]);
-          A10[l] += rd * (a10 * H[0][l][0] + a11 * H[0][l][1]);
-          A11[l] += rd * (a10 * H[1][l][0] + a11 * H[1][l][1]);
-          rv0 += Kkl * u[l][0];
-          rv1 += Kkl * u[l][1];
-        }
-      }
-      // B^T[(a,k),m] = -sum_q w (g_k)_a chi_m = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
-      double pb0 = 0.0, pb1 = 0.0;
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const double bh0 = s_Bh[k][m][0], bh1 = s_Bh[k][m][1];
-        const double t0 = a00 * bh0 + a01 * bh1, t1 = a10 * bh0 + a11 * bh1;
-        B0[m] = -d * t0;
-        B1[m] = -d * t1;
-        if (ns) {
-          const double pm = sol[__ldg(cd + 3 * m + 2)];
-          pb0 += pm * t0;
-          pb1 += pm * t1;
-        }
-      }
-      // residual (cpp:287-311)
-      if (ns) {
-        res0 = -vd * rv0 - rd * cr0 + d * pb0;
-        res1 = -vd * rv1 - rd * cr1 + d * pb1;
-        if (P.use_mass) {
-          double t0 = 0, t1 = 0;
-#pragma unroll
-          for (int l = 0; l < 6; ++l) {
-            const int32_t d0 = __ldg(cd + uidx(l));
-            const double mh = s_Mh[k][l];
-            t0 += mh * (u[l][0] - sol_old[d0]);
-            t1 += mh * (u[l][1] - sol_old[d0 + 1]);
-          }
-          res0 -= P.rho * P.dt_inv * d * t0;
-          res1 -= P.rho * P.dt_inv * d * t1;
-        }
-      }
-      res0 += P.f0 * d * s_mh[k];
-      res1 += P.f1 * d * s_mh[k];
-    }
-    const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < wrounds; ++r) {
-      if (work && slot == r) {
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-          row0[o] += A00[l];
-          row0[o + 1] += A01[l];
-          row1[o] += A10[l];
-          row1[o + 1] += A11[l];
-        }
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          const int l = 6 + m;
-          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-          row0[o] += B0[m];
-          row1[o] += B1[m];
-        }
-        s_res[2 * gl] += res0;
-        s_res[2 * gl + 1] += res1;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
-  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
-}
-
-// pressure rows, factored: B[m,(b,l)] = -d sum_c A_bc Bh[l][m][c];  Mp[m,n] = d/nu Mp_hat[m][n]
-__global__ void __launch_bounds__(NPC, 4)
-k_assemble_p2(const WorkList wl, int64_t n_own_u, const int64_t *__restrict__ rowptr, double *__restrict__ vals,
-              const int64_t *__restrict__ pm_rowptr, double *__restrict__ pm_vals, double *__restrict__ R,
-              const double *__restrict__ geom, const AsmParams P) {
-  extern __shared__ double s_vals[];
-  __shared__ double s_Bh[6][3][2], s_Mp[3][3];
-  const int t = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const ChunkInfo ci = wl.chunks[b];
-  const int ng = ci.g1 - ci.g0;
-  const int64_t rs = rowptr[n_own_u + ci.g0], re = rowptr[n_own_u + ci.g1];
-  const int64_t ms = pm_rowptr[n_own_u + ci.g0], me = pm_rowptr[n_own_u + ci.g1];
-  const int cnt = (int)(re - rs), mcnt = (int)(me - ms);
-  double *s_pm = s_vals + cnt;
-  for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
-  for (int i = t; i < 36; i += NPC) (&s_Bh[0][0][0])[i] = (&c_fe2.Bh[0][0][0])[i];
-  for (int i = t; i < 9; i += NPC) (&s_Mp[0][0])[i] = (&c_fe2.Mp[0][0])[i];
-  __syncthreads();
-  const int desc = t < ci.n_threads ? wl.tdesc[b * NPC + t] : 0xffff;
-  const bool have = desc != 0xffff;  // 0xffff: padding lane (an owner's slots never straddle a warp)
-  const int gl = have ? (desc & 0xff) : 0, slot = have ? (desc >> 8) : 0;
-  // commit rounds of THIS warp: the slots of an owner are adjacent lanes of one warp
-  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
-  const int64_t prow = n_own_u + ci.g0 + gl;
-  double *row = s_vals + (rowptr[prow] - rs);
-  double *mrow = s_pm + (pm_rowptr[prow] - ms);
-  const double inv_nu = 1.0 / P.nu;
-  for (int j = 0; j < ASM_PPT; ++j) {
-    uint4 ra = make_uint4(0xffffffffu, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (have) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
-      ra = __ldcs(rp);
-      rb = __ldcs(rp + 1);
-    }
-    const bool work = (int)ra.x >= 0;
-    double Bx[6], By[6], M[3];
-#pragma unroll
-    for (int l = 0; l < 6; ++l) Bx[l] = By[l] = 0.0;
-    M[0] = M[1] = M[2] = 0.0;
-    if (work) {
-      const int64_t c = (int)ra.x;
-      const int m = (int)ra.y;
-      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
-                   a11 = __ldg(geom + 5 * c + 3), d = __ldg(geom + 5 * c + 4);
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double bh0 = s_Bh[l][m][0], bh1 = s_Bh[l][m][1];
-        Bx[l] = -d * (a00 * bh0 + a01 * bh1);
-        By[l] = -d * (a10 * bh0 + a11 * bh1);
-      }
-#pragma unroll
-      for (int n = 0; n < 3; ++n) M[n] = s_Mp[m][n] * inv_nu * d;
-    }
-    const uint32_t ow[6] = {ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    for (int r = 0; r < wrounds; ++r) {
-      if (work && slot == r) {
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-          row[o] += Bx[l];
-          row[o + 1] += By[l];
-        }
-#pragma unroll
-        for (int n = 0; n < 3; ++n) {
-          const int l = 6 + n;
-          const int o = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-          mrow[o] += M[n];
-        }
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  for (int i = t; i < cnt; i += NPC) __stcs(vals + rs + i, s_vals[i]);
-  for (int i = t; i < mcnt; i += NPC) __stcs(pm_vals + ms + i, s_pm[i]);
-  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
-}
+// (Variants 1-3 of round 1 - factored tables without packets, packets with two pairs per thread, the column-half
+//  form - were measured slower than variant 4 and are in the git history at commit 573725d; profiles/r01_summary.md.)
 
 // ---- variant 2 ("cell packets"): everything that depends on the cell only is computed ONCE per cell ---------
 // The row-owner kernels above redo the field interpolation of a cell in each of its 6 velocity pairs and walk
@@ -758,225 +466,6 @@ struct __align__(16) KlTab {
 };
 constexpr int KL_STRIDE = 38;  // doubles per k row (6 x 6 entries + 2 pad): rows land on disjoint banks
 
-template <int MINB>
-__global__ void __launch_bounds__(NPC, MINB)
-k_assemble_u3(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
-              const AsmParams P) {
-  extern __shared__ __align__(16) double s_vals[];
-  __shared__ __align__(16) double s_kl[6 * KL_STRIDE];
-  __shared__ __align__(16) double s_Bh[6][3][2];
-  __shared__ double s_wpsi[7][6];
-  const int t = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const ChunkInfo ci = wl.chunks[b];
-  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
-  uint4 ra[ASM_PPT], rb[ASM_PPT];
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
-    if (t < ci.n_threads) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
-      ra[j] = __ldcs(rp);
-      rb[j] = __ldcs(rp + 1);
-    }
-  }
-  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
-  double *s_res = s_vals + cnt;
-  for (int i = t; i < cnt + 2 * ng; i += NPC) s_vals[i] = 0.0;
-  if (t < 36) {
-    const int k = t / 6, l = t % 6;
-    double *e = s_kl + k * KL_STRIDE + 6 * l;
-    e[0] = c_fe2.Mh[k][l], e[1] = c_fe2.Mx[k][l], e[2] = c_fe2.My[k][l];
-    e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
-    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
-  }
-  if (t >= 64 && t < 64 + 42) {
-    const int q = (t - 64) / 6, k = (t - 64) % 6;
-    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
-  }
-  __syncthreads();
-
-  const bool have = td.y != 0xffffffffu;
-  const int len = have ? (int)(td.y & 0xffffu) : 0, slot = have ? (int)((td.y >> 16) & 0xffu) : 0, gl = have ? (int)(td.y >> 24) : 0;
-  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
-  double *row0 = s_vals + (have ? (td.x & 0xffffu) : 0u), *row1 = row0 + len;
-  const bool ns = !P.stokes;
-  const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
-
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    const bool work = (int)ra[j].x >= 0;
-    double A00[6], A01[6], A10[6], A11[6], B0[3], B1[3];
-    double res0 = 0.0, res1 = 0.0;
-    if (work) {
-      const int k = (int)ra[j].y;
-      const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(int)ra[j].x);
-      const double2 ga = __ldg(pk), gb = __ldg(pk + 1), gd = __ldg(pk + 2);
-      const double a00 = ga.x, a01 = ga.y, a10 = gb.x, a11 = gb.y, d = gd.x;
-      const double2 rk = __ldg(pk + 16 + k);
-      res0 = rk.x, res1 = rk.y;
-      double H[2][6][2];
-#pragma unroll
-      for (int l = 0; l < 6; ++l) H[0][l][0] = H[0][l][1] = H[1][l][0] = H[1][l][1] = 0.0;
-      double2 g0a = make_double2(0, 0), g0b = g0a, gxa = g0a, gxb = g0a, gya = g0a, gyb = g0a;
-      if (ns) {
-        g0a = __ldg(pk + 3), g0b = __ldg(pk + 4), gxa = __ldg(pk + 5), gxb = __ldg(pk + 6), gya = __ldg(pk + 7), gyb = __ldg(pk + 8);
-        // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l   (second Frechet term, cpp:265-269)
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const double2 U = __ldg(pk + 9 + q);
-          const double wk = s_wpsi[q][k];
-          const double c0 = wk * U.x, c1 = wk * U.y;
-#pragma unroll
-          for (int l = 0; l < 6; ++l) {
-            H[0][l][0] += c0 * c_fe.dpsi[q][l][0];
-            H[0][l][1] += c0 * c_fe.dpsi[q][l][1];
-            H[1][l][0] += c1 * c_fe.dpsi[q][l][0];
-            H[1][l][1] += c1 * c_fe.dpsi[q][l][1];
-          }
-        }
-      }
-      const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
-      const double rd = P.rho * d, md = mdt * d, vd = nurho * d;
-      const double r00 = rd * a00, r01 = rd * a01, r10 = rd * a10, r11 = rd * a11;
-      const double *kl = s_kl + k * KL_STRIDE;
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double2 e0 = *reinterpret_cast<const double2 *>(kl + 6 * l), e1 = *reinterpret_cast<const double2 *>(kl + 6 * l + 2),
-                      e2 = *reinterpret_cast<const double2 *>(kl + 6 * l + 4);
-        const double Mkl = e0.x, Mx = e0.y, My = e1.x;
-        const double Kkl = S00 * e1.y + S01 * e2.x + S11 * e2.y;  // (1/d) sum_q w g_k.g_l
-        const double D = md * Mkl + vd * Kkl;
-        // rho w G_ab psi_k psi_l (cpp:259-263) + rho w psi_k U_b (g_l)_a (cpp:265-269)
-        A00[l] = D + (g0a.x * Mkl + gxa.x * Mx + gya.x * My) + (r00 * H[0][l][0] + r01 * H[0][l][1]);
-        A01[l] = (g0a.y * Mkl + gxa.y * Mx + gya.y * My) + (r00 * H[1][l][0] + r01 * H[1][l][1]);
-        A10[l] = (g0b.x * Mkl + gxb.x * Mx + gyb.x * My) + (r10 * H[0][l][0] + r11 * H[0][l][1]);
-        A11[l] = D + (g0b.y * Mkl + gxb.y * Mx + gyb.y * My) + (r10 * H[1][l][0] + r11 * H[1][l][1]);
-      }
-      // B^T[(a,k),m] = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[k][m][0]);
-        B0[m] = -d * (a00 * bh.x + a01 * bh.y);
-        B1[m] = -d * (a10 * bh.x + a11 * bh.y);
-      }
-    }
-    // commit rounds: slot r of every owner adds its pair into the owner's rows, in cell order; all 15 entries
-    // of a row are loaded before any is written back (they are distinct, which the compiler cannot know)
-    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
-    for (int r = 0; r < wrounds; ++r) {
-      if (work && slot == r) {
-        int o[9];
-#pragma unroll
-        for (int l = 0; l < 9; ++l) o[l] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-        double x[15], y[15];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          x[2 * l] = row0[o[l]], x[2 * l + 1] = row0[o[l] + 1];
-          y[2 * l] = row1[o[l]], y[2 * l + 1] = row1[o[l] + 1];
-        }
-#pragma unroll
-        for (int m = 0; m < 3; ++m) x[12 + m] = row0[o[6 + m]], y[12 + m] = row1[o[6 + m]];
-        const double e0 = s_res[2 * gl], e1 = s_res[2 * gl + 1];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) {
-          row0[o[l]] = x[2 * l] + A00[l], row0[o[l] + 1] = x[2 * l + 1] + A01[l];
-          row1[o[l]] = y[2 * l] + A10[l], row1[o[l] + 1] = y[2 * l + 1] + A11[l];
-        }
-#pragma unroll
-        for (int m = 0; m < 3; ++m) row0[o[6 + m]] = x[12 + m] + B0[m], row1[o[6 + m]] = y[12 + m] + B1[m];
-        s_res[2 * gl] = e0 + res0, s_res[2 * gl + 1] = e1 + res1;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  double *out = vals + ci.rs;
-  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
-  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
-}
-
-// pressure rows of variant 2: the factored integrals of k_assemble_p2 on the chain-free skeleton above
-__global__ void __launch_bounds__(NPC, 6)
-k_assemble_p3(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, double *__restrict__ pm_vals, double *__restrict__ R,
-              const double *__restrict__ geom, const AsmParams P) {
-  extern __shared__ __align__(16) double s_vals[];
-  __shared__ __align__(16) double s_Bh[3][6][2];  // [m][l][c]
-  __shared__ double s_Mp[3][3];
-  const int t = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const ChunkInfo ci = wl.chunks[b];
-  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
-  uint4 ra[ASM_PPT], rb[ASM_PPT];
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
-    if (t < ci.n_threads) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
-      ra[j] = __ldcs(rp);
-      rb[j] = __ldcs(rp + 1);
-    }
-  }
-  const int cnt = ci.cnt, mcnt = ci.mcnt, ng = ci.g1 - ci.g0;
-  double *s_pm = s_vals + cnt;
-  for (int i = t; i < cnt + mcnt; i += NPC) s_vals[i] = 0.0;
-  if (t < 36) {
-    const int l = t / 6, m = (t % 6) / 2, cc = t % 2;
-    s_Bh[m][l][cc] = c_fe2.Bh[l][m][cc];
-  }
-  if (t >= 64 && t < 73) (&s_Mp[0][0])[t - 64] = (&c_fe2.Mp[0][0])[t - 64];
-  __syncthreads();
-  const bool have = td.y != 0xffffffffu;
-  const int slot = have ? (int)((td.y >> 16) & 0xffu) : 0;
-  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
-  double *row = s_vals + (have ? (td.x & 0xffffu) : 0u);
-  double *mrow = s_pm + (have ? (td.x >> 16) : 0u);
-  const double inv_nu = 1.0 / P.nu;
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    const bool work = (int)ra[j].x >= 0;
-    double Bx[6], By[6], M[3];
-    if (work) {
-      const int64_t c = (int)ra[j].x;
-      const int m = (int)ra[j].y;
-      const double a00 = __ldg(geom + 5 * c), a01 = __ldg(geom + 5 * c + 1), a10 = __ldg(geom + 5 * c + 2),
-                   a11 = __ldg(geom + 5 * c + 3), d = __ldg(geom + 5 * c + 4);
-#pragma unroll
-      for (int l = 0; l < 6; ++l) {
-        const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[m][l][0]);
-        Bx[l] = -d * (a00 * bh.x + a01 * bh.y);
-        By[l] = -d * (a10 * bh.x + a11 * bh.y);
-      }
-#pragma unroll
-      for (int n = 0; n < 3; ++n) M[n] = s_Mp[m][n] * inv_nu * d;
-    }
-    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
-    for (int r = 0; r < wrounds; ++r) {
-      if (work && slot == r) {
-        int o[9];
-#pragma unroll
-        for (int l = 0; l < 9; ++l) o[l] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-        double x[12], y[3];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) x[2 * l] = row[o[l]], x[2 * l + 1] = row[o[l] + 1];
-#pragma unroll
-        for (int n = 0; n < 3; ++n) y[n] = mrow[o[6 + n]];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) row[o[l]] = x[2 * l] + Bx[l], row[o[l] + 1] = x[2 * l + 1] + By[l];
-#pragma unroll
-        for (int n = 0; n < 3; ++n) mrow[o[6 + n]] = y[n] + M[n];
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  double *out = vals + ci.rs, *mout = pm_vals + ci.ms;
-  for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
-  for (int i = t; i < mcnt; i += NPC) __stcs(mout + i, s_pm[i]);
-  // no statement of the reference tests the pressure space: R_p == 0
-  for (int i = t; i < ng; i += NPC) R[n_own_u + ci.g0 + i] = 0.0;
-}
-
 // ---- variant 3: variant 2 restructured for latency ----------------------------------------------------------
 // ncu on k_assemble_u3 (profiles/r01_asm_variants.md): 3 warps per scheduler (162 registers), issue slots 25 %
 // used; stall samples: 30 % waiting for the packet loads, 31 % in the commit rounds, 16 % zero-fill and
@@ -999,189 +488,6 @@ __device__ __forceinline__ void bulk_store_image(double *dst, const double *src_
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(NPC, MINB)
-k_assemble_u4(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
-              const AsmParams P) {
-  extern __shared__ __align__(16) double s_vals[];
-  __shared__ __align__(16) double s_kl[6 * KL_STRIDE];
-  __shared__ __align__(16) double s_Bh[6][3][2];
-  __shared__ double s_wpsi[7][6];
-  const int t = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const ChunkInfo ci = wl.chunks[b];
-  const uint2 td = __ldg(wl.tdesc3 + b * NPC + t);
-  uint4 ra[ASM_PPT], rb[ASM_PPT];
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    ra[j] = make_uint4(0xffffffffu, 0, 0, 0), rb[j] = make_uint4(0, 0, 0, 0);
-    if (t < ci.n_threads) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + ci.rec_base + (int64_t)j * ci.n_threads + t);
-      ra[j] = __ldcs(rp);
-      rb[j] = __ldcs(rp + 1);
-    }
-  }
-  // request the first pair's geometry now; pull the later pairs' packets towards L2 while the image is prepared
-  double2 hd0 = make_double2(0, 0), hd1 = hd0, hd2 = hd0;
-  if ((int)ra[0].x >= 0) {
-    const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(int)ra[0].x);
-    hd0 = __ldg(pk), hd1 = __ldg(pk + 1), hd2 = __ldg(pk + 2);
-  }
-#pragma unroll
-  for (int j = 1; j < ASM_PPT; ++j)
-    if ((int)ra[j].x >= 0) {
-      const char *pb = reinterpret_cast<const char *>(cellpk + PK * (int64_t)(int)ra[j].x);
-      pf_l2(pb), pf_l2(pb + 128), pf_l2(pb + 256), pf_l2(pb + 8 * PK - 8);
-    }
-  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
-  double *s_res = s_vals + cnt;
-  {
-    const int n2 = (cnt + 2 * ng + 1) >> 1;  // the image is 16-byte aligned and padded to an even length
-    double2 *z = reinterpret_cast<double2 *>(s_vals);
-    for (int i = t; i < n2; i += NPC) z[i] = make_double2(0.0, 0.0);
-  }
-  if (t < 36) {
-    const int k = t / 6, l = t % 6;
-    double *e = s_kl + k * KL_STRIDE + 6 * l;
-    e[0] = c_fe2.Mh[k][l], e[1] = c_fe2.Mx[k][l], e[2] = c_fe2.My[k][l];
-    e[3] = c_fe2.K00[k][l], e[4] = c_fe2.K01s[k][l], e[5] = c_fe2.K11[k][l];
-    (&s_Bh[0][0][0])[t] = (&c_fe2.Bh[0][0][0])[t];
-  }
-  if (t >= 64 && t < 64 + 42) {
-    const int q = (t - 64) / 6, k = (t - 64) % 6;
-    s_wpsi[q][k] = c_fe.w[q] * c_fe.psi[q][k];
-  }
-  __syncthreads();
-
-  const bool have = td.y != 0xffffffffu;
-  const int len = have ? (int)(td.y & 0xffffu) : 0, slot = have ? (int)((td.y >> 16) & 0xffu) : 0, gl = have ? (int)(td.y >> 24) : 0;
-  const int wrounds = __reduce_max_sync(0xffffffffu, have ? slot + 1 : 0);
-  double *row0 = s_vals + (have ? (td.x & 0xffffu) : 0u), *row1 = row0 + len;
-  const bool ns = !P.stokes;
-  const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
-
-#pragma unroll
-  for (int j = 0; j < ASM_PPT; ++j) {
-    const bool work = (int)ra[j].x >= 0;
-    const int k = work ? (int)ra[j].y : 0;
-    const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK * (int64_t)(work ? (int)ra[j].x : 0));
-    double a00 = 0, a01 = 0, a10 = 0, a11 = 0, d = 0, res0 = 0, res1 = 0;
-    if (work) {
-      if (j == 0) {
-        a00 = hd0.x, a01 = hd0.y, a10 = hd1.x, a11 = hd1.y, d = hd2.x;
-      } else {
-        const double2 ga = __ldg(pk), gb = __ldg(pk + 1), gd = __ldg(pk + 2);
-        a00 = ga.x, a01 = ga.y, a10 = gb.x, a11 = gb.y, d = gd.x;
-      }
-      const double2 rk = __ldg(pk + 16 + k);
-      res0 = rk.x, res1 = rk.y;
-    }
-    const double S00 = a00 * a00 + a10 * a10, S01 = a00 * a01 + a10 * a11, S11 = a01 * a01 + a11 * a11;
-    const double rd = P.rho * d, md = mdt * d, vd = nurho * d;
-    const double r00 = rd * a00, r01 = rd * a01, r10 = rd * a10, r11 = rd * a11;
-    const double *kl = s_kl + k * KL_STRIDE;
-    const uint32_t ow[6] = {ra[j].z, ra[j].w, rb[j].x, rb[j].y, rb[j].z, rb[j].w};
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      double A00[3], A01[3], A10[3], A11[3], B0[3], B1[3];
-      if (work) {
-        double H[2][3][2];
-#pragma unroll
-        for (int ll = 0; ll < 3; ++ll) H[0][ll][0] = H[0][ll][1] = H[1][ll][0] = H[1][ll][1] = 0.0;
-        if (ns) {
-          // the only quadrature loop: H[b][l][c] = sum_q w psi_k U_b dhat_c psi_l   (second Frechet term, cpp:265-269)
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const double2 U = ldg_v2_volatile(pk + 9 + q);
-            const double wk = s_wpsi[q][k];
-            const double c0 = wk * U.x, c1 = wk * U.y;
-#pragma unroll
-            for (int ll = 0; ll < 3; ++ll) {
-              const int l = 3 * half + ll;
-              H[0][ll][0] += c0 * c_fe.dpsi[q][l][0];
-              H[0][ll][1] += c0 * c_fe.dpsi[q][l][1];
-              H[1][ll][0] += c1 * c_fe.dpsi[q][l][0];
-              H[1][ll][1] += c1 * c_fe.dpsi[q][l][1];
-            }
-          }
-        }
-        double2 g0a = make_double2(0, 0), g0b = g0a, gxa = g0a, gxb = g0a, gya = g0a, gyb = g0a;
-        if (ns) {
-          g0a = ldg_v2_volatile(pk + 3), g0b = ldg_v2_volatile(pk + 4), gxa = ldg_v2_volatile(pk + 5);
-          gxb = ldg_v2_volatile(pk + 6), gya = ldg_v2_volatile(pk + 7), gyb = ldg_v2_volatile(pk + 8);
-        }
-#pragma unroll
-        for (int ll = 0; ll < 3; ++ll) {
-          const int l = 3 * half + ll;
-          const double2 e0 = *reinterpret_cast<const double2 *>(kl + 6 * l), e1 = *reinterpret_cast<const double2 *>(kl + 6 * l + 2),
-                        e2 = *reinterpret_cast<const double2 *>(kl + 6 * l + 4);
-          const double Mkl = e0.x, Mx = e0.y, My = e1.x;
-          const double Kkl = S00 * e1.y + S01 * e2.x + S11 * e2.y;  // (1/d) sum_q w g_k.g_l
-          const double D = md * Mkl + vd * Kkl;
-          // rho w G_ab psi_k psi_l (cpp:259-263) + rho w psi_k U_b (g_l)_a (cpp:265-269)
-          A00[ll] = D + (g0a.x * Mkl + gxa.x * Mx + gya.x * My) + (r00 * H[0][ll][0] + r01 * H[0][ll][1]);
-          A01[ll] = (g0a.y * Mkl + gxa.y * Mx + gya.y * My) + (r00 * H[1][ll][0] + r01 * H[1][ll][1]);
-          A10[ll] = (g0b.x * Mkl + gxb.x * Mx + gyb.x * My) + (r10 * H[0][ll][0] + r11 * H[0][ll][1]);
-          A11[ll] = D + (g0b.y * Mkl + gxb.y * Mx + gyb.y * My) + (r10 * H[1][ll][0] + r11 * H[1][ll][1]);
-        }
-        if (half == 0) {
-          // B^T[(a,k),m] = -d sum_c A_ac Bh[k][m][c]   (cpp:272-274)
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            const double2 bh = *reinterpret_cast<const double2 *>(&s_Bh[k][m][0]);
-            B0[m] = -d * (a00 * bh.x + a01 * bh.y);
-            B1[m] = -d * (a10 * bh.x + a11 * bh.y);
-          }
-        }
-      }
-      // commit rounds: slot r of every owner adds its half pair into the owner's rows, in cell order; all
-      // entries are loaded before any is written back (they are distinct, which the compiler cannot know)
-      for (int r = 0; r < wrounds; ++r) {
-        if (work && slot == r) {
-          int o[3];
-#pragma unroll
-          for (int ll = 0; ll < 3; ++ll) {
-            const int l = 3 * half + ll;
-            o[ll] = (ow[l >> 1] >> ((l & 1) * 16)) & 0xffff;
-          }
-          double x[6], y[6];
-#pragma unroll
-          for (int ll = 0; ll < 3; ++ll) {
-            x[2 * ll] = row0[o[ll]], x[2 * ll + 1] = row0[o[ll] + 1];
-            y[2 * ll] = row1[o[ll]], y[2 * ll + 1] = row1[o[ll] + 1];
-          }
-          if (half == 0) {
-            int op[3];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) op[m] = (ow[(6 + m) >> 1] >> (((6 + m) & 1) * 16)) & 0xffff;
-            double xb[3], yb[3];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) xb[m] = row0[op[m]], yb[m] = row1[op[m]];
-            const double e0 = s_res[2 * gl], e1 = s_res[2 * gl + 1];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) row0[op[m]] = xb[m] + B0[m], row1[op[m]] = yb[m] + B1[m];
-            s_res[2 * gl] = e0 + res0, s_res[2 * gl + 1] = e1 + res1;
-          }
-#pragma unroll
-          for (int ll = 0; ll < 3; ++ll) {
-            row0[o[ll]] = x[2 * ll] + A00[ll], row0[o[ll] + 1] = x[2 * ll + 1] + A01[ll];
-            row1[o[ll]] = y[2 * ll] + A10[ll], row1[o[ll] + 1] = y[2 * ll + 1] + A11[ll];
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-  double *out = vals + ci.rs;
-  if (((ci.rs | (int64_t)cnt) & 1) == 0) {
-    if (t == 0 && cnt > 0) bulk_store_image(out, s_vals, (uint32_t)cnt * 8u);
-  } else {
-    for (int i = t; i < cnt; i += NPC) __stcs(out + i, s_vals[i]);
-  }
-  for (int i = t; i < 2 * ng; i += NPC) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
 
 #ifndef NSG_NPC5

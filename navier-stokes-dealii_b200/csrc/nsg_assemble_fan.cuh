@@ -17,9 +17,14 @@
 //    one warp shuffle brings it over and the sum is stored ONCE.  The owner's own column (all cells of the fan)
 //    is a segmented shuffle tree.  Hence every entry of the image is written exactly once, by a plain store:
 //    no zero-fill, no loads from the image, no barriers between commit rounds.
-//  * The per-cell packets (256 bytes: grad lambda, |det J|, nodal velocities, the cell's local residual) of the
-//    cells a chunk touches are staged into shared memory by asynchronous copies (cp.async or one bulk copy per
-//    cell, TMA engine) - each packet crosses the LSU pipe once per chunk, not once per pair.
+//  * A streaming pre-pass writes one 192-byte packet per cell (nodal velocities, the cell's complete local
+//    residual); grad lambda_j is static (geom8).  A lane loads only what no neighbouring lane holds: the values
+//    of the nodes on the edge it shares with its predecessor in the fan come over by shuffle, the owner's own
+//    value from the head lane, |det J| is recomputed from grad lambda.  6-7 instead of 17 16-byte loads per pair.
+//    (Staging the packets in shared memory - cp.async, or one bulk copy per cell - was measured slower: 1.17 /
+//    1.12 ms against 1.02 ms at 1.65 M cells, profiles/r02_summary.md; the chunk image leaves by one bulk copy.)
+//  * The 2x2 blocks are stored with a lane-parity swizzle (odd lanes store the second column first): the column
+//    offsets of velocity pairs are even, so unswizzled stores would use half of the banks per instruction.
 // Summation order per entry is fixed (fan order), so the result is bitwise reproducible run to run; it differs
 // from variant 4 / the reference's cell-loop order by rounding only (1e-16 relative).
 // Meshes that are not consistently oriented, have an edge with more than two cells or a vertex with more than
@@ -30,8 +35,8 @@
 namespace nsg {
 
 constexpr int NPC6 = 128;  // lanes (pairs) per CTA
-constexpr int PK6 = 32;    // doubles per cell packet
-constexpr int PK6S = 34;   // staging stride (272 bytes: 16-byte aligned; 8 consecutive slots fall on 8 different 16-byte bank groups)
+constexpr int PK6 = 24;    // doubles per cell packet: [0..11] nodal velocities u_i, [12..23] local residual of the 6 velocity nodes
+constexpr int PK6S = 26;   // row stride of the pre-pass' transposition buffer (208 bytes: 16-byte aligned, conflict-free 128-bit stores)
 
 // tables of the owner's row in the rotated frame, K = 0 (index 0) and K = 3 (index 1)
 struct FanTab {
@@ -65,9 +70,9 @@ __global__ void k_cell_geometry8(int64_t T, const double *__restrict__ xy, const
   o[3] = make_double2(fabs(det), 0.0);
 }
 
-// ---- pre-pass: one 256-byte packet per cell ------------------------------------------------------------------
-//   [0..5] grad lambda_j   [6] d = |det J|   [8..19] nodal velocities u_i (FE_SimplexP(2) order: 3 vertices, 3 edges)
-//   [20..31] the cell's complete local residual of its 6 velocity nodes (cpp:287-311)
+// ---- pre-pass: one 192-byte packet per cell ------------------------------------------------------------------
+//   [0..11] nodal velocities u_i (FE_SimplexP(2) order: 3 vertices, 3 edges)
+//   [12..23] the cell's complete local residual of its 6 velocity nodes (cpp:287-311)
 // One thread per cell integrates; the packets of a CTA leave through shared memory, fully coalesced.
 __global__ void __launch_bounds__(128, 4)
 k_cell_packets6(int64_t T, const double *__restrict__ geom8, const int32_t *__restrict__ cell_dofs, const double *__restrict__ sol,
@@ -81,7 +86,7 @@ k_cell_packets6(int64_t T, const double *__restrict__ geom8, const int32_t *__re
     const double2 *gp = reinterpret_cast<const double2 *>(geom8 + 8 * c);
     const double2 l0 = __ldg(gp), l1 = __ldg(gp + 1), l2 = __ldg(gp + 2), dd = __ldg(gp + 3);
     const double a00 = l1.x, a10 = l1.y, a01 = l2.x, a11 = l2.y, d = dd.x;
-    mine[0] = l0, mine[1] = l1, mine[2] = l2, mine[3] = dd;
+    (void)l0;
     const bool ns = !P.stokes;
     const double nurho = P.nu * P.rho, rd = P.rho * d, vd = nurho * d;
     double res[6][2];
@@ -183,16 +188,16 @@ k_cell_packets6(int64_t T, const double *__restrict__ geom8, const int32_t *__re
       }
     }
 #pragma unroll
-    for (int l = 0; l < 6; ++l) mine[4 + l] = make_double2(u[l][0], u[l][1]);
+    for (int l = 0; l < 6; ++l) mine[l] = make_double2(u[l][0], u[l][1]);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) mine[10 + k] = make_double2(res[k][0] + P.f0 * d * c_fe2.mh[k], res[k][1] + P.f1 * d * c_fe2.mh[k]);
+    for (int k = 0; k < 6; ++k) mine[6 + k] = make_double2(res[k][0] + P.f0 * d * c_fe2.mh[k], res[k][1] + P.f1 * d * c_fe2.mh[k]);
   }
   __syncthreads();
-  // coalesced write-out: 16 double2 per packet, consecutive threads -> consecutive 16-byte pieces
+  // coalesced write-out: 12 double2 per packet, consecutive threads -> consecutive 16-byte pieces
   const int64_t n_here = (T - c0 < 128) ? (T - c0) : 128;
   double2 *out = reinterpret_cast<double2 *>(cellpk + PK6 * c0);
-  for (int i = t; i < (int)n_here * 16; i += 128) {
-    const int cell = i >> 4, part = i & 15;
+  for (int i = t; i < (int)n_here * 12; i += 128) {
+    const int cell = i / 12, part = i - 12 * cell;
     __stcs(out + i, *reinterpret_cast<const double2 *>(s_out + cell * PK6S + 2 * part));
   }
 }
@@ -268,69 +273,38 @@ __device__ __forceinline__ void fan_rows(const double2 n1, const double2 n2, con
 
 __device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(smem)), "l"(gmem) : "memory");
-}
-
 // Record of a lane (PairRec, 32 bytes):
 //   cell    the cell (-1: idle lane)
 //   k       canonical local index of the owner (3 bits) | partner lane in the warp << 3 (5) | has partner << 8 |
 //           head << 9 (writes the owner's own column and residual) | write_next << 10 (the lane's "next"-side
-//           columns have no partner: it stores them itself) | lanes of the owner after this one << 11 (5) |
-//           owner index in the chunk << 16 (8)
+//           columns have no partner: it stores them itself; = the lane has no predecessor in the fan) |
+//           lanes of the owner after this one << 11 (5) | owner index in the chunk << 16 (8) |
+//           predecessor lane << 24 (5; vertex owners: the lane whose "previous" edge is this lane's "next" edge)
 //   off     [0..5] offsets of the column pairs of the ROTATED local nodes 0..5 in the owner's rows, [6..8] of the
-//           three pressure columns (rotated order), [9] image offset of the owner's first row, [10] row length,
-//           [11] slot of the cell's packet in the chunk's staging area
-// ChunkInfo: g0,g1 owners; n_threads = number of staged cells; max_slots = number of warps holding vertex owners;
-//            rs, cnt image; pad != 0: the image has entries no lane writes (zero-fill first).
-template <int MINB, int STAGE>
+//           three pressure columns (rotated order), [9] image offset of the owner's first row, [10] row length
+// ChunkInfo: g0,g1 owners; rs, cnt image; pad != 0: the image has entries no lane writes (zero-fill first).
+template <int MINB>
 __global__ void __launch_bounds__(NPC6, MINB)
-k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk, const AsmParams P) {
-  extern __shared__ __align__(16) double s_mem[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  const int t = threadIdx.x;
+k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
+              const double *__restrict__ geom8, const AsmParams P) {
+  extern __shared__ __align__(16) double s_vals[];
+  const int t = threadIdx.x, lane = t & 31;
   const int64_t b = blockIdx.x;
   const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC6 + t);
   const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
   const ChunkInfo ci = wl.chunks[b];
-  const int n_stage = ci.n_threads;
-  double *s_pk = s_mem;
-  double *s_vals = s_mem + (STAGE ? n_stage * PK6S : 0);
   const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
   double *s_res = s_vals + cnt;
-  // ---- stage the packets of the chunk's cells
-  if (STAGE == 1) {
-    const int32_t *cl = wl.cells + b * NPC6;
-    const int part = t & 15;
-    for (int slot = t >> 4; slot < n_stage; slot += NPC6 / 16) {
-      const int32_t cell = __ldg(cl + slot);
-      cp_async16(s_pk + slot * PK6S + 2 * part, cellpk + (int64_t)cell * PK6 + 2 * part);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  } else if (STAGE == 2) {
-    const uint32_t bar = smem_addr_u32(&s_bar);
-    if (t == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)n_stage * (PK6 * 8u)) : "memory");
-    }
-    __syncthreads();
-    if (t < n_stage) {
-      const int32_t cell = __ldg(wl.cells + b * NPC6 + t);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_addr_u32(s_pk + t * PK6S)),
-                   "l"(cellpk + (int64_t)cell * PK6), "r"((uint32_t)(PK6 * 8)), "r"(bar)
-                   : "memory");
-    }
-  }
   if (ci.pad) {  // the pattern has entries no cell contributes to: they must read zero
     const int n2 = (cnt + 2 * ng + 1) >> 1;
     double2 *z = reinterpret_cast<double2 *>(s_vals);
     for (int i = t; i < n2; i += NPC6) z[i] = make_double2(0.0, 0.0);
+    __syncthreads();
   }
   const bool work = (int)ra.x >= 0;
   const uint32_t kw = ra.y;
   const int kc = (int)(kw & 7u), partner = (int)((kw >> 3) & 31u), rem = (int)((kw >> 11) & 31u), gl = (int)((kw >> 16) & 255u);
+  const int pred = (int)((kw >> 24) & 31u);
   const bool has_partner = (kw >> 8) & 1u, head = (kw >> 9) & 1u, write_next = (kw >> 10) & 1u;
   const int r = kc >= 3 ? kc - 3 : kc;
   const int i1 = r + 1 >= 3 ? r - 2 : r + 1, i2 = r + 2 >= 3 ? r - 1 : r + 2;
@@ -338,46 +312,52 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
   const uint32_t ow[5] = {ra.z, ra.w, rb.x, rb.y, rb.z};
   const bool ns = !P.stokes;
   const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
-  if (STAGE == 1) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  } else if (STAGE == 2) {
-    const uint32_t bar = smem_addr_u32(&s_bar);
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(bar), "r"(0u)
-          : "memory");
-    }
-  }
-  if (STAGE != 1 && ci.pad) __syncthreads();
-  // ---- the lane's packet in the rotated frame
-  double2 n1 = make_double2(0, 0), n2 = n1, rk = n1, dd = n1;
-  double2 u[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) u[i] = make_double2(0, 0);
-  if (work) {
-    const double2 *pk = STAGE ? reinterpret_cast<const double2 *>(s_pk + (rb.w >> 16) * PK6S)
-                              : reinterpret_cast<const double2 *>(cellpk + (int64_t)(int)ra.x * PK6);
-    if (STAGE) {
-      n1 = pk[i1], n2 = pk[i2], dd = pk[3], rk = pk[10 + kc];
-      u[0] = pk[4 + r], u[1] = pk[4 + i1], u[2] = pk[4 + i2], u[3] = pk[7 + r], u[4] = pk[7 + i1], u[5] = pk[7 + i2];
-    } else {
-      n1 = __ldg(pk + i1), n2 = __ldg(pk + i2), dd = __ldg(pk + 3), rk = __ldg(pk + 10 + kc);
-      u[0] = __ldg(pk + 4 + r), u[1] = __ldg(pk + 4 + i1), u[2] = __ldg(pk + 4 + i2);
-      u[3] = __ldg(pk + 7 + r), u[4] = __ldg(pk + 7 + i1), u[5] = __ldg(pk + 7 + i2);
-    }
-  }
-  double A[6][4], Bt[3][2];
   // uniform over the warp: the host packs vertex owners and edge owners into different warps (idle padding lanes have no
   // type of their own and must take the branch of their warp: the shuffles below are full-mask)
   const bool edge_owner = __any_sync(0xffffffffu, work && kc >= 3);
+  const int64_t cell = work ? (int)ra.x : 0;
+  const double2 *gp = reinterpret_cast<const double2 *>(geom8 + 8 * cell);
+  const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK6 * cell);
+  // ---- loads: everything a neighbouring lane does not hold
+  double2 n1 = make_double2(1.0, 0.0), n2 = make_double2(0.0, 1.0), rk = make_double2(0.0, 0.0);
+  double2 u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = make_double2(0.0, 0.0);
+  if (work) {
+    n1 = __ldg(gp + i1), n2 = __ldg(gp + i2);
+    u[2] = __ldg(pk + i2), u[4] = __ldg(pk + 3 + i1), u[5] = __ldg(pk + 3 + i2);
+    rk = __ldg(pk + 6 + kc);
+    if (!edge_owner) {
+      if (head) u[0] = __ldg(pk + r);
+      if (write_next) u[1] = __ldg(pk + i1), u[3] = __ldg(pk + 3 + r);  // no predecessor to take them from
+    } else {
+      u[0] = __ldg(pk + r);
+      if (head) u[3] = __ldg(pk + 3 + r);
+      if (!has_partner) u[1] = __ldg(pk + i1);
+    }
+  }
+  const double d = 1.0 / fabs(n1.x * n2.y - n1.y * n2.x);  // |det J| = 1 / |det (grad lambda'_1, grad lambda'_2)|
+  if (!edge_owner) {
+    // owner's own node from the head lane of the fan, the nodes of the "next" edge from the predecessor
+    // (its vertex 2 is this lane's vertex 1, its edge 5 = (v2, v0) this lane's edge 3 = (v0, v1))
+    const unsigned same = __match_any_sync(0xffffffffu, work ? gl : 256 + lane);
+    const int hl = __ffs(same) - 1;
+    const double h0x = shfl_d(u[0].x, hl), h0y = shfl_d(u[0].y, hl);
+    const double p2x = shfl_d(u[2].x, pred), p2y = shfl_d(u[2].y, pred), p5x = shfl_d(u[5].x, pred), p5y = shfl_d(u[5].y, pred);
+    if (!head) u[0] = make_double2(h0x, h0y);
+    if (!write_next) u[1] = make_double2(p2x, p2y), u[3] = make_double2(p5x, p5y);
+  } else {
+    // the other cell of the edge runs it the other way round: its vertex 0 is this lane's vertex 1; the owner's own
+    // node (3) is loaded by the head lane only
+    const double q0x = shfl_d(u[0].x, partner), q0y = shfl_d(u[0].y, partner), q3x = shfl_d(u[3].x, partner), q3y = shfl_d(u[3].y, partner);
+    if (has_partner) u[1] = make_double2(q0x, q0y);
+    if (!head) u[3] = make_double2(q3x, q3y);
+  }
+  double A[6][4], Bt[3][2];
   if (!edge_owner)
-    fan_rows<0>(n1, n2, dd.x, u, ns, mdt, nurho, P.rho, A, Bt);
+    fan_rows<0>(n1, n2, d, u, ns, mdt, nurho, P.rho, A, Bt);
   else
-    fan_rows<1>(n1, n2, dd.x, u, ns, mdt, nurho, P.rho, A, Bt);
+    fan_rows<1>(n1, n2, d, u, ns, mdt, nurho, P.rho, A, Bt);
   if (!work) {
 #pragma unroll
     for (int l = 0; l < 6; ++l) A[l][0] = A[l][1] = A[l][2] = A[l][3] = 0.0;
@@ -385,9 +365,13 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
     for (int m = 0; m < 3; ++m) Bt[m][0] = Bt[m][1] = 0.0;
   }
   auto off = [&](int l) -> int { return (int)((ow[l >> 1] >> ((l & 1) * 16)) & 0xffffu); };
+  // the column offsets of velocity pairs are even: odd lanes store the second column first, so that one store
+  // instruction of the warp spreads over all banks
+  const int sw = lane & 1;
   auto st_block = [&](int l, double v0, double v1, double v2, double v3) {
     const int o = off(l);
-    row0[o] = v0, row0[o + 1] = v1, row1[o] = v2, row1[o + 1] = v3;
+    row0[o + sw] = sw ? v1 : v0, row1[o + sw] = sw ? v3 : v2;
+    row0[o + 1 - sw] = sw ? v0 : v1, row1[o + 1 - sw] = sw ? v2 : v3;
   };
   auto st_p = [&](int m, double v0, double v1) {
     const int o = off(6 + m);
@@ -432,9 +416,8 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
       }
     }
   } else {
-    // -- edge owner (midpoint of rotated edge 0 = v0 v1): the other cell of the edge runs it the other way round
-    //    (its v0 is my v1), so my column of v0 takes the partner's column of ITS v1; the head lane also sums the
-    //    owner's own column (node 3) and the residual
+    // -- edge owner (midpoint of rotated edge 0 = v0 v1): my column of v0 takes the partner's column of ITS v1; the
+    //    head lane also sums the owner's own column (node 3) and the residual
     double x1[4], x3[4], xb[2], xr[2];
 #pragma unroll
     for (int e = 0; e < 4; ++e) x1[e] = shfl_d(A[1][e], partner), x3[e] = shfl_d(A[3][e], partner);
@@ -530,24 +513,24 @@ k_assemble_p6(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, dou
       if (dlt <= rem) sv[e] += o;
     }
   }
+  const int sw = t & 1;  // lane-parity swizzle, as in k_assemble_u6
+  auto st_pair = [&](int l, double v0, double v1) {
+    const int o = off(l);
+    row[o + sw] = sw ? v1 : v0;
+    row[o + 1 - sw] = sw ? v0 : v1;
+  };
   if (work) {
-    int o = off(2);
-    row[o] = Bx[2] + x1[0], row[o + 1] = By[2] + x1[1];
-    o = off(5);
-    row[o] = Bx[5] + x3[0], row[o + 1] = By[5] + x3[1];
-    o = off(4);
-    row[o] = Bx[4], row[o + 1] = By[4];
+    st_pair(2, Bx[2] + x1[0], By[2] + x1[1]);
+    st_pair(5, Bx[5] + x3[0], By[5] + x3[1]);
+    st_pair(4, Bx[4], By[4]);
     mrow[off(8)] = M[2] + xm;
     if (write_next) {
-      o = off(1);
-      row[o] = Bx[1], row[o + 1] = By[1];
-      o = off(3);
-      row[o] = Bx[3], row[o + 1] = By[3];
+      st_pair(1, Bx[1], By[1]);
+      st_pair(3, Bx[3], By[3]);
       mrow[off(7)] = M[1];
     }
     if (head) {
-      o = off(0);
-      row[o] = sv[0], row[o + 1] = sv[1];
+      st_pair(0, sv[0], sv[1]);
       mrow[off(6)] = sv[2];
     }
   }

@@ -76,43 +76,44 @@ struct WorkList {
                                  // J-row offset | mass-row offset << 16); y = row length | slot << 16 | owner << 24;
                                  // y = 0xffffffff marks a padding lane
   PairRec *recs = nullptr;       // [n_recs]; cell = -1 marks "no work"
-  int32_t *cells = nullptr;      // [n_chunks*NPC6] fan scheme: the cells whose packets a chunk stages (ChunkInfo::n_threads of them)
   int64_t max_stage = 0;         // max number of staged matrix entries of a chunk
 };
 
-// One-shot all-reduce over NVLink peer memory, fused into the tail of the reduction kernels.  Every rank
-// owns a mailbox (two parities x one slot per source rank) that all peers can write (CUDA IPC).  A
-// reduction with sequence number s: write my partial value(s) into slot [s&1][my rank] of EVERY rank's
-// mailbox, fence, publish s in the slot's flag; then wait until all P flags of my own mailbox show s and
-// add the P values in rank order - every rank gets the bit-identical sum, with no host or NCCL call on
-// the critical path of the k+1 dependent reductions of a GMRES step.  (Parity double-buffering is safe:
-// nobody can start s+2 before everybody has finished reading s.)
+// Peer memory over NVLink (CUDA IPC): every rank owns ONE mailbox allocation that all peers map:
+//   [ all-reduce words | halo table | halo inbox ]
+// Every datum travels as a 16-byte {value, sequence stamp} word written by one 128-bit store and read by one 128-bit
+// load: the stamp arrives with the value, so neither side needs a fence, a separate flag or a second round trip.
+//
+// One-shot all-reduce, fused into the tail of the reduction kernels: reduction number s writes my partial value(s) into
+// slot [s&1][my rank] of EVERY rank's mailbox, then polls the P slots of my own mailbox until they carry stamp s and
+// adds the P values in rank order - every rank gets the bit-identical sum, with no host or NCCL call on the critical
+// path of the k+1 dependent reductions of a GMRES step.  (Parity double-buffering is safe: nobody can start s+2
+// before everybody has finished reading s.)
+//
+// Halo exchange (the Epetra Import behind every vmult, cpp:583,587,618): the owner of a DoF stores {value, stamp} straight
+// into the inbox of each neighbour that holds it as a ghost (k_halo_push); the neighbour polls its own inbox and scatters
+// into the ghost range (k_halo_wait_scatter).  The inbox interleaves the two parities ([slot][parity]).
 constexpr int PEER_MAX_RANKS = 16;
 constexpr int PEER_MAX_VALS = 32;
-struct PeerSlot {
-  double v[PEER_MAX_VALS];
+struct __align__(16) PeerWord {
+  double v;
   unsigned long long seq;
-  unsigned long long pad[3];
 };
-static_assert(sizeof(PeerSlot) == 288, "PeerSlot layout");
+static_assert(sizeof(PeerWord) == 16, "PeerWord layout");
+constexpr int64_t PEER_AR_WORDS = 2ll * PEER_MAX_RANKS * PEER_MAX_VALS;  // [parity][source rank][value]
+struct PeerHaloTable {                                                   // what a sender needs to know about my inbox
+  int64_t recv_off[PEER_MAX_RANKS];  // first inbox slot of source rank q (-1: not a neighbour)
+  int64_t recv_cnt[PEER_MAX_RANKS];
+};
+constexpr int64_t PEER_TABLE_BYTES = 256;
+static_assert(sizeof(PeerHaloTable) <= PEER_TABLE_BYTES, "halo table");
+constexpr int64_t PEER_INBOX_OFFSET = PEER_AR_WORDS * 16 + PEER_TABLE_BYTES;  // bytes
 constexpr long long PEER_TIMEOUT_CYCLES = 60000000000ll;  // ~30 s at 1.9 GHz: bounded, so a lost peer cannot hang the GPU
 struct PeerComm {
-  PeerSlot *box[PEER_MAX_RANKS];  // box[p] = mailbox of rank p: [2][PEER_MAX_RANKS] slots
+  PeerWord *ar[PEER_MAX_RANKS];   // ar[p] = all-reduce words of rank p's mailbox
   unsigned long long *seq_ctr;    // this rank's count of completed fused reductions (device memory)
   int rank, n_ranks;
 };
-
-// Pair-compressed column index of the fixed CSR (SpMV variant 2).  Rows 2n,2n+1 of a velocity node
-// have the same column pattern and velocity columns come in pairs (2m,2m+1), so one stored index
-// serves up to 4 matrix entries.  A group = the two rows of a velocity node or one pressure row; its
-// columns are [np1 pairs | ns1 singles | np2 pairs | ns2 singles] = [owned u | owned p | ghost u | ghost p].
-struct __align__(8) GroupMeta {
-  int64_t val_start;    // rowptr of the group's first row
-  uint32_t item_start;  // first compressed index
-  uint16_t np1, ns1, np2, ns2;
-  uint32_t pad;
-};
-static_assert(sizeof(GroupMeta) == 24, "GroupMeta must be 24 bytes");
 
 // deal.II SolverGMRES bookkeeping kept on the device
 constexpr int GM_MAX_TMP = 64;
@@ -183,7 +184,6 @@ struct nsg_ctx {
   // device CSR
   int64_t *rowptr = nullptr, *pm_rowptr = nullptr;
   int32_t *col = nullptr, *pm_col = nullptr;
-  int32_t *col7 = nullptr;  // compact column index of SpMV variant 9 (one list per velocity node pair, then the pressure rows)
   double *vals = nullptr, *pm_vals = nullptr;
   int32_t *spmv_chunk_rows = nullptr;
   int64_t *diag_pos = nullptr;
@@ -197,11 +197,7 @@ struct nsg_ctx {
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;
   int32_t last_solve[4] = {0, 0, 0, 0};  // nsg_last_solve_info
-  nsg::GroupMeta *gmeta = nullptr;
-  int32_t *row_perm = nullptr, *group_perm = nullptr;
-  int32_t *gitems = nullptr;
-  int64_t n_groups = 0, n_ugroups = 0, n_items = 0;
-  bool have_paired = false;
+  bool have_paired = false;  // rows 2g, 2g+1 of every velocity node have the same column list (SpMV variant 7)
   int64_t spmv_n_chunks = 0;
   // mesh
   double *geom = nullptr;  // [5T] J^-T (a00,a01,a10,a11), |det J|
@@ -213,7 +209,6 @@ struct nsg_ctx {
   nsg::WorkList wl_u5, wl_p5;  // assembly variant 4: one pair per lane, lanes sorted by (round, cell)
   nsg::WorkList wl_u6, wl_p6;  // assembly variant 5 ("fan"): the lanes of an owner in one warp, every entry stored once
   bool fan_ok = false;         // the mesh is an oriented manifold triangulation the fan scheme can serve
-  int asm_stage = 1;           // variant 5: 0 lanes read the packets from global memory, 1 cp.async staging, 2 bulk-copy (TMA) staging
   // Neumann: boundary nodes -> faces
   int64_t n_bnodes = 0;
   int32_t *bnode_dof = nullptr, *bnode_ptr = nullptr, *bnode_face = nullptr, *bnode_pos = nullptr;
@@ -244,7 +239,16 @@ struct nsg_ctx {
   int64_t n_send = 0, n_recv = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
-  nsg::PeerSlot *mailbox = nullptr;      // this rank's mailbox (peer-writable)
+  char *mailbox = nullptr;               // this rank's mailbox (peer-writable): all-reduce words, halo table, halo inbox
+  int64_t mailbox_bytes = 0;
+  // peer-store halo exchange (after nsg_comm_set_peers): per send entry the destination word in the neighbour's inbox
+  bool halo_peer = false;
+  nsg::PeerWord **send_dst = nullptr;    // [n_send] parity-0 word; parity 1 is the next word
+  unsigned long long *halo_ctr = nullptr;  // [0] pushes completed, [1] receives completed (device)
+  unsigned int *halo_ticket = nullptr;     // [2]
+  int32_t *halo_err = nullptr;
+  int32_t *bgroups = nullptr;            // SpMV variant 7: row groups with a ghost column (recomputed after the exchange)
+  int64_t n_bgroups = 0;
   nsg::PeerComm peer{};                  // n_ranks <= 1 until nsg_comm_set_peers
   unsigned long long *ar_seq = nullptr;  // device counter behind peer.seq_ctr
   void *peer_mapped[nsg::PEER_MAX_RANKS] = {};

@@ -108,7 +108,6 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
   std::memset(&no_work, 0, sizeof no_work);
   no_work.cell = -1;
   std::vector<PairRec> recs((size_t)nchunks * NPC6, no_work);
-  std::vector<int32_t> cells((size_t)nchunks * NPC6, 0);
   int bad = 0, unsupported = 0;
   int64_t max_smem = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_smem) reduction(+ : bad, unsupported)
@@ -125,18 +124,6 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
     const int64_t img = kind == 0 ? (int64_t)ci.cnt : (int64_t)ci.cnt + ci.mcnt;
     std::vector<uint8_t> touched((size_t)img, 0);
     int64_t n_touched = 0;
-    // staged cells of the chunk
-    std::vector<int32_t> ccells;
-    for (int64_t g = ci.g0; g < ci.g1; ++g)
-      for (int64_t pi = gptr[g]; pi < gptr[g + 1]; ++pi) ccells.push_back(pcell[pi]);
-    std::sort(ccells.begin(), ccells.end());
-    ccells.erase(std::unique(ccells.begin(), ccells.end()), ccells.end());
-    if ((int64_t)ccells.size() > NPC6) {
-      bad++;
-      continue;
-    }
-    ci.n_threads = (int32_t)ccells.size();
-    for (size_t i = 0; i < ccells.size(); ++i) cells[(size_t)(b * NPC6) + i] = ccells[i];
     int owners_with_cells = 0;
     for (int64_t g = ci.g0; g < ci.g1; ++g) {
       const int s = (int)(gptr[g + 1] - gptr[g]);
@@ -263,18 +250,19 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
             }
           }
         }
+        const int pred_lane = pred[i] >= 0 ? lane0 + posn[pred[i]] : lane;
         rcd.k = (int32_t)((uint32_t)pk[p0 + i] | ((uint32_t)partner << 3) | ((uint32_t)has_partner << 8) | ((uint32_t)head << 9) |
-                          ((uint32_t)write_next << 10) | ((uint32_t)(s - 1 - posn[i]) << 11) | ((uint32_t)(g - ci.g0) << 16));
+                          ((uint32_t)write_next << 10) | ((uint32_t)(s - 1 - posn[i]) << 11) | ((uint32_t)(g - ci.g0) << 16) |
+                          ((uint32_t)pred_lane << 24));
         rcd.off[9] = (uint16_t)roff;
         rcd.off[10] = kind == 0 ? (uint16_t)len : (uint16_t)mrow_off;
-        rcd.off[11] = (uint16_t)(std::lower_bound(ccells.begin(), ccells.end(), rcd.cell) - ccells.begin());
         recs[(size_t)(ci.rec_base + warp * 32 + lane)] = rcd;
       }
     }
     // an entry of the pattern no cell contributes to (a pattern wider than the mesh implies) must still be written: zero-fill
     // (pressure chunks are always zero-filled: the p-p block of the Jacobian is structurally present and never written)
     if (kind == 0) ci.pad = (n_touched == img && owners_with_cells == ci.g1 - ci.g0) ? 0 : 1;
-    const int64_t smem = kind == 0 ? (int64_t)ci.n_threads * PK6S + ci.cnt + 2 * (ci.g1 - ci.g0) + 2 : (int64_t)ci.cnt + ci.mcnt + 2;
+    const int64_t smem = kind == 0 ? (int64_t)ci.cnt + 2 * (ci.g1 - ci.g0) + 2 : (int64_t)ci.cnt + ci.mcnt + 2;
     max_smem = std::max(max_smem, smem);
   }
   if (bad) return fail(NSG_ERR_ARG, "cell_dofs do not match the sparsity pattern (or a row has >= 65535 entries)");
@@ -286,7 +274,6 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
   out->max_stage = max_smem;
   NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
   NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC6));
-  if (kind == 0) NSG_TRY(upload(c, &out->cells, cells.data(), nchunks * NPC6));
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   *supported = true;
   return NSG_OK;

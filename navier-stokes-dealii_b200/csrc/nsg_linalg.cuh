@@ -146,272 +146,8 @@ k_spmv_vec8u(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *
   }
 }
 
-// variant 5 ("TMA stream"): persistent CTAs; the value / column / row-pointer slices of a chunk of
-// rows are brought into shared memory by 1-D bulk async copies (cp.async.bulk, completion on an
-// mbarrier) two chunks ahead of the compute, so the HBM stream never waits for the x gathers.
-constexpr int TMA_STAGES = 2;
-constexpr int TMA_VAL_ELEMS = SPMV_CAP + 8;          // slice start is aligned down to 4 elements
-constexpr int TMA_RP_ELEMS = SPMV_THREADS + 4;
-struct __align__(128) TmaStage {
-  double val[TMA_VAL_ELEMS];
-  int32_t col[TMA_VAL_ELEMS];
-  int64_t rp[TMA_RP_ELEMS];
-};
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok)
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-}
-
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_tma(int64_t n_chunks, const int32_t *__restrict__ chunk_rows, const int64_t *__restrict__ rowptr,
-           const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x,
-           double *__restrict__ y, const int32_t *__restrict__ state) {
-  if (state && *state != 0) return;
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  TmaStage *stage = reinterpret_cast<TmaStage *>(s_raw);
-  __shared__ uint64_t bars[TMA_STAGES];
-  __shared__ int64_t s_base[TMA_STAGES];   // first (aligned) non-zero held by the stage
-  __shared__ int32_t s_r0[TMA_STAGES], s_nr[TMA_STAGES], s_rpo[TMA_STAGES];
-  const int t = threadIdx.x;
-  if (t == 0) {
-    for (int i = 0; i < TMA_STAGES; ++i) mbar_init(&bars[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue = [&](int64_t chunk, int b) {  // thread 0 only
-    const int32_t r0 = chunk_rows[chunk], r1 = chunk_rows[chunk + 1];
-    const int64_t s = rowptr[r0], e = rowptr[r1];
-    const int64_t s4 = s & ~(int64_t)3, e4 = (e + 3) & ~(int64_t)3;
-    const int32_t r0e = r0 & ~1;
-    const int nrp = ((r1 - r0e + 1) + 1) & ~1;
-    s_base[b] = s4, s_r0[b] = r0, s_nr[b] = r1 - r0, s_rpo[b] = r0 - r0e;
-    const uint32_t nv = (uint32_t)(e4 - s4);
-    if (nv > (uint32_t)TMA_VAL_ELEMS) {  // a single over-long row: handled without staging
-      s_nr[b] = -1;
-      mbar_expect_tx(&bars[b], 0);
-      return;
-    }
-    mbar_expect_tx(&bars[b], nv * 12u + (uint32_t)nrp * 8u);
-    bulk_g2s(stage[b].val, vals + s4, nv * 8u, &bars[b]);
-    bulk_g2s(stage[b].col, col + s4, nv * 4u, &bars[b]);
-    bulk_g2s(stage[b].rp, rowptr + r0e, (uint32_t)nrp * 8u, &bars[b]);
-  };
-  const int64_t first = blockIdx.x, stride = gridDim.x;
-  if (t == 0)
-    for (int i = 0; i < TMA_STAGES; ++i)
-      if (first + i * stride < n_chunks) issue(first + i * stride, i);
-  __syncthreads();
-  const int sub = t >> 3, l8 = t & 7;
-  int it = 0;
-  for (int64_t chunk = first; chunk < n_chunks; chunk += stride, ++it) {
-    const int b = it % TMA_STAGES;
-    mbar_wait(&bars[b], (it / TMA_STAGES) & 1);
-    const int nr = s_nr[b];
-    const int32_t r0 = s_r0[b];
-    if (nr >= 0) {
-      const int64_t base = s_base[b];
-      const int64_t *rp = stage[b].rp + s_rpo[b];
-      const double *sv = stage[b].val;
-      const int32_t *sc = stage[b].col;
-      for (int rb = 0; rb < nr; rb += SPMV_THREADS / 8) {
-        const int r = rb + sub;
-        double acc = 0.0;
-        if (r < nr) {
-          const int pe = (int)(rp[r + 1] - base);
-#pragma unroll 4
-          for (int p = (int)(rp[r] - base) + l8; p < pe; p += 8) acc += sv[p] * __ldg(x + sc[p]);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (r < nr && l8 == 0) y[r0 + r] = acc;
-      }
-    } else {
-      const int64_t s = rowptr[r0], e = rowptr[r0 + 1];
-      double acc = 0.0;
-      for (int64_t p = s + t; p < e; p += SPMV_THREADS) acc += vals[p] * x[col[p]];
-      acc = warp_sum_all(acc);
-      __shared__ double s_part[SPMV_THREADS / 32];
-      if ((t & 31) == 0) s_part[t >> 5] = acc;
-      __syncthreads();
-      if (t == 0) {
-        double a = 0.0;
-        for (int i = 0; i < SPMV_THREADS / 32; ++i) a += s_part[i];
-        y[r0] = a;
-      }
-    }
-    __syncthreads();  // every thread is done with stage b
-    const int64_t nxt = chunk + TMA_STAGES * stride;
-    if (t == 0 && nxt < n_chunks) issue(nxt, b);
-    __syncthreads();  // s_* of stage b are published before anyone can pass the next wait on it
-  }
-}
-
-// variant 2 ("paired CSR"): values stay in CSR order; the column index is pair-compressed (GroupMeta).
-// 8 lanes walk the flat value positions of a group; the two rows of a velocity node share every
-// decoded index and every gathered x entry.  ~9.4 instead of 12 bytes per non-zero.
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_paired(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__ meta,
-              const int32_t *__restrict__ items, const double *__restrict__ vals, const double *__restrict__ x,
-              double *__restrict__ y, const int32_t *__restrict__ state) {
-  if (state && *state != 0) return;
-  // metas are stored sorted by length inside windows (groups of similar length share a warp);
-  // the group id travels in the descriptor
-  const int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  const int l8 = threadIdx.x & 7;
-  if (threadIdx.x < 6) {  // 32 descriptors of a future CTA = 6 lines
-    const int64_t fs = (blockIdx.x + SPMV_PF_DIST) * (int64_t)(SPMV_THREADS / 8);
-    if (fs < n_groups) prefetch_l2(reinterpret_cast<const char *>(meta + fs) + 128 * threadIdx.x);
-  }
-  double acc0 = 0.0, acc1 = 0.0;
-  GroupMeta m;
-  m.pad = 0xffffffffu;
-  if (slot < n_groups) m = meta[slot];
-  const int64_t g = slot < n_groups ? (int64_t)m.pad : n_groups;
-  const bool two = g < n_ugroups;
-  if (g < n_groups) {
-    const int np1 = m.np1, ns1 = m.ns1, np2 = m.np2;
-    const int b1 = 2 * np1, b2 = b1 + ns1, b3 = b2 + 2 * np2, len = b3 + m.ns2;
-    const double *v0 = vals + m.val_start;
-    const double *v1 = v0 + len;
-    const int32_t *it = items + m.item_start;
-#pragma unroll 4
-    for (int i = l8; i < len; i += 8) {
-      int j, sub;
-      if (i < b1) {
-        j = i >> 1, sub = i & 1;
-      } else if (i < b2) {
-        j = np1 + (i - b1), sub = 0;
-      } else if (i < b3) {
-        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
-      } else {
-        j = np1 + ns1 + np2 + (i - b3), sub = 0;
-      }
-      const double xv = __ldg(x + __ldg(it + j) + sub);
-      acc0 += __ldcs(v0 + i) * xv;
-      if (two) acc1 += __ldcs(v1 + i) * xv;
-    }
-  }
-  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
-  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
-  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-  if (g < n_groups && l8 == 0) {
-    if (two) {
-      y[2 * g] = acc0;
-      y[2 * g + 1] = acc1;
-    } else {
-      y[2 * n_ugroups + (g - n_ugroups)] = acc0;
-    }
-  }
-}
-
-// variant 6: the paired index of variant 2 in the persistent, extent-prefetching, fully unrolled
-// form of variant 4 (least bytes per non-zero AND a short dependent-load chain)
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_paired_p(int64_t n_groups, int64_t n_ugroups, const GroupMeta *__restrict__ meta, const int32_t *__restrict__ items,
-                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                const int32_t *__restrict__ state) {
-  if (state && *state != 0) return;
-  const int l8 = threadIdx.x & 7;
-  const int64_t G = ((int64_t)gridDim.x * SPMV_THREADS) >> 3;
-  int64_t slot = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  GroupMeta m;
-  m.val_start = 0, m.item_start = 0, m.np1 = m.ns1 = m.np2 = m.ns2 = 0, m.pad = 0xffffffffu;
-  if (slot < n_groups) m = meta[slot];
-  while (true) {
-    GroupMeta mn;
-    mn.val_start = 0, mn.item_start = 0, mn.np1 = mn.ns1 = mn.np2 = mn.ns2 = 0, mn.pad = 0xffffffffu;
-    const int64_t sn = slot + G;
-    if (sn < n_groups) mn = meta[sn];
-    const int64_t g = (int64_t)m.pad;
-    const bool valid = slot < n_groups;
-    const bool two = valid && g < n_ugroups;
-    const int np1 = m.np1, ns1 = m.ns1, np2 = m.np2;
-    const int b1 = 2 * np1, b2 = b1 + ns1, b3 = b2 + 2 * np2, len = valid ? b3 + m.ns2 : 0;
-    const double *v0 = vals + m.val_start;
-    const double *v1 = v0 + len;
-    const int32_t *it = items + m.item_start;
-    double a0[8], a1[8];
-    int32_t cc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = l8 + 8 * k;
-      const bool in = i < len;
-      int j, sub;
-      if (i < b1) {
-        j = i >> 1, sub = i & 1;
-      } else if (i < b2) {
-        j = np1 + (i - b1), sub = 0;
-      } else if (i < b3) {
-        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
-      } else {
-        j = np1 + ns1 + np2 + (i - b3), sub = 0;
-      }
-      a0[k] = in ? __ldcs(v0 + i) : 0.0;
-      a1[k] = (in && two) ? __ldcs(v1 + i) : 0.0;
-      cc[k] = in ? __ldg(it + j) + sub : -1;
-    }
-    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (cc[k] >= 0) {
-        const double xv = __ldg(x + cc[k]);
-        acc0 += a0[k] * xv;
-        acc1 += a1[k] * xv;
-      }
-    for (int i = l8 + 64; i < len; i += 8) {  // rows longer than 64 entries
-      int j, sub;
-      if (i < b1) {
-        j = i >> 1, sub = i & 1;
-      } else if (i < b2) {
-        j = np1 + (i - b1), sub = 0;
-      } else if (i < b3) {
-        j = np1 + ns1 + ((i - b2) >> 1), sub = (i - b2) & 1;
-      } else {
-        j = np1 + ns1 + np2 + (i - b3), sub = 0;
-      }
-      const double xv = __ldg(x + __ldg(it + j) + sub);
-      acc0 += __ldcs(v0 + i) * xv;
-      if (two) acc1 += __ldcs(v1 + i) * xv;
-    }
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-    if (valid && l8 == 0) {
-      if (two) {
-        y[2 * g] = acc0;
-        y[2 * g + 1] = acc1;
-      } else {
-        y[2 * n_ugroups + (g - n_ugroups)] = acc0;
-      }
-    }
-    if (__all_sync(0xffffffffu, sn >= n_groups)) break;
-    slot = sn;
-    m = mn;
-  }
-}
+// (The measured-slower SpMV variants of round 1 - TMA stream, pair-compressed index, two-entry row pairs, compact
+//  column index - are in the git history at tag-less commit 573725d; profiles/r01_summary.md has their rates.)
 
 // Variant 7 ("row pairs"): the two rows of a velocity node have the SAME column list (full coupling of the two
 // components), so 8 lanes serve both rows at once: one column index and one x gather feed two matrix entries.
@@ -422,21 +158,27 @@ template <bool PERSISTENT>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-               const int32_t *__restrict__ state) {
+               const int32_t *__restrict__ state, const int32_t *__restrict__ list = nullptr, int64_t n_list = 0) {
+  // list != nullptr: only the groups list[0..n_list) (the rows with a ghost column, recomputed after the halo exchange
+  // while the full sweep ran beside it); same lanes, same summation order per row as the full sweep
   if (state && *state != 0) return;
   const int l8 = threadIdx.x & 7;
-  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t n_all = n_ugroups + (n_rows - 2 * n_ugroups);
+  const int64_t n_groups = list ? n_list : n_all;
   const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
-  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t gi = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  int64_t g = gi < n_groups ? (list ? (int64_t)list[gi] : gi) : n_all;
   int64_t s = 0, e = 0;
-  if (g < n_groups) {
+  if (gi < n_groups) {
     const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
     s = rowptr[r], e = rowptr[r + 1];
   }
   while (true) {
     int64_t sn = 0, en = 0;
-    const int64_t gn = g + G;
-    if (PERSISTENT && gn < n_groups) {
+    const int64_t gin = gi + G;
+    int64_t gn = n_all;
+    if (PERSISTENT && gin < n_groups) {
+      gn = list ? (int64_t)list[gin] : gin;
       const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
       sn = rowptr[r], en = rowptr[r + 1];
     }
@@ -471,7 +213,7 @@ k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ ro
     acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
     acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-    if (g < n_groups && l8 == 0) {
+    if (gi < n_groups && l8 == 0) {
       if (pair) {
         y[2 * g] = acc0;
         y[2 * g + 1] = acc1;
@@ -480,199 +222,9 @@ k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ ro
       }
     }
     if (!PERSISTENT) break;
-    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
-    g = gn, s = sn, e = en;
-    if (g >= n_groups) s = e = 0;
-  }
-}
-
-// Variant 9: variant 7 reading a COMPACT copy of the column index that stores the shared column list of a
-// velocity node once (col7: the first row of every node pair, then the pressure rows; built once by
-// k_build_col7).  Variant 7 skips the second row's indices but they sit in the same DRAM lines as the values
-// around them, so its DRAM traffic stays at 12 B per non-zero; with the compact copy the index really costs
-// 2 B per velocity non-zero.  The position of a group's list needs no pointer array: rows 2g and 2g+1 have equal
-// lengths, so list(g) starts at rowptr[2g]/2, and pressure row r at rowptr[n_u]/2 + rowptr[r] - rowptr[n_u].
-__global__ void k_build_col7(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                             int32_t *__restrict__ col7) {
-  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
-  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
-  const int64_t half = rowptr[2 * n_ugroups] >> 1;
-  const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
-  const int64_t s = rowptr[r], e = rowptr[r + 1];
-  const int64_t dst = g < n_ugroups ? (s >> 1) : half + (s - rowptr[2 * n_ugroups]);
-  for (int64_t i = lane; i < e - s; i += 32) col7[dst + i] = col[s + i];
-}
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_rowpair_c(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col7,
-                 const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                 const int32_t *__restrict__ state) {
-  if (state && *state != 0) return;
-  const int l8 = threadIdx.x & 7;
-  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
-  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
-  const int64_t nnz_u = rowptr[2 * n_ugroups], half = nnz_u >> 1;
-  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  int64_t s = 0, e = 0;
-  if (g < n_groups) {
-    const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
-    s = rowptr[r], e = rowptr[r + 1];
-  }
-  while (true) {
-    int64_t sn = 0, en = 0;
-    const int64_t gn = g + G;
-    if (PERSISTENT && gn < n_groups) {
-      const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
-      sn = rowptr[r], en = rowptr[r + 1];
-    }
-    const bool pair = g < n_ugroups;
-    const int64_t len = pair ? e - s : 0;
-    const int64_t coff = (pair ? (s >> 1) : half + (s - nnz_u)) - s;  // col7[coff + p] = column of entry p of the group's first row
-    double v0[8], v1[8];
-    int32_t c[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int64_t p = s + l8 + 8 * k;
-      const bool in = p < e;
-      v0[k] = in ? __ldcs(vals + p) : 0.0;
-      v1[k] = (in && pair) ? __ldcs(vals + p + len) : 0.0;
-      c[k] = in ? __ldcs(col7 + coff + p) : -1;
-    }
-    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (c[k] >= 0) {
-        const double xv = __ldg(x + c[k]);
-        acc0 += v0[k] * xv;
-        acc1 += v1[k] * xv;
-      }
-    for (int64_t p = s + l8 + 64; p < e; p += 8) {
-      const double xv = __ldg(x + __ldcs(col7 + coff + p));
-      acc0 += __ldcs(vals + p) * xv;
-      if (pair) acc1 += __ldcs(vals + p + len) * xv;
-    }
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-    if (g < n_groups && l8 == 0) {
-      if (pair) {
-        y[2 * g] = acc0;
-        y[2 * g + 1] = acc1;
-      } else {
-        y[g + n_ugroups] = acc0;
-      }
-    }
-    if (!PERSISTENT) break;
-    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
-    g = gn, s = sn, e = en;
-    if (g >= n_groups) s = e = 0;
-  }
-}
-
-// Variant 8: variant 7 with two adjacent entries per lane and step (64-bit index loads, 128-bit value loads of the
-// first row) and ONE 128-bit gather of x when the two columns are the (2m, 2m+1) pair of a velocity node - which
-// they are for all velocity columns, since a row starts at an even position and velocity columns come in pairs.
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_rowpair2(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                const int32_t *__restrict__ state) {
-  if (state && *state != 0) return;
-  const int l8 = threadIdx.x & 7;
-  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
-  const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
-  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  int64_t s = 0, e = 0;
-  if (g < n_groups) {
-    const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
-    s = rowptr[r], e = rowptr[r + 1];
-  }
-  while (true) {
-    int64_t sn = 0, en = 0;
-    const int64_t gn = g + G;
-    if (PERSISTENT && gn < n_groups) {
-      const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
-      sn = rowptr[r], en = rowptr[r + 1];
-    }
-    const bool pair = g < n_ugroups;
-    const int64_t len = pair ? e - s : 0;
-    double acc0 = 0.0, acc1 = 0.0;
-    if (pair) {  // velocity node: the row starts at an even position -> aligned 2-entry accesses
-      int2 c[4];
-      double2 v0[4];
-      double v1a[4], v1b[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t p = s + 2 * l8 + 16 * k;
-        const bool in0 = p < e, in1 = p + 1 < e;
-        c[k] = make_int2(-1, -1), v0[k] = make_double2(0.0, 0.0), v1a[k] = v1b[k] = 0.0;
-        if (in0) {
-          c[k] = __ldcs(reinterpret_cast<const int2 *>(col + p));
-          v0[k] = __ldcs(reinterpret_cast<const double2 *>(vals + p));
-          v1a[k] = __ldcs(vals + p + len);
-          if (in1) v1b[k] = __ldcs(vals + p + len + 1);
-          else c[k].y = -1, v0[k].y = 0.0;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c[k].x >= 0) {
-          double x0, x1 = 0.0;
-          if (c[k].y == c[k].x + 1 && !(c[k].x & 1)) {
-            const double2 xx = __ldg(reinterpret_cast<const double2 *>(x + c[k].x));
-            x0 = xx.x, x1 = xx.y;
-          } else {
-            x0 = __ldg(x + c[k].x);
-            if (c[k].y >= 0) x1 = __ldg(x + c[k].y);
-          }
-          acc0 += v0[k].x * x0;
-          acc0 += v0[k].y * x1;
-          acc1 += v1a[k] * x0;
-          acc1 += v1b[k] * x1;
-        }
-      for (int64_t p = s + l8 + 64; p < e; p += 8) {
-        const double xv = __ldg(x + __ldcs(col + p));
-        acc0 += __ldcs(vals + p) * xv;
-        acc1 += __ldcs(vals + p + len) * xv;
-      }
-    } else {
-      double v[8];
-      int32_t c[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int64_t p = s + l8 + 8 * k;
-        const bool in = p < e;
-        v[k] = in ? __ldcs(vals + p) : 0.0;
-        c[k] = in ? __ldcs(col + p) : -1;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (c[k] >= 0) acc0 += v[k] * __ldg(x + c[k]);
-      for (int64_t p = s + l8 + 64; p < e; p += 8) acc0 += __ldcs(vals + p) * __ldg(x + __ldcs(col + p));
-    }
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-    if (g < n_groups && l8 == 0) {
-      if (pair) {
-        y[2 * g] = acc0;
-        y[2 * g + 1] = acc1;
-      } else {
-        y[g + n_ugroups] = acc0;
-      }
-    }
-    if (!PERSISTENT) break;
-    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
-    g = gn, s = sn, e = en;
-    if (g >= n_groups) s = e = 0;
+    if (__all_sync(0xffffffffu, gin >= n_groups)) break;
+    gi = gin, g = gn, s = sn, e = en;
+    if (gi >= n_groups) s = e = 0;
   }
 }
 
@@ -682,43 +234,107 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// peer all-reduce of cnt (<= blockDim.x, <= PEER_MAX_VALS) values held in shared memory `sv`, executed by
-// the last block of a reduction; result left in sv (identical bits on every rank).  The sequence number
-// lives on the device (pc.seq_ctr) and advances only when a reduction really runs, so kernels skipped by
-// the solver's `state` early-exit (identically on every rank) do not break the parity double-buffering.
+__device__ __forceinline__ ulonglong2 ld_volatile_word(const PeerWord *p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_word(PeerWord *p, double v, unsigned long long seq) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)), "l"(seq) : "memory");
+}
+
+// peer all-reduce of cnt (<= PEER_MAX_VALS) values held in shared memory `sv`, executed by all threads of the last block of
+// a reduction; result left in sv (identical bits on every rank).  Thread (p, j) stores {sv[j], seq} into rank p's mailbox
+// with one 128-bit store and then polls slot (p, j) of its OWN mailbox with 128-bit loads until the stamp is seq: no
+// fence, no separate flag.  The sequence number lives on the device (pc.seq_ctr) and advances only when a reduction
+// really runs, so kernels skipped by the solver's `state` early-exit (identically on every rank) do not break the parity
+// double-buffering.  A wait that runs into its time limit (a lost peer) turns the result into NaN on this rank and
+// poisons the stamp it publishes from then on, so the peers fail in their next reduction instead of hanging.
 __device__ __forceinline__ void peer_allreduce_block(const PeerComm &pc, double *sv, int cnt) {
+  __shared__ double s_in[PEER_MAX_RANKS * PEER_MAX_VALS];
+  __shared__ int s_bad;
   const int t = threadIdx.x;
   const unsigned long long seq = *(volatile unsigned long long *)pc.seq_ctr + 1ull;  // written below, after the barriers
-  const int par = (int)(seq & 1ull);
-  if (t < cnt)
-    for (int p = 0; p < pc.n_ranks; ++p) pc.box[p][par * PEER_MAX_RANKS + pc.rank].v[t] = sv[t];
-  __threadfence_system();
-  __syncthreads();
-  if (t < pc.n_ranks) {
-    volatile unsigned long long *flag = &pc.box[t][par * PEER_MAX_RANKS + pc.rank].seq;
-    *flag = seq;  // publish to rank t
-    // wait for rank t's contribution in my own mailbox
-    volatile unsigned long long *mine = &pc.box[pc.rank][par * PEER_MAX_RANKS + t].seq;
-    const long long t0 = clock64();
-    while (*mine != seq) {
-      __nanosleep(32);
-      if (clock64() - t0 > PEER_TIMEOUT_CYCLES) break;  // a peer is gone: the NaN below surfaces as a solver failure
-    }
+  const int64_t par = (int64_t)(seq & 1ull) * PEER_MAX_RANKS * PEER_MAX_VALS;
+  const int total = pc.n_ranks * cnt;
+  if (t == 0) s_bad = 0;
+  for (int i = t; i < total; i += blockDim.x) {
+    const int p = i / cnt, j = i - p * cnt;
+    st_volatile_word(pc.ar[p] + par + (int64_t)pc.rank * PEER_MAX_VALS + j, sv[j], seq);
   }
-  __threadfence_system();
+  __syncthreads();
+  for (int i = t; i < total; i += blockDim.x) {
+    const int p = i / cnt, j = i - p * cnt;
+    const PeerWord *w = pc.ar[pc.rank] + par + (int64_t)p * PEER_MAX_VALS + j;
+    ulonglong2 x = ld_volatile_word(w);
+    if (x.y != seq) {
+      const long long t0 = clock64();
+      do {
+        x = ld_volatile_word(w);
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
+          s_bad = 1;
+          break;
+        }
+      } while (x.y != seq);
+    }
+    s_in[p * PEER_MAX_VALS + j] = __longlong_as_double((long long)x.x);
+  }
   __syncthreads();
   if (t < cnt) {
-    const PeerSlot *my = pc.box[pc.rank] + par * PEER_MAX_RANKS;
     double a = 0.0;
-    bool ok = true;
-    for (int q = 0; q < pc.n_ranks; ++q) {
-      ok &= (*(volatile const unsigned long long *)&my[q].seq == seq);
-      a += *(volatile const double *)&my[q].v[t];
-    }
-    sv[t] = ok ? a : nan("");
+    for (int q = 0; q < pc.n_ranks; ++q) a += s_in[q * PEER_MAX_VALS + t];  // rank order: identical bits everywhere
+    sv[t] = s_bad ? nan("") : a;
   }
-  if (t == 0) *pc.seq_ctr = seq;
+  if (t == 0) *pc.seq_ctr = s_bad ? seq + (1ull << 40) : seq;  // poisoned: no later stamp of this rank matches any more
   __syncthreads();
+}
+
+// ---- halo exchange over peer memory (K8) ----------------------------------------------------------------------
+// push: {value of my owned DoF, stamp} straight into the inbox of the neighbour that holds it as a ghost
+__global__ void k_halo_push(int64_t n_send, const int32_t *__restrict__ send_idx, const double *__restrict__ vec,
+                            PeerWord *const *__restrict__ send_dst, unsigned long long *ctr, unsigned int *ticket) {
+  __shared__ bool s_last;
+  const unsigned long long seq = *(volatile unsigned long long *)ctr + 1ull;
+  const int par = (int)(seq & 1ull);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_send; i += (int64_t)gridDim.x * blockDim.x)
+    st_volatile_word(send_dst[i] + par, vec[send_idx[i]], seq);
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *ctr = seq;
+    *ticket = 0u;
+  }
+}
+// wait + scatter: poll my own inbox until every word carries this exchange's stamp, then write the ghost entries
+__global__ void k_halo_wait_scatter(int64_t n_recv, const int32_t *__restrict__ recv_idx, const PeerWord *inbox, double *__restrict__ vec,
+                                    unsigned long long *ctr, unsigned int *ticket, int32_t *err) {
+  __shared__ bool s_last;
+  const unsigned long long seq = *(volatile unsigned long long *)ctr + 1ull;
+  const int par = (int)(seq & 1ull);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_recv; i += (int64_t)gridDim.x * blockDim.x) {
+    const PeerWord *w = inbox + 2 * i + par;
+    ulonglong2 x = ld_volatile_word(w);
+    if (x.y != seq) {
+      const long long t0 = clock64();
+      do {
+        x = ld_volatile_word(w);
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
+          *err = 1;
+          x.x = (unsigned long long)__double_as_longlong(nan(""));
+          break;
+        }
+      } while (x.y != seq);
+    }
+    vec[recv_idx[i]] = __longlong_as_double((long long)x.x);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *ctr = seq;
+    *ticket = 0u;
+  }
 }
 
 // block partial -> partials[], last block sums partials in index order -> *out

@@ -17,6 +17,10 @@
 #include <thread>
 
 #include "nsg.h"
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "nst.h"
 
 namespace {
@@ -33,6 +37,22 @@ double env_double(const char *n, double dflt) {
 std::string env_str(const char *n, const std::string &dflt) {
   const char *v = std::getenv(n);
   return v ? std::string(v) : dflt;
+}
+// what all ranks of one launch share and a later launch does not: NS_RENDEZVOUS_NONCE, else the parent process
+// (torchrun agent / mpirun) identified by pid and start time (field 22 of /proc/<pid>/stat)
+std::string launch_nonce() {
+  if (const char *v = std::getenv("NS_RENDEZVOUS_NONCE")) return v;
+  const long ppid = (long)::getppid();
+  std::string start = "0";
+  std::ifstream f("/proc/" + std::to_string(ppid) + "/stat");
+  std::string line;
+  if (f && std::getline(f, line)) {
+    const size_t rp = line.rfind(')');   // the command name may contain spaces
+    std::stringstream ss(rp == std::string::npos ? line : line.substr(rp + 1));
+    std::string tok;
+    for (int i = 0; i < 20 && (ss >> tok); ++i) start = tok;   // 20th field after the name = starttime
+  }
+  return std::to_string(ppid) + "-" + start;
 }
 std::vector<int> env_list(const char *n, std::vector<int> dflt) {
   const char *v = std::getenv(n);
@@ -148,24 +168,45 @@ void NavierStokesSolver::setup() {
                         nst_part_n_boundary_faces(part), nst_part_bface_cell(part), nst_part_bface_face(part),
                         nst_part_bface_tag(part)));
   if (mpi_size > 1) {
-    // ncclUniqueId from rank 0 through a rendezvous file (no MPI in this image)
-    const std::string path = env_str("NS_RENDEZVOUS", "/tmp/ns_nccl_id." + env_str("MASTER_PORT", "0"));
+    // ncclUniqueId from rank 0 through a rendezvous file (no MPI in this image).  The file belongs to ONE launch: its
+    // name and its header carry a nonce all ranks of the launch share (the launcher's pid and start time - the ranks
+    // are siblings under torchrun / mpirun - or NS_RENDEZVOUS_NONCE), rank 0 removes a stale file before it creates the
+    // new one with O_EXCL | O_NOFOLLOW (mode 0600), readers accept only a regular file of their own uid whose header
+    // matches, and rank 0 removes the file once the communicator is up.
+    const std::string nonce = launch_nonce();
+    const std::string path = env_str("NS_RENDEZVOUS", "/tmp/ns_nccl_id." + env_str("MASTER_PORT", "0")) + "." + nonce;
     char id[128];
+    char header[64];
+    std::memset(header, 0, sizeof header);
+    std::snprintf(header, sizeof header, "NSNCCLID1 %s", nonce.c_str());
     if (mpi_rank == 0) {
       NSG_CALL(nsg_comm_unique_id(id));
-      std::ofstream f(path + ".tmp", std::ios::binary);
-      f.write(id, 128);
-      f.close();
-      std::rename((path + ".tmp").c_str(), path.c_str());
+      ::unlink(path.c_str());
+      const std::string tmp = path + ".tmp";
+      ::unlink(tmp.c_str());
+      const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+      if (fd < 0) fail("cannot create the NCCL id file " + tmp);
+      const bool ok = ::write(fd, header, sizeof header) == (ssize_t)sizeof header && ::write(fd, id, 128) == 128;
+      ::close(fd);
+      if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) fail("cannot write the NCCL id file " + path);
     } else {
       for (int tries = 0;; ++tries) {
-        std::ifstream f(path, std::ios::binary);
-        if (f && f.read(id, 128)) break;
+        const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+        if (fd >= 0) {
+          struct stat st;
+          char h[64];
+          const bool ok = ::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_uid == ::getuid() &&
+                          ::read(fd, h, sizeof h) == (ssize_t)sizeof h && std::memcmp(h, header, sizeof h) == 0 &&
+                          ::read(fd, id, 128) == 128;
+          ::close(fd);
+          if (ok) break;
+        }
         if (tries > 6000) fail("timed out waiting for the NCCL id file " + path);
         std::this_thread::sleep_for(std::chrono::milliseconds(10));
       }
     }
-    NSG_CALL(nsg_comm_init(dev, (int)mpi_rank, (int)mpi_size, id));
+    NSG_CALL(nsg_comm_init(dev, (int)mpi_rank, (int)mpi_size, id));  // collective: every rank has read the file when it returns
+    if (mpi_rank == 0) ::unlink(path.c_str());
     NSG_CALL(nsg_set_halo(dev, I.n_neighbors, nst_part_neighbors(part), nst_part_send_ptr(part), nst_part_send_idx(part),
                           nst_part_recv_ptr(part), nst_part_recv_idx(part)));
   }

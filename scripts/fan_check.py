@@ -24,9 +24,8 @@ for case in CASES:
         o.set_params(**kw); o.set_solution(sol); o.set_solution_old(old); o.assemble()
         Jo, Mo, Ro = o.get_matrix_values(), o.get_pm_values(), o.get_residual()
         dev.set_params(**kw); dev.set_solution(sol); dev.set_solution_old(old)
-        for variant, stage in ((4, 0), (5, 0), (5, 1), (5, 2)):
+        for variant, stage in ((4, 0), (5, 0)):
             dev.set_tuning(1, variant)
-            dev.set_tuning(6, stage)
             dev.assemble()
             J, M, R = dev.get_matrix_values(), dev.get_pm_values(), dev.get_residual()
             ej = row_scaled_err(J, Jo, part.jac_rowptr); em = row_scaled_err(M, Mo, part.pm_rowptr)
@@ -60,9 +59,9 @@ ms = dev.time_kernel(5, 3)
 sms = 148
 print(f"FP64 pipe micro-benchmark: {ms:.3f} ms per launch -> {sms * 67108864 * 2 / ms / 1e9:.1f} TFLOP/s (if {sms} SMs)", flush=True)
 ref = None
-for variant, stage, conc in ((4, 0, 1), (5, 0, 1), (5, 1, 1), (5, 2, 1), (5, 1, 0), (5, 2, 0)):
+for variant, stage, conc in ((4, 0, 1), (5, 0, 1), (5, 0, 0)):
     os.environ["NSG_ASM_CONCURRENT"] = str(conc)
-    dev.set_tuning(1, variant); dev.set_tuning(6, stage)
+    dev.set_tuning(1, variant)
     dev.time_kernel(0, 3)
     ms = dev.time_kernel(0, 10)
     J, R = np.concatenate([dev.get_matrix_values(), dev.get_pm_values()]), dev.get_residual()

@@ -54,11 +54,19 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
         obj.set_solution_old(0.9 * s)
         obj.assemble()
 
-    def check(what, a, b, tol):
+    def check(what, a, b, tol, category="assembly"):
         err = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
         good = err <= tol
         state["ok"] &= good
+        state["checks"].append({"mesh": name, "category": category, "what": what, "err": err, "tol": tol, "ok": bool(good)})
         print(f"[rank {rank}] {time.strftime('%H:%M:%S')} {name}: {what:28s} rel err {err:.3e} {'ok' if good else 'FAIL'}", flush=True)
+
+    def record(what, good, category, detail):
+        state["ok"] &= bool(good)
+        state["checks"].append({"mesh": name, "category": category, "what": what, "err": None, "tol": None, "ok": bool(good),
+                                "detail": detail})
+        if not good:
+            print(f"[rank {rank}] {name}: {what} FAIL {detail}", flush=True)
 
     Jo = o.get_matrix_values()
     jo_rows = np.concatenate([_reorder(part, Jo, rp, col, gr) for gr in own])
@@ -69,21 +77,21 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
     check("R after Dirichlet", dev.get_residual(), o.get_residual()[own], 1e-12)
     check("||R|| (allreduce)", np.array([dev.residual_norm()]), np.array([o.residual_norm()]), 1e-12)
     x = np.random.default_rng(5).standard_normal(d.n)
-    for variant in (0, 2, 1):
+    for variant in (0, 1, 4, 7):       # 7 = the default
         dev.set_tuning(0, variant)
-        check(f"SpMV with halo, variant {variant}", dev.spmv(x[own]), o.spmv(x)[own], 1e-12)
+        check(f"SpMV with halo, variant {variant}", dev.spmv(x[own]), o.spmv(x)[own], 1e-12, "spmv")
+    state["neighbors"] = max(state.get("neighbors", 0), int(part.n_neighbors))
     rd = dev.solve(0, 1e-2, 100000, 30, 0, check=False)
     ro = o.solve(0, 1e-2, 100000, 30, 0)
     print(f"[rank {rank}] {name}: GMRES identity: device {rd} oracle {ro}", flush=True)
-    good = rd[2] == ro[2] and abs(rd[0] - ro[0]) <= max(2, 0.1 * ro[0])
-    if not good:
-        print(f"[rank {rank}] {name}: GMRES identity step counts FAIL", flush=True)
-    state["ok"] &= good
+    record("GMRES identity step counts", rd[2] == ro[2] and abs(rd[0] - ro[0]) <= max(2, 0.1 * ro[0]), "gmres", f"device {rd} oracle {ro}")
+    info = dev.last_solve_info()
+    record("GMRES identity ran the multi-kernel path with SpMV 7", (not info["fused"]) and info["spmv_variant"] == 7, "gmres", str(info))
     h1, h2 = dev.gmres_history(), o.gmres_history()
     k = min(28, len(h1), len(h2))
-    check("GMRES history (first cycle)", h1[:k], h2[:k], 1e-9)
+    check("GMRES history (first cycle)", h1[:k], h2[:k], 1e-9, "gmres")
     if rd[0] == ro[0] and rd[0] < 400:
-        check("delta", dev.get_delta(), o.get_delta()[own], 1e-6)
+        check("delta", dev.get_delta(), o.get_delta()[own], 1e-6, "gmres")
     # block preconditioners: per-rank ILU(0) == block-Jacobi ILU(0) in the oracle
     u_off = np.concatenate([[0], np.cumsum(d.part_n_u)])
     p_off = np.concatenate([[0], np.cumsum(d.part_n_p)])
@@ -94,11 +102,8 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
         rd = dev.solve(precond, 1e-6, 2000, 30, 0, check=False)
         ro = o.solve(precond, 1e-6, 2000, 30, 0)
         print(f"[rank {rank}] {name}: GMRES precond {precond}: device {rd} oracle {ro}", flush=True)
-        good = rd[2] == ro[2] == 0 and rd[0] == ro[0]
-        if not good:
-            print(f"[rank {rank}] {name}: GMRES precond {precond} step counts FAIL", flush=True)
-        state["ok"] &= good
-        check(f"delta precond {precond}", dev.get_delta(), o.get_delta()[own], 1e-6)
+        record(f"GMRES precond {precond} step counts", rd[2] == ro[2] == 0 and rd[0] == ro[0], "precond", f"device {rd} oracle {ro}")
+        check(f"delta precond {precond}", dev.get_delta(), o.get_delta()[own], 1e-6, "precond")
     dev.close()
 
 
@@ -109,7 +114,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    state = {"ok": True}
+    state = {"ok": True, "checks": []}
     for case in (("cylinder_cmy.msh", 0, [{11: True}, {11: True, 12: False, 13: False}], dict(u_m=1.5, H=0.41), dict(), 0.02, ()),
                  ("square_h0.05.msh", 0, [{0: True}, {2: False, 3: False}], dict(u_m=1.5, H=1.0), dict(nu=0.01, neumann_id=1), 0.05,
                   (2, 1))):
@@ -118,6 +123,11 @@ def main():
         run_case(rank, world, local, uid[0], case[0], case[1], case[2], case[3], case[4], case[5], case[6], state)
     t = torch.tensor([1.0 if state["ok"] else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out_dir = os.environ.get("MGPU_RESULT_DIR")
+    if out_dir:      # per-rank machine-readable results for tests/test_gpu_multi.py
+        import json
+        with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+            json.dump({"rank": rank, "world": world, "neighbors": state.get("neighbors", 0), "checks": state["checks"]}, f)
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_CHECK", "PASS" if t.item() == 1.0 else "FAIL", flush=True)

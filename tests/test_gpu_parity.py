@@ -39,14 +39,14 @@ def rel(a, b):
 
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("mode", ["newton", "steady", "stokes"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 4, 5])
 def test_assembly_parity(pkg, case, mode, variant):
     m, d, part, calls, neumann, inlet = build(pkg, case)
     dev, o = pkg.DeviceProblem(part, 0), Oracle(part)
-    dev.set_tuning(1, variant)     # 0: literal quadrature loop, 1: factored tables, 2: factored + per-cell packets
-    # the factored variant re-associates the quadrature sums (geometry x pre-integrated table):
-    # same integrals, a few more ulps of difference from the oracle's literal loop
-    tol = 1e-12 if variant == 0 else 5e-12
+    dev.set_tuning(1, variant)     # 0: literal quadrature loop in the reference's order, 4: packets + round-sorted lanes, 5: fan scheme (default)
+    # measured: every variant agrees with the oracle to 4e-14 of the row maximum (the factored variants re-associate the
+    # quadrature sums: same integrals, a few more ulps than variant 0); north_star's bound is 1e-12
+    tol = 1e-12
     kw = dict(nu=0.001, rho=1.3, p_out=10.0, deltat=0.05, forcing=(0.0, -0.7), neumann_id=neumann,
               use_mass=0 if mode == "steady" else 1, stokes=1 if mode == "stokes" else 0)
     dev.set_params(**kw)
@@ -148,7 +148,7 @@ def test_spmv_parity_and_linearity(pkg):
     lin = dev.spmv(2.0 * x - 0.5 * y)
     assert np.abs(lin - (2.0 * ax - 0.5 * ay)).max() <= 1e-12 * np.abs(lin).max()
     assert np.array_equal(dev.spmv(x), ax)        # run-to-run deterministic
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):       # the SpMV kernels differ only in summation order
+    for variant in (0, 1, 4, 7):       # the SpMV kernels differ only in summation order
         dev.set_tuning(0, variant)
         got = dev.spmv(x)
         assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), variant
@@ -524,7 +524,7 @@ def test_classical_gram_schmidt_option(pkg):
     dev.close()
 
 
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("variant", [0, 4, 5])
 def test_assembly_pattern_wider_than_the_mesh(pkg, variant):
     """Edge case of the write-once assembly: a sparsity pattern with entries NO cell contributes to (a caller may pass
     a wider pattern than make_sparsity_pattern). Those entries must read exactly 0 after every assembly - variant 4 has
