@@ -200,7 +200,8 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * key 1 = 5 (default since round 2): the "fan" scheme - one (owner, cell) pair per lane integrated in a rotated local
  * frame (owner = local vertex 0 / edge 0: all tables are immediates), the lanes of an owner in one warp in fan order,
  * shared-edge contributions combined by warp shuffles, every entry stored exactly once (no read-modify-write, no
- * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically. */
+ * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically.
+ * key 6 = L2 prefetch distances of variant 5 in chunks: records (low 16 bits, default 600), packets (high 16 bits, default 0). */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 
 /* Counters since creation: kernel launches issued by this library, bytes it moved H2D / D2H. */

@@ -544,8 +544,19 @@ static bool rows_come_in_pairs(const nsg_ctx *c, const int64_t *rowptr, const in
 // -------------------------------------------------------------------------------------------------
 // communication helpers
 // -------------------------------------------------------------------------------------------------
-static int halo_exchange(nsg_ctx *c, double *vec) {
+// Ghost import, first half: make my owned values visible to the neighbours that hold them as ghosts.  With the peer
+// mailboxes mapped (nsg_comm_set_peers) this is ONE kernel storing {value, stamp} words straight into the neighbours'
+// inboxes over NVLink; otherwise gather + grouped ncclSend/ncclRecv (which also completes the import).
+static int halo_begin(nsg_ctx *c, double *vec) {
   if (c->n_ranks <= 1 || c->n_neighbors == 0) return NSG_OK;
+  if (c->halo_peer) {
+    if (c->n_send > 0) {
+      k_halo_push<<<grid_for(c->n_send, 256, sm_count()), 256, 0, c->stream>>>(c->n_send, c->send_idx, vec, c->send_dst, c->halo_ctr,
+                                                                              c->halo_ticket);
+      NSG_LAUNCH_CHECK(c);
+    }
+    return NSG_OK;
+  }
   if (c->n_send > 0) {
     k_gather<<<grid_for(c->n_send, 256, 1 << 20), 256, 0, c->stream>>>(c->n_send, c->send_idx, vec, c->send_buf);
     NSG_LAUNCH_CHECK(c);
@@ -562,6 +573,21 @@ static int halo_exchange(nsg_ctx *c, double *vec) {
     NSG_LAUNCH_CHECK(c);
   }
   return NSG_OK;
+}
+// second half (peer path only): wait for the neighbours' words in my own inbox and write my ghost range
+static int halo_end(nsg_ctx *c, double *vec) {
+  if (c->n_ranks <= 1 || c->n_neighbors == 0 || !c->halo_peer) return NSG_OK;
+  if (c->n_recv > 0) {
+    const PeerWord *inbox = reinterpret_cast<const PeerWord *>(c->mailbox + PEER_INBOX_OFFSET);
+    k_halo_wait_scatter<<<grid_for(c->n_recv, 256, sm_count()), 256, 0, c->stream>>>(c->n_recv, c->recv_idx, inbox, vec, c->halo_ctr + 1,
+                                                                                    c->halo_ticket + 1, c->halo_err);
+    NSG_LAUNCH_CHECK(c);
+  }
+  return NSG_OK;
+}
+static int halo_exchange(nsg_ctx *c, double *vec) {
+  NSG_TRY(halo_begin(c, vec));
+  return halo_end(c, vec);
 }
 static int allreduce_scalar(nsg_ctx *c, double *d) {
   if (c->n_ranks <= 1) return NSG_OK;
@@ -601,14 +627,32 @@ static int dev_multi_axpy_norm(nsg_ctx *c, int64_t n, double *w, const double *b
 }
 
 static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t *state) {
-  NSG_TRY(halo_exchange(c, x_with_ghosts));
   if (c->spmv_variant == 7) {
     static int per_sm7 = 0;
     if (!per_sm7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm7, k_spmv_rowpair<true>, SPMV_THREADS, 0);
     const int64_t n_groups = c->n_own_u / 2 + c->n_own_p;
+    // peer-store halo: the sweep over ALL rows runs while the neighbours' values are in flight; the rows with a ghost
+    // column (a list made once, O(sqrt(n)) of them) are then recomputed by the same kernel once the ghosts have landed
+    const bool overlap = c->halo_peer && c->n_ranks > 1 && c->n_neighbors > 0 && c->bgroups != nullptr;
+    if (overlap)
+      NSG_TRY(halo_begin(c, x_with_ghosts));
+    else
+      NSG_TRY(halo_exchange(c, x_with_ghosts));
     k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((n_groups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm7, 1)),
                            SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
-  } else if (c->spmv_variant == 4) {
+    if (overlap) {
+      NSG_LAUNCH_CHECK(c);
+      NSG_TRY(halo_end(c, x_with_ghosts));
+      if (c->n_bgroups > 0)
+        k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((c->n_bgroups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm7, 1)),
+                               SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state,
+                                                             c->bgroups, c->n_bgroups);
+    }
+    NSG_LAUNCH_CHECK(c);
+    return NSG_OK;
+  }
+  NSG_TRY(halo_exchange(c, x_with_ghosts));
+  if (c->spmv_variant == 4) {
     static int per_sm = 0;
     if (!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_vec8u<true>, SPMV_THREADS, 0);
     k_spmv_vec8u<true><<<(unsigned)std::min<int64_t>((c->n_own * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm, 1)),
@@ -662,8 +706,15 @@ static int launch_assembly(nsg_ctx *c) {
       NSG_LAUNCH_CHECK(c);
     }
     if (c->wl_u6.n_chunks > 0) {
-      k_assemble_u6<4><<<(unsigned)c->wl_u6.n_chunks, NPC6, sizeof(double) * (size_t)c->wl_u6.max_stage, c->stream>>>(
-          c->wl_u6, c->vals, c->R, c->cellpk, c->geom8, P);
+      static const int minb = std::getenv("NSG_ASM6_MINB") ? std::atoi(std::getenv("NSG_ASM6_MINB")) : 4;
+      const unsigned grid = (unsigned)c->wl_u6.n_chunks;
+      const size_t smem = sizeof(double) * (size_t)c->wl_u6.max_stage;
+      if (minb == 5)
+        k_assemble_u6<5><<<grid, NPC6, smem, c->stream>>>(c->wl_u6, c->vals, c->R, c->cellpk, c->geom8, P, c->asm_pf_rec, c->asm_pf_pk);
+      else if (minb == 6)
+        k_assemble_u6<6><<<grid, NPC6, smem, c->stream>>>(c->wl_u6, c->vals, c->R, c->cellpk, c->geom8, P, c->asm_pf_rec, c->asm_pf_pk);
+      else
+        k_assemble_u6<4><<<grid, NPC6, smem, c->stream>>>(c->wl_u6, c->vals, c->R, c->cellpk, c->geom8, P, c->asm_pf_rec, c->asm_pf_pk);
       NSG_LAUNCH_CHECK(c);
     }
     if (fork)
@@ -962,6 +1013,7 @@ void nsg_destroy(nsg_ctx *c) {
   for (void *m : c->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
   dev_free(c->mailbox), dev_free(c->ar_seq), dev_free(c->gf_partials);
+  dev_free(c->send_dst), dev_free(c->halo_ctr), dev_free(c->halo_ticket), dev_free(c->halo_err), dev_free(c->bgroups);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
   dev_free(c->spmv_chunk_rows), dev_free(c->diag_pos), dev_free(c->first_idx), dev_free(c->geom), dev_free(c->cellpk), dev_free(c->xy), dev_free(c->cell_vertices), dev_free(c->cell_dofs);
@@ -1036,6 +1088,21 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   c->spmv_n_chunks = (int64_t)chunks.size() - 1;
   NSG_TRY(upload(c, &c->spmv_chunk_rows, chunks.data(), (int64_t)chunks.size()));
   c->have_paired = rows_come_in_pairs(c, jac_rowptr, jac_col);
+  if (c->have_paired && n_ghost_u + n_ghost_p > 0) {  // row groups of SpMV variant 7 that read a ghost column
+    const int64_t n_ug = n_own_u / 2, n_groups = n_ug + n_own_p;
+    std::vector<uint8_t> flag((size_t)n_groups, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < n_groups; ++g) {
+      const int64_t r = g < n_ug ? 2 * g : g + n_ug;
+      // columns ascend: ghosts, if any, are at the end of the row
+      if (jac_rowptr[r + 1] > jac_rowptr[r] && jac_col[jac_rowptr[r + 1] - 1] >= n) flag[g] = 1;
+    }
+    std::vector<int32_t> list;
+    for (int64_t g = 0; g < n_groups; ++g)
+      if (flag[g]) list.push_back((int32_t)g);
+    c->n_bgroups = (int64_t)list.size();
+    NSG_TRY(upload(c, &c->bgroups, list.data(), c->n_bgroups));
+  }
   c->spmv_variant = c->have_paired ? 7 : 4;  // fastest measured (profiles/r01_summary.md); 7 needs the node-pair row structure
   for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
     NSG_TRY(dev_alloc(v, c->stride));
@@ -1088,7 +1155,7 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
     c->fan_ok = ok_u && ok_p && s6u <= 200 * 1024 && s6p <= 200 * 1024;
     if (c->fan_ok) {
       NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
-      NSG_CUDA(cudaFuncSetAttribute(k_assemble_p6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6p, 1024)));
+      NSG_CUDA(cudaFuncSetAttribute(k_assemble_u6<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(s6u, 1024)));
     } else {
       free_worklist(c->wl_u6), free_worklist(c->wl_p6);
       if (c->asm_variant == 5) c->asm_variant = 4;
@@ -1188,10 +1255,24 @@ int nsg_comm_ipc_handle(nsg_ctx *c, void *out64) {
   if (!c || !out64) return fail(NSG_ERR_ARG, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   NSG_CUDA(cudaSetDevice(c->device));
+  if (c->n_ranks > PEER_MAX_RANKS) return fail(NSG_ERR_ARG, "more ranks than mailbox slots");
+  // mailbox = [ all-reduce words | halo table | halo inbox (two parities per ghost) ]; (re)made and zeroed on every call, so
+  // that no stamp of an earlier session can match (the sequence counters restart at 0 in nsg_comm_set_peers)
+  const int64_t bytes = PEER_INBOX_OFFSET + 2 * 16 * std::max<int64_t>(c->n_recv, 1);
+  if (c->mailbox && c->mailbox_bytes < bytes) dev_free(c->mailbox);
   if (!c->mailbox) {
-    NSG_TRY(dev_alloc(&c->mailbox, 2 * PEER_MAX_RANKS));
-    NSG_CUDA(cudaMemset(c->mailbox, 0, sizeof(PeerSlot) * 2 * PEER_MAX_RANKS));
+    NSG_TRY(dev_alloc(&c->mailbox, bytes));
+    c->mailbox_bytes = bytes;
   }
+  NSG_CUDA(cudaMemset(c->mailbox, 0, (size_t)c->mailbox_bytes));
+  PeerHaloTable tab;
+  for (int q = 0; q < PEER_MAX_RANKS; ++q) tab.recv_off[q] = -1, tab.recv_cnt[q] = 0;
+  for (int k = 0; k < c->n_neighbors; ++k) {
+    const int q = c->neighbors[k];
+    if (q < 0 || q >= PEER_MAX_RANKS) return fail(NSG_ERR_ARG, "neighbour rank out of range");
+    tab.recv_off[q] = c->recv_ptr[k], tab.recv_cnt[q] = c->recv_ptr[k + 1] - c->recv_ptr[k];
+  }
+  NSG_CUDA(cudaMemcpy(c->mailbox + PEER_AR_WORDS * 16, &tab, sizeof tab, cudaMemcpyHostToDevice));
   cudaIpcMemHandle_t h;
   NSG_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
   std::memcpy(out64, &h, sizeof h);
@@ -1206,23 +1287,53 @@ int nsg_comm_set_peers(nsg_ctx *c, const void *handles) {
   NSG_CUDA(cudaSetDevice(c->device));
   PeerComm pc{};
   pc.rank = c->rank;
+  char *base[PEER_MAX_RANKS] = {};
   for (int p = 0; p < c->n_ranks; ++p) {
     if (p == c->rank) {
-      pc.box[p] = c->mailbox;
-      continue;
+      base[p] = c->mailbox;
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char *)handles + 64 * (size_t)p, sizeof h);
+      void *ptr = nullptr;
+      NSG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_mapped[p] = ptr;
+      base[p] = (char *)ptr;
     }
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, (const char *)handles + 64 * (size_t)p, sizeof h);
-    void *ptr = nullptr;
-    NSG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer_mapped[p] = ptr;
-    pc.box[p] = (PeerSlot *)ptr;
+    pc.ar[p] = reinterpret_cast<PeerWord *>(base[p]);
   }
   if (!c->ar_seq) NSG_TRY(dev_alloc(&c->ar_seq, 1));
   NSG_CUDA(cudaMemset(c->ar_seq, 0, sizeof(unsigned long long)));
   pc.seq_ctr = c->ar_seq;
+  // halo over peer stores: where in each neighbour's inbox do my values go? (the neighbour wrote its table before it
+  // exported its handle, i.e. before the host gathered the handles)
+  c->halo_peer = false;
+  if (c->n_neighbors > 0) {
+    std::vector<PeerWord *> dst((size_t)std::max<int64_t>(c->n_send, 1), nullptr);
+    for (int k = 0; k < c->n_neighbors; ++k) {
+      const int q = c->neighbors[k];
+      PeerHaloTable tab;
+      NSG_CUDA(cudaMemcpy(&tab, base[q] + PEER_AR_WORDS * 16, sizeof tab, cudaMemcpyDeviceToHost));
+      const int64_t ns = c->send_ptr[k + 1] - c->send_ptr[k];
+      if (tab.recv_off[c->rank] < 0 || tab.recv_cnt[c->rank] != ns)
+        return fail(NSG_ERR_ARG, "halo plans of two neighbouring ranks do not match");
+      PeerWord *inbox = reinterpret_cast<PeerWord *>(base[q] + PEER_INBOX_OFFSET);
+      for (int64_t j = 0; j < ns; ++j) dst[(size_t)(c->send_ptr[k] + j)] = inbox + 2 * (tab.recv_off[c->rank] + j);
+    }
+    dev_free(c->send_dst);
+    NSG_TRY(upload(c, &c->send_dst, dst.data(), (int64_t)dst.size()));
+    if (!c->halo_ctr) NSG_TRY(dev_alloc(&c->halo_ctr, 2));
+    if (!c->halo_ticket) NSG_TRY(dev_alloc(&c->halo_ticket, 2));
+    if (!c->halo_err) NSG_TRY(dev_alloc(&c->halo_err, 1));
+    NSG_CUDA(cudaMemsetAsync(c->halo_ctr, 0, 16, c->stream));
+    NSG_CUDA(cudaMemsetAsync(c->halo_ticket, 0, 8, c->stream));
+    NSG_CUDA(cudaMemsetAsync(c->halo_err, 0, 4, c->stream));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+    c->halo_peer = !(std::getenv("NSG_NO_PEER_HALO") && std::atoi(std::getenv("NSG_NO_PEER_HALO")) != 0);
+  }
   pc.n_ranks = c->n_ranks;  // switches the reductions to the fused all-reduce
   c->peer = pc;
+  for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
+  c->graphs.clear();
   return NSG_OK;
 }
 
@@ -1230,7 +1341,10 @@ int nsg_comm_release_peers(nsg_ctx *c) {
   if (!c) return fail(NSG_ERR_ARG, "null context");
   NSG_CUDA(cudaSetDevice(c->device));
   NSG_CUDA(cudaStreamSynchronize(c->stream));
-  c->peer.n_ranks = 1;  // reductions go back to NCCL
+  c->peer.n_ranks = 1;  // reductions and the halo exchange go back to NCCL
+  c->halo_peer = false;
+  for (auto &e : c->graphs) cudaGraphExecDestroy(e.exec);
+  c->graphs.clear();
   for (void *&m : c->peer_mapped)
     if (m) {
       cudaIpcCloseMemHandle(m);
@@ -1538,6 +1652,10 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       return NSG_OK;
     case 2:
       c->use_graphs = value != 0;
+      return NSG_OK;
+    case 6:  // L2 prefetch distances of assembly variant 5, in chunks: records (low 16 bits), packets (high 16 bits); 0 = off
+      if (value < 0) return fail(NSG_ERR_ARG, "prefetch distances must be >= 0");
+      c->asm_pf_rec = value & 0xffff, c->asm_pf_pk = (value >> 16) & 0xffff;
       return NSG_OK;
     case 5:
       if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "fused GMRES must be 0 (off), 1 (small systems) or 2 (whenever it fits)");

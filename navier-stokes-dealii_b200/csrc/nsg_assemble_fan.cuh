@@ -34,7 +34,10 @@
 
 namespace nsg {
 
-constexpr int NPC6 = 128;  // lanes (pairs) per CTA
+#ifndef NSG_NPC6
+#define NSG_NPC6 128
+#endif
+constexpr int NPC6 = NSG_NPC6;  // lanes (pairs) per CTA
 constexpr int PK6 = 24;    // doubles per cell packet: [0..11] nodal velocities u_i, [12..23] local residual of the 6 velocity nodes
 constexpr int PK6S = 26;   // row stride of the pre-pass' transposition buffer (208 bytes: 16-byte aligned, conflict-free 128-bit stores)
 
@@ -283,58 +286,45 @@ __device__ __forceinline__ double shfl_d(const double v, const int src) { return
 //   off     [0..5] offsets of the column pairs of the ROTATED local nodes 0..5 in the owner's rows, [6..8] of the
 //           three pressure columns (rotated order), [9] image offset of the owner's first row, [10] row length
 // ChunkInfo: g0,g1 owners; rs, cnt image; pad != 0: the image has entries no lane writes (zero-fill first).
-template <int MINB>
-__global__ void __launch_bounds__(NPC6, MINB)
-k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
-              const double *__restrict__ geom8, const AsmParams P) {
-  extern __shared__ __align__(16) double s_vals[];
-  const int t = threadIdx.x, lane = t & 31;
-  const int64_t b = blockIdx.x;
-  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC6 + t);
-  const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
-  const ChunkInfo ci = wl.chunks[b];
-  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
-  double *s_res = s_vals + cnt;
-  if (ci.pad) {  // the pattern has entries no cell contributes to: they must read zero
-    const int n2 = (cnt + 2 * ng + 1) >> 1;
-    double2 *z = reinterpret_cast<double2 *>(s_vals);
-    for (int i = t; i < n2; i += NPC6) z[i] = make_double2(0.0, 0.0);
-    __syncthreads();
-  }
-  const bool work = (int)ra.x >= 0;
+// what a lane loads for its pair (before the values its neighbours hold are shuffled in)
+struct FanIn {
+  double2 n1, n2, rk;  // grad lambda'_1, grad lambda'_2, the cell's local residual at the owner's node
+  double2 u[6];        // nodal velocities in rotated order; [0], [1], [3] only where no neighbouring lane holds them
+};
+struct FanFlags {
+  int kc, r, i1, i2, partner, pred, rem, gl;
+  bool work, has_partner, head, write_next;
+};
+__device__ __forceinline__ FanFlags fan_flags(const uint4 ra) {
+  FanFlags f;
   const uint32_t kw = ra.y;
-  const int kc = (int)(kw & 7u), partner = (int)((kw >> 3) & 31u), rem = (int)((kw >> 11) & 31u), gl = (int)((kw >> 16) & 255u);
-  const int pred = (int)((kw >> 24) & 31u);
-  const bool has_partner = (kw >> 8) & 1u, head = (kw >> 9) & 1u, write_next = (kw >> 10) & 1u;
-  const int r = kc >= 3 ? kc - 3 : kc;
-  const int i1 = r + 1 >= 3 ? r - 2 : r + 1, i2 = r + 2 >= 3 ? r - 1 : r + 2;
+  f.work = (int)ra.x >= 0;
+  f.kc = (int)(kw & 7u), f.partner = (int)((kw >> 3) & 31u), f.rem = (int)((kw >> 11) & 31u), f.gl = (int)((kw >> 16) & 255u);
+  f.pred = (int)((kw >> 24) & 31u);
+  f.has_partner = (kw >> 8) & 1u, f.head = (kw >> 9) & 1u, f.write_next = (kw >> 10) & 1u;
+  f.r = f.kc >= 3 ? f.kc - 3 : f.kc;
+  f.i1 = f.r + 1 >= 3 ? f.r - 2 : f.r + 1, f.i2 = f.r + 2 >= 3 ? f.r - 1 : f.r + 2;
+  return f;
+}
+
+// Everything after the loads: shuffle in what the neighbouring lanes hold, integrate the owner's two rows of the cell,
+// combine the shared-edge contributions, store every entry of the image once.
+__device__ __forceinline__ void fan_commit_u(const uint4 ra, const uint4 rb, const FanFlags f, const bool edge_owner, FanIn in,
+                                             double *s_vals, double *s_res, const int lane, const AsmParams &P) {
+  const bool work = f.work, head = f.head, write_next = f.write_next, has_partner = f.has_partner;
+  const int partner = f.partner, pred = f.pred, rem = f.rem, gl = f.gl;
   double *row0 = s_vals + (rb.z >> 16), *row1 = row0 + (rb.w & 0xffffu);
   const uint32_t ow[5] = {ra.z, ra.w, rb.x, rb.y, rb.z};
   const bool ns = !P.stokes;
   const double mdt = (P.use_mass && ns) ? P.dt_inv : 0.0, nurho = P.nu * P.rho;
-  // uniform over the warp: the host packs vertex owners and edge owners into different warps (idle padding lanes have no
-  // type of their own and must take the branch of their warp: the shuffles below are full-mask)
-  const bool edge_owner = __any_sync(0xffffffffu, work && kc >= 3);
-  const int64_t cell = work ? (int)ra.x : 0;
-  const double2 *gp = reinterpret_cast<const double2 *>(geom8 + 8 * cell);
-  const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK6 * cell);
-  // ---- loads: everything a neighbouring lane does not hold
-  double2 n1 = make_double2(1.0, 0.0), n2 = make_double2(0.0, 1.0), rk = make_double2(0.0, 0.0);
+  double2 n1 = in.n1, n2 = in.n2, rk = in.rk;
   double2 u[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) u[i] = make_double2(0.0, 0.0);
-  if (work) {
-    n1 = __ldg(gp + i1), n2 = __ldg(gp + i2);
-    u[2] = __ldg(pk + i2), u[4] = __ldg(pk + 3 + i1), u[5] = __ldg(pk + 3 + i2);
-    rk = __ldg(pk + 6 + kc);
-    if (!edge_owner) {
-      if (head) u[0] = __ldg(pk + r);
-      if (write_next) u[1] = __ldg(pk + i1), u[3] = __ldg(pk + 3 + r);  // no predecessor to take them from
-    } else {
-      u[0] = __ldg(pk + r);
-      if (head) u[3] = __ldg(pk + 3 + r);
-      if (!has_partner) u[1] = __ldg(pk + i1);
-    }
+  for (int i = 0; i < 6; ++i) u[i] = in.u[i];
+  if (!work) {
+    n1 = make_double2(1.0, 0.0), n2 = make_double2(0.0, 1.0), rk = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = make_double2(0.0, 0.0);
   }
   const double d = 1.0 / fabs(n1.x * n2.y - n1.y * n2.x);  // |det J| = 1 / |det (grad lambda'_1, grad lambda'_2)|
   if (!edge_owner) {
@@ -445,6 +435,60 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
       }
     }
   }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(NPC6, (MINB * 128) / NPC6)
+k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__ R, const double *__restrict__ cellpk,
+              const double *__restrict__ geom8, const AsmParams P, const int pf_rec, const int pf_pk) {
+  extern __shared__ __align__(16) double s_vals[];
+  const int t = threadIdx.x, lane = t & 31;
+  const int64_t b = blockIdx.x;
+  const uint4 *rp = reinterpret_cast<const uint4 *>(wl.recs + b * NPC6 + t);
+  const uint4 ra = __ldcs(rp), rb = __ldcs(rp + 1);
+  const ChunkInfo ci = wl.chunks[b];
+  // Pull the lines of chunks that will run a little later towards L2: the record of chunk b + pf_rec (one sector per
+  // lane, no register held), and - through the cell id of chunk b + pf_pk's record - its packet and geometry lines.
+  if (pf_rec > 0 && b + pf_rec < wl.n_chunks) pf_l2(wl.recs + (b + pf_rec) * NPC6 + t);
+  int pf_cell = -1;
+  if (pf_pk > 0 && b + pf_pk < wl.n_chunks) pf_cell = __ldg(&wl.recs[(b + pf_pk) * NPC6 + t].cell);
+  const int cnt = ci.cnt, ng = ci.g1 - ci.g0;
+  double *s_res = s_vals + cnt;
+  if (ci.pad) {  // the pattern has entries no cell contributes to: they must read zero
+    const int n2 = (cnt + 2 * ng + 1) >> 1;
+    double2 *z = reinterpret_cast<double2 *>(s_vals);
+    for (int i = t; i < n2; i += NPC6) z[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+  }
+  const FanFlags f = fan_flags(ra);
+  // uniform over the warp: the host packs vertex owners and edge owners into different warps (idle padding lanes have no
+  // type of their own and must take the branch of their warp: the shuffles are full-mask)
+  const bool edge_owner = __any_sync(0xffffffffu, f.work && f.kc >= 3);
+  const int64_t cell = f.work ? (int)ra.x : 0;
+  const double2 *gp = reinterpret_cast<const double2 *>(geom8 + 8 * cell);
+  const double2 *pk = reinterpret_cast<const double2 *>(cellpk + PK6 * cell);
+  FanIn in;
+  in.n1 = in.n2 = in.rk = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) in.u[i] = make_double2(0.0, 0.0);
+  if (f.work) {  // everything a neighbouring lane does not hold
+    in.n1 = __ldg(gp + f.i1), in.n2 = __ldg(gp + f.i2);
+    in.u[2] = __ldg(pk + f.i2), in.u[4] = __ldg(pk + 3 + f.i1), in.u[5] = __ldg(pk + 3 + f.i2);
+    in.rk = __ldg(pk + 6 + f.kc);
+    if (!edge_owner) {
+      if (f.head) in.u[0] = __ldg(pk + f.r);
+      if (f.write_next) in.u[1] = __ldg(pk + f.i1), in.u[3] = __ldg(pk + 3 + f.r);  // no predecessor to take them from
+    } else {
+      in.u[0] = __ldg(pk + f.r);
+      if (f.head) in.u[3] = __ldg(pk + 3 + f.r);
+      if (!f.has_partner) in.u[1] = __ldg(pk + f.i1);
+    }
+  }
+  if (pf_cell >= 0) {
+    const char *q = reinterpret_cast<const char *>(cellpk + PK6 * (int64_t)pf_cell);
+    pf_l2(q), pf_l2(q + 128), pf_l2(geom8 + 8 * (int64_t)pf_cell);
+  }
+  fan_commit_u(ra, rb, f, edge_owner, in, s_vals, s_res, lane, P);
   __syncthreads();
   double *out = vals + ci.rs;
   if (((ci.rs | (int64_t)cnt) & 1) == 0) {
@@ -455,11 +499,19 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
   for (int i = t; i < 2 * ng; i += NPC6) R[2 * (int64_t)ci.g0 + i] = s_res[i];
 }
 
+// (A persistent, software-pipelined form of this kernel - next chunk's values copied into lane-private shared-memory
+//  slots by cp.async while the current chunk is integrated, records and headers one and two chunks ahead in registers,
+//  two image buffers so that the TMA write-out of chunk i overlaps chunk i+1 - was built and measured in round 2:
+//  bitwise the same result, long_scoreboard stalls 4.3 -> 1.2 per issue, but the SAME time (0.964 vs 0.957 ms at
+//  1.65 M cells, 10.93 vs 10.78 ms at 18.9 M): with ~1050 issued instructions per warp and chunk, two thirds of them
+//  shuffles, selects and address arithmetic, the kernel is bound by instruction issue at 12-16 warps per SM, not by
+//  the loads.  It is in the git history (commit "pipelined u7"); profiles/r02_summary.md has the numbers.)
+
 // ---- pressure rows (B, the structurally present zero p-p block, pressure mass): vertex fans only --------------
 // Record as above; off[0..5] = column pairs of the rotated P2 nodes in the Jacobian row, off[6..8] = the three
 // pressure columns in the pressure-mass row, off[9] = image offset of the Jacobian row, off[10] = offset of the
 // pressure-mass row in the mass image.  The p-p block of the Jacobian is never written: the image is zero-filled.
-__global__ void __launch_bounds__(NPC6, 6)
+__global__ void __launch_bounds__(NPC6, (6 * 128) / NPC6)
 k_assemble_p6(const WorkList wl, int64_t n_own_u, double *__restrict__ vals, double *__restrict__ pm_vals, double *__restrict__ R,
               const double *__restrict__ geom8, const AsmParams P) {
   extern __shared__ __align__(16) double s_mem[];

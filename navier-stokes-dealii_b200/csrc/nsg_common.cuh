@@ -208,6 +208,7 @@ struct nsg_ctx {
   nsg::WorkList wl_u, wl_p;
   nsg::WorkList wl_u5, wl_p5;  // assembly variant 4: one pair per lane, lanes sorted by (round, cell)
   nsg::WorkList wl_u6, wl_p6;  // assembly variant 5 ("fan"): the lanes of an owner in one warp, every entry stored once
+  int asm_pf_rec = 600, asm_pf_pk = 0;  // variant 5: L2 prefetch distances in chunks (tuning key 6; measured: records 600 ahead -3 %)
   bool fan_ok = false;         // the mesh is an oriented manifold triangulation the fan scheme can serve
   // Neumann: boundary nodes -> faces
   int64_t n_bnodes = 0;

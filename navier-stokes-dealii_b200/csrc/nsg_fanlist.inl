@@ -262,6 +262,9 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
     // an entry of the pattern no cell contributes to (a pattern wider than the mesh implies) must still be written: zero-fill
     // (pressure chunks are always zero-filled: the p-p block of the Jacobian is structurally present and never written)
     if (kind == 0) ci.pad = (n_touched == img && owners_with_cells == ci.g1 - ci.g0) ? 0 : 1;
+    // the first 16 bytes of the header carry what the pipelined kernel needs at the end of an iteration: g0, g1, image
+    // entries, zero-fill flag
+    ci.n_threads = ci.cnt, ci.max_slots = (int32_t)ci.pad;
     const int64_t smem = kind == 0 ? (int64_t)ci.cnt + 2 * (ci.g1 - ci.g0) + 2 : (int64_t)ci.cnt + ci.mcnt + 2;
     max_smem = std::max(max_smem, smem);
   }

@@ -131,7 +131,9 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
     return !(nv > 10. * ns * std::sqrt(std::numeric_limits<double>::epsilon()));
   };
   // run `body` either directly or as a cached graph (captured on first use)
-  const bool use_graphs = lazy && c->use_graphs && c->n_ranks == 1;
+  // graphs need launch segments made of kernels only: one rank, or all inter-rank traffic in peer-memory kernels
+  // (fused all-reduce + peer-store halo; their sequence counters live on the device, so a replay stays in step)
+  const bool use_graphs = lazy && c->use_graphs && (c->n_ranks == 1 || (c->halo_peer && c->peer.n_ranks > 1));
   auto run_segment = [&](int seg, const std::function<int()> &body) -> int {
     if (!use_graphs || seg < 0) return body();
     const GraphKey key{seg, n_tmp, n, o, x, b, basis, hist};

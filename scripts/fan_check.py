@@ -59,14 +59,16 @@ ms = dev.time_kernel(5, 3)
 sms = 148
 print(f"FP64 pipe micro-benchmark: {ms:.3f} ms per launch -> {sms * 67108864 * 2 / ms / 1e9:.1f} TFLOP/s (if {sms} SMs)", flush=True)
 ref = None
-for variant, stage, conc in ((4, 0, 1), (5, 0, 1), (5, 0, 0)):
+for variant, stage, conc in ((4, 0, 1), (5, 0, 1), (5, 0, 0), (5, 600, 1), (5, 1200, 1), (5, 2400, 1), (5, 1200 | (300 << 16), 1),
+                            (5, 1200 | (600 << 16), 1), (5, 2400 | (600 << 16), 1), (5, 2400 | (1200 << 16), 1), (5, 4800 | (1200 << 16), 1)):
     os.environ["NSG_ASM_CONCURRENT"] = str(conc)
     dev.set_tuning(1, variant)
+    dev.set_tuning(6, stage)
     dev.time_kernel(0, 3)
     ms = dev.time_kernel(0, 10)
     J, R = np.concatenate([dev.get_matrix_values(), dev.get_pm_values()]), dev.get_residual()
     if ref is None:
         ref = (J, R)
     ej = np.abs(J - ref[0]).max() / np.abs(ref[0]).max(); er = np.abs(R - ref[1]).max() / np.abs(ref[1]).max()
-    print(f"variant {variant} stage {stage} concurrent {conc}: {ms:8.3f} ms  {d.n / ms / 1e3:9.1f} MDoF/s   |dJ| {ej:.2e} |dR| {er:.2e}", flush=True)
+    print(f"variant {variant} prefetch rec {stage & 0xffff} pk {stage >> 16} concurrent {conc}: {ms:8.3f} ms  {d.n / ms / 1e3:9.1f} MDoF/s   |dJ| {ej:.2e} |dR| {er:.2e}", flush=True)
 dev.close()
