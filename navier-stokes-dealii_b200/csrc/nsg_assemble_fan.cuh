@@ -505,7 +505,7 @@ k_assemble_u6(const WorkList wl, double *__restrict__ vals, double *__restrict__
 //  bitwise the same result, long_scoreboard stalls 4.3 -> 1.2 per issue, but the SAME time (0.964 vs 0.957 ms at
 //  1.65 M cells, 10.93 vs 10.78 ms at 18.9 M): with ~1050 issued instructions per warp and chunk, two thirds of them
 //  shuffles, selects and address arithmetic, the kernel is bound by instruction issue at 12-16 warps per SM, not by
-//  the loads.  It is in the git history (commit "pipelined u7"); profiles/r02_summary.md has the numbers.)
+//  the loads.  It was not kept; profiles/r02_summary.md has the numbers.)
 
 // ---- pressure rows (B, the structurally present zero p-p block, pressure mass): vertex fans only --------------
 // Record as above; off[0..5] = column pairs of the rotated P2 nodes in the Jacobian row, off[6..8] = the three
