@@ -105,8 +105,12 @@ k_cell_packets6(int64_t T, const double *__restrict__ geom8, const int32_t *__re
 #pragma unroll
       for (int l = 0; l < 6; ++l) {
         dof[l] = __ldg(cd + uidx(l));
-        const double2 v = *reinterpret_cast<const double2 *>(sol + dof[l]);  // velocity pairs are 16-byte aligned (even dof)
-        u[l][0] = v.x, u[l][1] = v.y;
+        if ((dof[l] & 1) == 0) {  // owned velocity pairs start at an even index; ghost pairs need not (they follow the owned p)
+          const double2 v = *reinterpret_cast<const double2 *>(sol + dof[l]);
+          u[l][0] = v.x, u[l][1] = v.y;
+        } else {
+          u[l][0] = sol[dof[l]], u[l][1] = sol[dof[l] + 1];
+        }
       }
 #pragma unroll
       for (int m = 0; m < 3; ++m) pr[m] = sol[__ldg(cd + 3 * m + 2)];
@@ -156,9 +160,12 @@ k_cell_packets6(int64_t T, const double *__restrict__ geom8, const int32_t *__re
       if (P.use_mass) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
-          const double2 v = *reinterpret_cast<const double2 *>(sol_old + dof[l]);
-          du[l][0] = u[l][0] - v.x;
-          du[l][1] = u[l][1] - v.y;
+          if ((dof[l] & 1) == 0) {
+            const double2 v = *reinterpret_cast<const double2 *>(sol_old + dof[l]);
+            du[l][0] = u[l][0] - v.x, du[l][1] = u[l][1] - v.y;
+          } else {
+            du[l][0] = u[l][0] - sol_old[dof[l]], du[l][1] = u[l][1] - sol_old[dof[l] + 1];
+          }
         }
       }
 #pragma unroll

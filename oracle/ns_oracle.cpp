@@ -296,29 +296,35 @@ void assemble(Ctx &c) {
 // `sol` is delta_owned (Newton) or solution (Stokes).
 void apply_dirichlet(Ctx &c, int64_t n, const int32_t *dofs, const double *vals, std::vector<double> &sol) {
   for (int block = 0; block < 2; ++block) {
-    const int64_t r0 = block == 0 ? 0 : c.n_u, r1 = block == 0 ? c.n_u : c.N;
-    bool any = false;
-    for (int64_t k = 0; k < n; ++k) any |= (dofs[k] >= r0 && dofs[k] < r1);
-    if (!any) continue;
-    double first_nz = 1;
-    for (int64_t i = r0; i < r1; ++i) {
-      const int64_t p = find_col(c, c.rowptr, c.col, i, (int32_t)i);
-      if (p >= 0 && c.J[p] != 0) {
-        first_nz = std::fabs(c.J[p]);
-        break;
+    // "local row range" of a rank: with virtual ranks (orc_set_block_jacobi, the P > 1 comparisons) every rank takes d
+    // from ITS rows of the block, as apply_boundary_values does on each MPI rank (d is rank-local)
+    const std::vector<int64_t> &off = block == 0 ? c.u_off : c.p_off;
+    const int64_t base = block == 0 ? 0 : c.n_u;
+    for (size_t vr = 0; vr + 1 < off.size(); ++vr) {
+      const int64_t r0 = base + off[vr], r1 = base + off[vr + 1];
+      bool any = false;
+      for (int64_t k = 0; k < n; ++k) any |= (dofs[k] >= r0 && dofs[k] < r1);
+      if (!any) continue;
+      double first_nz = 1;
+      for (int64_t i = r0; i < r1; ++i) {
+        const int64_t p = find_col(c, c.rowptr, c.col, i, (int32_t)i);
+        if (p >= 0 && c.J[p] != 0) {
+          first_nz = std::fabs(c.J[p]);
+          break;
+        }
       }
-    }
-    for (int64_t k = 0; k < n; ++k) {
-      const int64_t i = dofs[k];
-      if (i < r0 || i >= r1) continue;
-      const int64_t pd = find_col(c, c.rowptr, c.col, i, (int32_t)i);
-      for (int64_t p = c.rowptr[i]; p < c.rowptr[i + 1]; ++p)
-        if (p != pd) c.J[p] = 0;  // clears the row in the diagonal and the off-diagonal blocks
-      double diag = first_nz;
-      if (c.prm.dirichlet_diag == 1 && pd >= 0 && c.J[pd] != 0) diag = c.J[pd];
-      if (pd >= 0) c.J[pd] = diag;
-      sol[i] = vals[k];
-      c.R[i] = vals[k] * diag;
+      for (int64_t k = 0; k < n; ++k) {
+        const int64_t i = dofs[k];
+        if (i < r0 || i >= r1) continue;
+        const int64_t pd = find_col(c, c.rowptr, c.col, i, (int32_t)i);
+        for (int64_t p = c.rowptr[i]; p < c.rowptr[i + 1]; ++p)
+          if (p != pd) c.J[p] = 0;  // clears the row in the diagonal and the off-diagonal blocks
+        double diag = first_nz;
+        if (c.prm.dirichlet_diag == 1 && pd >= 0 && c.J[pd] != 0) diag = c.J[pd];
+        if (pd >= 0) c.J[pd] = diag;
+        sol[i] = vals[k];
+        c.R[i] = vals[k] * diag;
+      }
     }
   }
 }

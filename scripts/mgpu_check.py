@@ -46,6 +46,11 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
     g.xy, g.cell_vertices, g.cell_dofs = m.xy.reshape(-1).copy(), m.cells.reshape(-1).copy(), d.cell_dofs.reshape(-1).copy()
     g.bface_cell, g.bface_face, g.bface_tag = m.boundary_faces()
     o = Oracle(g)
+    # per-rank quantities of the reference (the Dirichlet diagonal d of apply_boundary_values, the ILU(0) blocks) are
+    # taken rank by rank in the oracle too: virtual ranks = the owned ranges of the partition
+    u_off = np.concatenate([[0], np.cumsum(d.part_n_u)])
+    p_off = np.concatenate([[0], np.cumsum(d.part_n_p)])
+    o.set_block_jacobi(u_off, p_off)
 
     sol = analytic_state(d, scale)
     for obj, s in ((dev, sol[own]), (o, sol)):
@@ -92,10 +97,7 @@ def run_case(rank, world, local, uid, name, levels, calls, inlet, params, scale,
     check("GMRES history (first cycle)", h1[:k], h2[:k], 1e-9, "gmres")
     if rd[0] == ro[0] and rd[0] < 400:
         check("delta", dev.get_delta(), o.get_delta()[own], 1e-6, "gmres")
-    # block preconditioners: per-rank ILU(0) == block-Jacobi ILU(0) in the oracle
-    u_off = np.concatenate([[0], np.cumsum(d.part_n_u)])
-    p_off = np.concatenate([[0], np.cumsum(d.part_n_p)])
-    o.set_block_jacobi(u_off, p_off)
+    # block preconditioners: per-rank ILU(0) == block-Jacobi ILU(0) in the oracle (virtual ranks set above)
     for precond in preconds:
         dev.set_delta(np.zeros(part.n_own))
         o.set_delta(np.zeros(d.n))
