@@ -644,9 +644,8 @@ static int dev_spmv(nsg_ctx *c, double *x_with_ghosts, double *y, const int32_t 
       NSG_LAUNCH_CHECK(c);
       NSG_TRY(halo_end(c, x_with_ghosts));
       if (c->n_bgroups > 0)
-        k_spmv_rowpair<true><<<(unsigned)std::min<int64_t>((c->n_bgroups * 8 + SPMV_THREADS - 1) / SPMV_THREADS, (int64_t)sm_count() * std::max(per_sm7, 1)),
-                               SPMV_THREADS, 0, c->stream>>>(c->n_own_u / 2, c->n_own, c->rowptr, c->col, c->vals, x_with_ghosts, y, state,
-                                                             c->bgroups, c->n_bgroups);
+        k_spmv_rowpair_list<<<(unsigned)((c->n_bgroups * 8 + SPMV_THREADS - 1) / SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
+            c->n_bgroups, c->bgroups, c->n_own_u / 2, c->rowptr, c->col, c->vals, x_with_ghosts, y, state);
     }
     NSG_LAUNCH_CHECK(c);
     return NSG_OK;
@@ -901,17 +900,26 @@ namespace nsg {
 static bool gmres_fused_applicable(const nsg_ctx *c, int32_t precond) {
   if (c->gmres_fused == 0 || precond != NSG_PRECOND_IDENTITY || c->n_ranks != 1 || c->orthogonalization != 0) return false;
   if (c->n_own <= 0) return false;
-  const int64_t limit = c->gmres_fused == 2 ? (int64_t)148 * GF_THREADS * GF_MAX_EPT : c->gmres_fused_max_n;
-  return c->n_own <= std::min<int64_t>(limit, (int64_t)148 * GF_THREADS * GF_MAX_EPT);
+  // one CTA per SM, all co-resident (cooperative launch): the SM count comes from the device (a MIG/MPS slice has fewer
+  // than 148), and without cooperative-launch support the multi-kernel solver runs instead
+  static int coop = -1;
+  if (coop < 0) {
+    int v = 0;
+    coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, c->device) == cudaSuccess && v) ? 1 : 0;
+  }
+  if (!coop) return false;
+  const int64_t cap = (int64_t)std::min(sm_count(), GF_MAX_GRID) * GF_THREADS * GF_MAX_EPT;
+  const int64_t limit = c->gmres_fused == 2 ? cap : c->gmres_fused_max_n;
+  return c->n_own <= std::min<int64_t>(limit, cap);
 }
 static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int n_tmp, int hist_cap, GmresResult *out) {
   int64_t n = c->n_own;
-  const int grid = (int)std::min<int64_t>(148, (n + GF_THREADS - 1) / GF_THREADS);
+  const int grid = (int)std::min<int64_t>(std::min(sm_count(), GF_MAX_GRID), (n + GF_THREADS - 1) / GF_THREADS);
   const int64_t T = (int64_t)grid * GF_THREADS;
   const int ept = (int)((n + T - 1) / T);
-  if (!c->gf_partials) {  // [2][148] {value, epoch} words + the epoch counter, zeroed once
-    NSG_TRY(dev_alloc(&c->gf_partials, 2 * (2 * 148 + 1) + 8));
-    NSG_CUDA(cudaMemsetAsync(c->gf_partials, 0, sizeof(double) * (2 * (2 * 148 + 1) + 8), c->stream));
+  if (!c->gf_partials) {  // [2][GF_MAX_GRID] {value, epoch} words + the broadcast word + the epoch counters, zeroed once
+    NSG_TRY(dev_alloc(&c->gf_partials, 2 * (2 * GF_MAX_GRID + 1) + 8));
+    NSG_CUDA(cudaMemsetAsync(c->gf_partials, 0, sizeof(double) * (2 * (2 * GF_MAX_GRID + 1) + 8), c->stream));
   }
   // tolerance = rel_tol * ||R|| and the scalar state, exactly as gmres_core sets them up
   NSG_TRY(dev_dot(c, n, c->R, c->R, &c->ctl->nrm2, nullptr));
@@ -922,7 +930,7 @@ static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int
   const double *vals = c->vals, *b = c->R;
   double *basis = c->basis, *hist = c->hist;
   ulonglong2 *slots = reinterpret_cast<ulonglong2 *>(c->gf_partials);
-  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->gf_partials + 2 * (2 * 148 + 1));
+  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->gf_partials + 2 * (2 * GF_MAX_GRID + 1));
   int64_t S = c->stride;
   GmresCtl *ctl = c->ctl;
   void *args[] = {&n, &rowptr, &col, &vals, &x, &b, &basis, &S, &n_tmp, &ctl, &hist, &slots, &epoch_ctr};
@@ -932,7 +940,7 @@ static int gmres_fused(nsg_ctx *c, double *x, double rel_tol, int max_steps, int
                             : (const void *)k_gmres_solve_fused<8>;
   int per_sm = 0;
   NSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, GF_THREADS, 0));
-  if (per_sm < 1) return fail(NSG_ERR_CUDA, "the fused GMRES kernel does not fit an SM");
+  if (per_sm < 1 || grid > per_sm * sm_count()) return fail(NSG_ERR_CUDA, "the fused GMRES kernel cannot be co-resident on this device");
   NSG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GF_THREADS), args, 0, c->stream));
   c->launches++;
   NSG_TRY(read_ctl_header(c, c->ctl, c->h_ctl));

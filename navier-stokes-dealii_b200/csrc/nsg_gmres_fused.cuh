@@ -19,6 +19,8 @@
 #include "nsg_linalg.cuh"
 
 namespace nsg {
+constexpr int GF_MAX_GRID = 256;  // capacity of the partial-slot array: one CTA per SM, SM count taken from the device
+
 namespace cg = cooperative_groups;
 
 constexpr int GF_THREADS = 256;
@@ -121,7 +123,7 @@ k_gmres_solve_fused(int64_t n, const int64_t *__restrict__ rowptr, const int32_t
   cg::grid_group grid = cg::this_grid();
   __shared__ double s_red[2 * (GF_THREADS / 32 + 1)];
   __shared__ double s_b[2];
-  ulonglong2 *bword = slots + 2 * 148;  // broadcast word at a fixed place behind the (at most 2 x 148) partial slots
+  ulonglong2 *bword = slots + 2 * GF_MAX_GRID;  // broadcast word at a fixed place behind the (at most 2 x GF_MAX_GRID) partial slots
   const int64_t T = (int64_t)gridDim.x * GF_THREADS, tid = (int64_t)blockIdx.x * GF_THREADS + threadIdx.x;
   const int m = n_tmp - 2;
   // both counters continue where the previous solve stopped: stale stamps never match.  Reductions and broadcasts

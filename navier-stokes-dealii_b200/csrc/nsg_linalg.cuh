@@ -17,7 +17,7 @@ namespace nsg {
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_CAP = 4096;  // non-zeros per chunk (32 KB of products)
 constexpr int RED_THREADS = 256;
-constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
+constexpr int RED_MAX_BLOCKS = 1184;  // capacity of the partials arrays (8 CTAs on each of a B200's 148 SMs)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // CTAs are dispatched roughly in index order: a CTA warms L2 with the row extents of the CTA that will
@@ -158,27 +158,21 @@ template <bool PERSISTENT>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-               const int32_t *__restrict__ state, const int32_t *__restrict__ list = nullptr, int64_t n_list = 0) {
-  // list != nullptr: only the groups list[0..n_list) (the rows with a ghost column, recomputed after the halo exchange
-  // while the full sweep ran beside it); same lanes, same summation order per row as the full sweep
+               const int32_t *__restrict__ state) {
   if (state && *state != 0) return;
   const int l8 = threadIdx.x & 7;
-  const int64_t n_all = n_ugroups + (n_rows - 2 * n_ugroups);
-  const int64_t n_groups = list ? n_list : n_all;
+  const int64_t n_groups = n_ugroups + (n_rows - 2 * n_ugroups);
   const int64_t G = PERSISTENT ? ((int64_t)gridDim.x * SPMV_THREADS) >> 3 : 0;
-  int64_t gi = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
-  int64_t g = gi < n_groups ? (list ? (int64_t)list[gi] : gi) : n_all;
+  int64_t g = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
   int64_t s = 0, e = 0;
-  if (gi < n_groups) {
+  if (g < n_groups) {
     const int64_t r = g < n_ugroups ? 2 * g : g + n_ugroups;
     s = rowptr[r], e = rowptr[r + 1];
   }
   while (true) {
     int64_t sn = 0, en = 0;
-    const int64_t gin = gi + G;
-    int64_t gn = n_all;
-    if (PERSISTENT && gin < n_groups) {
-      gn = list ? (int64_t)list[gin] : gin;
+    const int64_t gn = g + G;
+    if (PERSISTENT && gn < n_groups) {
       const int64_t r = gn < n_ugroups ? 2 * gn : gn + n_ugroups;
       sn = rowptr[r], en = rowptr[r + 1];
     }
@@ -213,7 +207,7 @@ k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ ro
     acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
     acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-    if (gi < n_groups && l8 == 0) {
+    if (g < n_groups && l8 == 0) {
       if (pair) {
         y[2 * g] = acc0;
         y[2 * g + 1] = acc1;
@@ -222,9 +216,68 @@ k_spmv_rowpair(int64_t n_ugroups, int64_t n_rows, const int64_t *__restrict__ ro
       }
     }
     if (!PERSISTENT) break;
-    if (__all_sync(0xffffffffu, gin >= n_groups)) break;
-    gi = gin, g = gn, s = sn, e = en;
-    if (gi >= n_groups) s = e = 0;
+    if (__all_sync(0xffffffffu, gn >= n_groups)) break;
+    g = gn, s = sn, e = en;
+    if (g >= n_groups) s = e = 0;
+  }
+}
+
+// The same rows for a LIST of groups only (the rows with a ghost column, recomputed once the halo exchange has landed
+// while the full sweep ran beside it): one group per 8 lanes, same lane mapping and summation order per row as above,
+// so the recomputed entries are bitwise what a single sweep after the exchange would give.  A separate kernel: as a
+// run-time branch inside k_spmv_rowpair the indirection cost the full sweep 8 registers = one CTA per SM = 14 %.
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_rowpair_list(int64_t n_list, const int32_t *__restrict__ list, int64_t n_ugroups, const int64_t *__restrict__ rowptr,
+                    const int32_t *__restrict__ col, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                    const int32_t *__restrict__ state) {
+  if (state && *state != 0) return;
+  const int l8 = threadIdx.x & 7;
+  const int64_t gi = (blockIdx.x * (int64_t)SPMV_THREADS + threadIdx.x) >> 3;
+  const bool in_list = gi < n_list;
+  const int64_t g = in_list ? (int64_t)list[gi] : 0;
+  const bool pair = g < n_ugroups;
+  int64_t s = 0, e = 0;
+  if (in_list) {
+    const int64_t r = pair ? 2 * g : g + n_ugroups;
+    s = rowptr[r], e = rowptr[r + 1];
+  }
+  const int64_t len = pair ? e - s : 0;
+  double v0[8], v1[8];
+  int32_t c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int64_t p = s + l8 + 8 * k;
+    const bool in = p < e;
+    v0[k] = in ? __ldcs(vals + p) : 0.0;
+    v1[k] = (in && pair) ? __ldcs(vals + p + len) : 0.0;
+    c[k] = in ? __ldcs(col + p) : -1;
+  }
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (c[k] >= 0) {
+      const double xv = __ldg(x + c[k]);
+      acc0 += v0[k] * xv;
+      acc1 += v1[k] * xv;
+    }
+  for (int64_t p = s + l8 + 64; p < e; p += 8) {
+    const double xv = __ldg(x + __ldcs(col + p));
+    acc0 += __ldcs(vals + p) * xv;
+    if (pair) acc1 += __ldcs(vals + p + len) * xv;
+  }
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+  if (in_list && l8 == 0) {
+    if (pair) {
+      y[2 * g] = acc0;
+      y[2 * g + 1] = acc1;
+    } else {
+      y[g + n_ugroups] = acc0;
+    }
   }
 }
 
@@ -427,7 +480,9 @@ k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const doub
 
 // ---- classical Gram-Schmidt sweep (tuning key 3): two passes over the basis instead of k dependent ones ----
 constexpr int CGS_MAXK = 32;
-// out[j] = w . v_j for j < k, one pass over w and the k basis vectors
+// out[j] = w . v_j for j < k, one pass over w and the k basis vectors: (8k + 8) bytes per entry.
+// Two entries per thread and step (128-bit loads), the basis vectors taken in chunks of 8 whose loads are all in flight
+// before the first multiply; 32 accumulators in registers.  n2 = n / 2 pairs; an odd tail entry is added by block 0.
 __global__ void __launch_bounds__(RED_THREADS)
 k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ basis, int64_t stride, int k,
             double *partials /* [CGS_MAXK][gridDim.x] */, unsigned int *ticket, double *out, const int32_t *__restrict__ state,
@@ -436,11 +491,30 @@ k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ 
   double acc[CGS_MAXK];
 #pragma unroll
   for (int j = 0; j < CGS_MAXK; ++j) acc[j] = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
-    const double wi = w[i];
+  const int64_t n2 = n >> 1;
+  const double2 *w2 = reinterpret_cast<const double2 *>(w);
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * RED_THREADS) {
+    const double2 wi = w2[i];
+#pragma unroll
+    for (int j0 = 0; j0 < CGS_MAXK; j0 += 8) {
+      if (j0 < k) {
+        double2 v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          v[jj] = (j0 + jj < k) ? __ldcs(reinterpret_cast<const double2 *>(basis + (int64_t)(j0 + jj) * stride) + i) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          acc[j0 + jj] += wi.x * v[jj].x;
+          acc[j0 + jj] += wi.y * v[jj].y;
+        }
+      }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double wi = w[n - 1];
 #pragma unroll
     for (int j = 0; j < CGS_MAXK; ++j)
-      if (j < k) acc[j] += wi * __ldcs(basis + j * stride + i);
+      if (j < k) acc[j] += wi * basis[(int64_t)j * stride + n - 1];
   }
   __shared__ double s_part[RED_THREADS / 32][CGS_MAXK];
   __shared__ bool s_last;
@@ -464,11 +538,13 @@ k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ 
   __syncthreads();
   if (s_last) {
     __threadfence();
+    // every vector's partials are summed in index order by one warp (8 warps: vectors wid, wid + 8, ...)
     __shared__ double s_tot[CGS_MAXK];
-    if (t < k) {
+    for (int j = wid; j < k; j += RED_THREADS / 32) {
       double v = 0.0;
-      for (unsigned g = 0; g < gridDim.x; ++g) v += __ldcg(partials + (int64_t)t * gridDim.x + g);  // index order
-      s_tot[t] = v;
+      for (unsigned g = lane; g < gridDim.x; g += 32) v += __ldcg(partials + (int64_t)j * gridDim.x + g);
+      v = warp_sum(v);
+      if (lane == 0) s_tot[j] = v;
     }
     __syncthreads();
     if (pc.n_ranks > 1) peer_allreduce_block(pc, s_tot, k);
@@ -476,16 +552,41 @@ k_multi_dot(int64_t n, const double *__restrict__ w, const double *__restrict__ 
     if (t == 0) *ticket = 0u;
   }
 }
-// w -= sum_{j<k} h_j v_j (sequential in j per entry);  out = w . w
+// w -= sum_{j<k} h_j v_j (sequential in j per entry);  out = w . w   - (8k + 16) bytes per entry, same load scheme
 __global__ void __launch_bounds__(RED_THREADS)
 k_multi_axpy_norm(int64_t n, double *__restrict__ w, const double *__restrict__ basis, int64_t stride, const double *__restrict__ h,
                   int k, double *partials, unsigned int *ticket, double *out, const int32_t *__restrict__ state, const PeerComm pc) {
   if (state && *state != 0) return;
+  __shared__ double s_h[CGS_MAXK];
+  if (threadIdx.x < CGS_MAXK) s_h[threadIdx.x] = threadIdx.x < k ? h[threadIdx.x] : 0.0;
+  __syncthreads();
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
-    double a = w[i];
-    for (int j = 0; j < k; ++j) a -= h[j] * __ldcs(basis + j * stride + i);
-    w[i] = a;
+  const int64_t n2 = n >> 1;
+  double2 *w2 = reinterpret_cast<double2 *>(w);
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * RED_THREADS) {
+    double2 a = w2[i];
+#pragma unroll
+    for (int j0 = 0; j0 < CGS_MAXK; j0 += 8) {
+      if (j0 < k) {
+        double2 v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          v[jj] = (j0 + jj < k) ? __ldcs(reinterpret_cast<const double2 *>(basis + (int64_t)(j0 + jj) * stride) + i) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          a.x -= s_h[j0 + jj] * v[jj].x;
+          a.y -= s_h[j0 + jj] * v[jj].y;
+        }
+      }
+    }
+    w2[i] = a;
+    acc += a.x * a.x;
+    acc += a.y * a.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double a = w[n - 1];
+    for (int j = 0; j < k; ++j) a -= s_h[j] * basis[(int64_t)j * stride + n - 1];
+    w[n - 1] = a;
     acc += a * a;
   }
   finish_reduce(acc, partials, ticket, out, pc);

@@ -327,7 +327,7 @@ static int ilu_apply(nsg_ctx *c, CsrBlock &B, double *y, const double *x) {
     ++B.epoch;  // 64-bit stamp: never wraps
     // rows in flight = 4 x CTAs; measured on a 51 842-row block (1 120 levels): 148 CTAs 3.55 ms, 296: 3.64, 592: 3.69,
     // 1 184: 3.93, one CTA per 4 rows: 6.0 (level-scheduled launches: 9.3)
-    static const int sf_grid = std::getenv("NSG_SF_GRID") ? std::max(1, std::atoi(std::getenv("NSG_SF_GRID"))) : 148;
+    static const int sf_grid = std::getenv("NSG_SF_GRID") ? std::max(1, std::atoi(std::getenv("NSG_SF_GRID"))) : sm_count();
     const unsigned grid = (unsigned)std::min<int64_t>((B.n + SF_WARPS - 1) / SF_WARPS, (int64_t)sf_grid);
     const unsigned long long used = (unsigned long long)((B.n + SF_WARPS - 1) / SF_WARPS) + grid;  // every CTA draws one ticket past the end
     k_ilu_solve_sf<false><<<grid, 32 * SF_WARPS, 0, c->stream>>>(B.level_rows, B.n, B.rowptr, B.col, B.diag, B.fval, B.dinv, x, nullptr,
