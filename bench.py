@@ -281,13 +281,19 @@ def main():
         ph = dev.phase_ms()
         return r, its, ph
 
+    e2e_parts = []
+
     def step_e2e(host_sol):
         t0 = time.perf_counter()
         dev.set_solution(host_sol)                 # H2D from pinned host memory: the step's input iterate
+        t1 = time.perf_counter()
         dev.assemble()
+        t2 = time.perf_counter()
         dev.apply_dirichlet(ld, lv)
+        t3 = time.perf_counter()
         r = dev.residual_norm()                    # D2H: the step's result (assembly metric)
         t_asm = time.perf_counter() - t0
+        e2e_parts.append((t1 - t0, t2 - t1, t3 - t2, t0 + t_asm - t3))
         its, res, rc = dev.solve(0, 1e-2, args.gmres_its, 30, 0, check=False)
         delta = dev.get_delta(host_delta)          # D2H into pinned host memory: the Newton increment
         return t_asm, time.perf_counter() - t0, delta
@@ -381,11 +387,18 @@ def main():
     for _ in range(2):
         step_e2e(host_sol)
     barrier()
+    e2e_parts.clear()
     for _ in range(max(2, args.steps // 2)):
         dev.set_delta(zero)
+        if world > 1:
+            dist.barrier()                         # every rank starts its step together (the halo refresh is a rendezvous)
         a, s, _ = step_e2e(host_sol)
         e2e_asm.append(a), e2e_step.append(s)
     barrier()
+    parts_t = torch.tensor(np.mean(np.array(e2e_parts), axis=0), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(parts_t, op=dist.ReduceOp.MAX)
+    e2e_breakdown = [1e3 * float(x) for x in parts_t.cpu()]
     e2e_t = torch.tensor([np.mean(e2e_asm), np.mean(e2e_step)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -406,6 +419,8 @@ def main():
                 "e2e": {"value": N / e2e_asm_s / 1e6, "unit": "MDoF/s",
                         "h2d_bytes_per_step": int(8 * part.n_own + 12 * len(ld)), "d2h_bytes_per_step": 8,
                         "newton_step_ms": 1e3 * e2e_step_s, "newton_step_d2h_bytes": int(8 + 8 * part.n_own),
+                        "breakdown_ms_max_over_ranks": dict(zip(("set_solution_h2d_and_halo", "assemble", "dirichlet",
+                                                                 "residual_norm"), e2e_breakdown)),
                         "what": "value: set_solution(host, pinned) + assemble + Dirichlet + residual norm to host (8 bytes back); "
                                 "newton_step_ms adds GMRES and get_delta(host), whose bytes are newton_step_d2h_bytes"}}
         if not args.no_cpu_baseline and world == 1:
