@@ -40,7 +40,7 @@ def analytic_state(xy, n_u):
     return sol
 
 
-def build_problem(pkg, mesh, levels, world, rank):
+def build_problem(pkg, mesh, levels, world, rank, patterns=True):
     fn, ent, geo, calls, neumann, inlet = MESHES[mesh]
     m = pkg.Mesh.read_msh(os.path.join(ROOT, "tests", "golden", fn), ent)
     if geo:
@@ -49,7 +49,7 @@ def build_problem(pkg, mesh, levels, world, rank):
         m = m.refine(levels)
     cp = m.partition_rcb(world) if world > 1 else None
     d = pkg.Dofs(m, world, cp)
-    part = pkg.Part(d, rank)
+    part = pkg.Part(d, rank, patterns=patterns)   # patterns=False: built on the device
     gd, gv = d.dirichlet_values(calls, dict(time_factor=1.0, **inlet))
     ld, lv = part.localize_dirichlet(gd, gv)
     xy = d.support_points()
@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--nu", type=float, default=0.001, help="viscosity (reference hpp:703; configs[4]: 5e-4 = Re 200)")
     ap.add_argument("--deltat", type=float, default=0.05, help="time step (reference main.cpp:13; configs[4]: small)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-patterns", action="store_true", help="build the sparsity patterns on the host (libnst) and upload them")
     args = ap.parse_args()
     if args.cpu_level is None:
         args.cpu_level = {"cmy": 2, "mesh2d": 4}[args.mesh]
@@ -252,7 +253,8 @@ def main():
     pkg = importlib.import_module("navier-stokes-dealii_b200")
 
     t_setup = time.perf_counter()
-    m, d, part, (ld, lv), neumann, sol = build_problem(pkg, args.mesh, args.levels, world, rank)
+    m, d, part, (ld, lv), neumann, sol = build_problem(pkg, args.mesh, args.levels, world, rank, patterns=args.host_patterns)
+    t_topology = time.perf_counter() - t_setup
     dev = pkg.DeviceProblem(part, local)
     if world > 1:
         uid = [pkg.DeviceProblem.comm_unique_id() if rank == 0 else None]
@@ -332,7 +334,7 @@ def main():
     # roofline of the dominant kernel (SpMV: G launches per step) + the other two hot kernels
     hbm, hbm_src = peaks()
     reps = 10
-    n_rows, nnz, n_cols = part.n_own, part.nnz_jac, part.n_loc
+    n_rows, nnz, n_cols = part.n_own, dev.nnz, part.n_loc
     spmv_ms = dev.time_kernel(1, reps)
     spmv_bytes = 12 * nnz + 8 * n_cols + 8 * n_rows + 8 * (n_rows + 1)
     aad_ms = dev.time_kernel(2, reps)
@@ -340,7 +342,7 @@ def main():
     mgs_passes = sum(min(i % 28, 27) + 1 for i in range(g_its))   # add_and_dot launches of the MGS sweeps
     asm_k_ms = dev.time_kernel(0, reps)
     fp64_tf = torch.cuda.get_device_properties(local).multi_processor_count * 67108864 * 2 / dev.time_kernel(5, 3) / 1e9
-    asm_bytes = (8 * nnz + 8 * part.nnz_pm + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
+    asm_bytes = (8 * nnz + 8 * dev.pm_nnz + 8 * n_rows + part.n_cells * (15 * 4 + 5 * 8) + 2 * 8 * n_cols)
     traffic = None   # dram__bytes_read+write per launch of the same kernel on the same workload, from profiles/
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tpath):
@@ -411,6 +413,7 @@ def main():
                 "host_binding": numa,
                 "assembly_ms": t_asm_ms, "gmres_ms_per_newton_step": t_sol_ms, "gmres_its": int(its_seen[-1]),
                 "gmres_ms_per_iteration": t_sol_ms / max(1, its_seen[-1]), "setup_s": t_setup,
+                "setup_topology_s": t_topology,
                 "gmres_ms_per_newton_step_classical_gs": cgs_ms,
                 "krylov_allreduce": ("fused into the reduction kernels (NVLink peer mailboxes)" if world > 1 and peer_ar
                                      else "nccl" if world > 1 else None),

@@ -58,6 +58,16 @@ int nsg_set_pattern(nsg_ctx *ctx, int64_t n_own_u, int64_t n_own_p, int64_t n_gh
                     const int64_t *jac_rowptr, const int32_t *jac_col, const int64_t *pm_rowptr,
                     const int32_t *pm_col);
 
+/* SURVEY 8f N4 - the same two patterns (DoFTools::make_sparsity_pattern, cpp:107-110 full coupling; cpp:143-158 p-p only)
+ * built ON THE DEVICE from the cell -> dof table instead of uploaded: bit-identical to the patterns of nst_part_build
+ * (tests/test_gpu_parity.py::test_device_pattern_is_bit_identical), without the host construction, the host copies and the
+ * upload of ~10 GB of column indices at 85 M DoFs. cell_dofs[15*n_cells] as for nsg_set_mesh. Use INSTEAD of
+ * nsg_set_pattern; nsg_get_pattern_sizes / nsg_get_pattern read the result back (sizes; rowptr n_own+1, col nnz). */
+int nsg_set_pattern_from_cells(nsg_ctx *ctx, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p,
+                               int64_t n_cells, const int32_t *cell_dofs);
+int nsg_get_pattern_sizes(nsg_ctx *ctx, int64_t *nnz_jac, int64_t *nnz_pm);
+int nsg_get_pattern(nsg_ctx *ctx, int64_t *jac_rowptr, int32_t *jac_col, int64_t *pm_rowptr, int32_t *pm_col);
+
 /* What the cell loop reads through deal.II (cell->vertex, get_dof_indices, boundary_id;
  * cpp:218-343): vertex coordinates xy[2*n_vertices], cell_vertices[3*n_cells],
  * cell_dofs[15*n_cells] (local ids, FESystem order: 3v+{0,1} u, 3v+2 p, 9+2l+{0,1} u),

@@ -127,6 +127,11 @@ int nst_dofs_support_points(const nst_mesh *m, const nst_dofs *d, double *xy);
  * DoF (owned cells + the part of the ghost layer that is needed), in global order. */
 int nst_part_build(const nst_mesh *m, const nst_dofs *d, int n_parts, const int32_t *cell_part,
                    int rank, nst_part **out);
+/* The same with flags: NST_PART_NO_PATTERNS leaves the two sparsity patterns (cpp:101-158) out - the device builds them
+ * from the cell -> dof table (nsg_set_pattern_from_cells); rowptrs are all zero, nnz_jac = nnz_pm = 0. */
+#define NST_PART_NO_PATTERNS 1
+int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const int32_t *cell_part,
+                      int rank, int flags, nst_part **out);
 void nst_part_free(nst_part *p);
 typedef struct {
   int64_t n_own_u, n_own_p, n_ghost_u, n_ghost_p;

@@ -94,6 +94,7 @@ _NST_SIGS = {
                                        _opt(i32p), _opt(f64p)]),
     "nst_dofs_support_points": (C.c_int, [vp, vp, f64p]),
     "nst_part_build": (C.c_int, [vp, vp, C.c_int, _opt(i32p), C.c_int, C.POINTER(vp)]),
+    "nst_part_build_ex": (C.c_int, [vp, vp, C.c_int, _opt(i32p), C.c_int, C.c_int, C.POINTER(vp)]),
     "nst_part_free": (None, [vp]),
     "nst_part_get_info": (C.c_int, [vp, C.POINTER(PartInfo)]),
     "nst_part_l2g": (C.POINTER(i64), [vp]),
@@ -123,6 +124,9 @@ _NSG_SIGS = {
     "nsg_destroy": (None, [vp]),
     "nsg_set_stream": (C.c_int, [vp, vp]),
     "nsg_set_pattern": (C.c_int, [vp, i64, i64, i64, i64, i64p, i32p, i64p, i32p]),
+    "nsg_set_pattern_from_cells": (C.c_int, [vp, i64, i64, i64, i64, i64, i32p]),
+    "nsg_get_pattern_sizes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "nsg_get_pattern": (C.c_int, [vp, i64p, i32p, i64p, i32p]),
     "nsg_set_mesh": (C.c_int, [vp, i64, i64, f64p, i32p, i32p, i64, i32p, i32p, i32p]),
     "nsg_set_halo": (C.c_int, [vp, i32, i32p, i64p, i32p, i64p, i32p]),
     "nsg_comm_unique_id": (C.c_int, [C.c_char_p]),

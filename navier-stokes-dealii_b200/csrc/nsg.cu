@@ -7,9 +7,11 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <omp.h>
 
 #include "nsg_assemble.cuh"
 #include "nsg_assemble_fan.cuh"
+#include "nsg_pattern.cuh"
 #include "nsg_common.cuh"
 #include "nsg_linalg.cuh"
 
@@ -19,6 +21,22 @@ int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
+
+// NSG_TRACE=1: wall-clock marks of the one-time setup calls on stderr
+struct Trace {
+  bool on;
+  double t0;
+  const char *what;
+  explicit Trace(const char *w) : on(std::getenv("NSG_TRACE") != nullptr), t0(0), what(w) {
+    if (on) t0 = omp_get_wtime();
+  }
+  void mark(const char *label) {
+    if (!on) return;
+    const double t = omp_get_wtime();
+    std::fprintf(stderr, "[nsg trace] %s: %s %.3f s\n", what, label, t - t0);
+    t0 = t;
+  }
+};
 
 template <class T>
 int dev_alloc(T **p, int64_t n) {
@@ -1052,9 +1070,8 @@ int nsg_set_stream(nsg_ctx *c, void *s) {
   return NSG_OK;
 }
 
-int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p,
-                    const int64_t *jac_rowptr, const int32_t *jac_col, const int64_t *pm_rowptr, const int32_t *pm_col) {
-  if (!c || !jac_rowptr || !jac_col || !pm_rowptr || !pm_col) return fail(NSG_ERR_ARG, "null argument");
+// sizes of a pattern call, common to the two ways a pattern can arrive
+static int pattern_sizes(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p) {
   if (n_own_u < 0 || n_own_p < 0 || (n_own_u & 1)) return fail(NSG_ERR_ARG, "n_own_u must be even and sizes non-negative");
   if (c->have_pattern) return fail(NSG_ERR_STATE, "pattern already set (the CSR is fixed for the life of the context)");
   NSG_CUDA(cudaSetDevice(c->device));
@@ -1063,24 +1080,11 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
   c->n_loc = c->n_own + n_ghost_u + n_ghost_p;
   if (c->n_loc >= (int64_t)INT32_MAX) return fail(NSG_ERR_ARG, "local DoF count exceeds 32-bit column indices");
   c->stride = (c->n_loc + 31) / 32 * 32;
+  return NSG_OK;
+}
+// everything after the device CSR (rowptr, col, pm_rowptr, pm_col) and c->h_rowptr / c->h_pm_rowptr exist
+static int finish_pattern(nsg_ctx *c, Trace &tr) {
   const int64_t n = c->n_own;
-  c->nnz = jac_rowptr[n], c->pm_nnz = pm_rowptr[n];
-  for (int64_t i = 0; i < n; ++i)
-    if (jac_rowptr[i + 1] < jac_rowptr[i] || pm_rowptr[i + 1] < pm_rowptr[i]) return fail(NSG_ERR_ARG, "row pointers not monotone");
-  c->h_rowptr.assign(jac_rowptr, jac_rowptr + n + 1);
-  c->h_col.assign(jac_col, jac_col + c->nnz);
-  c->h_pm_rowptr.assign(pm_rowptr, pm_rowptr + n + 1);
-  c->h_pm_col.assign(pm_col, pm_col + c->pm_nnz);
-  // +16 elements of slack: the bulk copies of SpMV variant 5 round their slices up to 16 bytes
-  NSG_TRY(dev_alloc(&c->rowptr, n + 1 + 16));
-  NSG_CUDA(cudaMemsetAsync(c->rowptr, 0, 8 * (size_t)(n + 17), c->stream));
-  NSG_CUDA(cudaMemcpyAsync(c->rowptr, jac_rowptr, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
-  NSG_TRY(dev_alloc(&c->col, c->nnz + 16));
-  NSG_CUDA(cudaMemsetAsync(c->col, 0, 4 * (size_t)(c->nnz + 16), c->stream));
-  NSG_CUDA(cudaMemcpyAsync(c->col, jac_col, 4 * (size_t)c->nnz, cudaMemcpyHostToDevice, c->stream));
-  c->h2d += 8 * (n + 1) + 4 * c->nnz;
-  NSG_TRY(upload(c, &c->pm_rowptr, pm_rowptr, n + 1));
-  NSG_TRY(upload(c, &c->pm_col, pm_col, c->pm_nnz));
   NSG_TRY(dev_alloc(&c->vals, c->nnz + 16));
   NSG_TRY(dev_alloc(&c->pm_vals, c->pm_nnz));
   NSG_CUDA(cudaMemsetAsync(c->vals, 0, 8 * (size_t)std::max<int64_t>(c->nnz, 1), c->stream));
@@ -1092,9 +1096,46 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
     NSG_LAUNCH_CHECK(c);
   }
   std::vector<int32_t> chunks;
-  make_spmv_chunks(jac_rowptr, n, chunks);
+  make_spmv_chunks(c->h_rowptr.data(), n, chunks);
   c->spmv_n_chunks = (int64_t)chunks.size() - 1;
   NSG_TRY(upload(c, &c->spmv_chunk_rows, chunks.data(), (int64_t)chunks.size()));
+  tr.mark("values, diagonal positions, spmv chunks");
+  for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
+    NSG_TRY(dev_alloc(v, c->stride));
+    NSG_CUDA(cudaMemsetAsync(*v, 0, 8 * (size_t)c->stride, c->stream));
+  }
+  NSG_TRY(dev_alloc(&c->work, 8 * c->stride));
+  NSG_CUDA(cudaMemsetAsync(c->work, 0, 8 * 8 * (size_t)c->stride, c->stream));
+  NSG_CUDA(cudaStreamSynchronize(c->stream));
+  tr.mark("vectors + sync");
+  c->have_pattern = true;
+  return NSG_OK;
+}
+
+int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p,
+                    const int64_t *jac_rowptr, const int32_t *jac_col, const int64_t *pm_rowptr, const int32_t *pm_col) {
+  if (!c || !jac_rowptr || !jac_col || !pm_rowptr || !pm_col) return fail(NSG_ERR_ARG, "null argument");
+  NSG_TRY(pattern_sizes(c, n_own_u, n_own_p, n_ghost_u, n_ghost_p));
+  const int64_t n = c->n_own;
+  c->nnz = jac_rowptr[n], c->pm_nnz = pm_rowptr[n];
+  for (int64_t i = 0; i < n; ++i)
+    if (jac_rowptr[i + 1] < jac_rowptr[i] || pm_rowptr[i + 1] < pm_rowptr[i]) return fail(NSG_ERR_ARG, "row pointers not monotone");
+  c->h_rowptr.assign(jac_rowptr, jac_rowptr + n + 1);
+  Trace tr("nsg_set_pattern");
+  c->h_col.assign(jac_col, jac_col + c->nnz);
+  c->h_pm_rowptr.assign(pm_rowptr, pm_rowptr + n + 1);
+  c->h_pm_col.assign(pm_col, pm_col + c->pm_nnz);
+  // +16 elements of slack behind the arrays
+  NSG_TRY(dev_alloc(&c->rowptr, n + 1 + 16));
+  NSG_CUDA(cudaMemsetAsync(c->rowptr, 0, 8 * (size_t)(n + 17), c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->rowptr, jac_rowptr, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+  NSG_TRY(dev_alloc(&c->col, c->nnz + 16));
+  NSG_CUDA(cudaMemsetAsync(c->col, 0, 4 * (size_t)(c->nnz + 16), c->stream));
+  NSG_CUDA(cudaMemcpyAsync(c->col, jac_col, 4 * (size_t)c->nnz, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += 8 * (n + 1) + 4 * c->nnz;
+  NSG_TRY(upload(c, &c->pm_rowptr, pm_rowptr, n + 1));
+  NSG_TRY(upload(c, &c->pm_col, pm_col, c->pm_nnz));
+  tr.mark("host copies + uploads queued");
   c->have_paired = rows_come_in_pairs(c, jac_rowptr, jac_col);
   if (c->have_paired && n_ghost_u + n_ghost_p > 0) {  // row groups of SpMV variant 7 that read a ghost column
     const int64_t n_ug = n_own_u / 2, n_groups = n_ug + n_own_p;
@@ -1112,14 +1153,115 @@ int nsg_set_pattern(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghos
     NSG_TRY(upload(c, &c->bgroups, list.data(), c->n_bgroups));
   }
   c->spmv_variant = c->have_paired ? 7 : 4;  // fastest measured (profiles/r01_summary.md); 7 needs the node-pair row structure
-  for (double **v : {&c->sol, &c->sol_old, &c->delta, &c->R}) {
-    NSG_TRY(dev_alloc(v, c->stride));
-    NSG_CUDA(cudaMemsetAsync(*v, 0, 8 * (size_t)c->stride, c->stream));
-  }
-  NSG_TRY(dev_alloc(&c->work, 8 * c->stride));
-  NSG_CUDA(cudaMemsetAsync(c->work, 0, 8 * 8 * (size_t)c->stride, c->stream));
-  NSG_CUDA(cudaStreamSynchronize(c->stream));
-  c->have_pattern = true;
+  tr.mark("row-pair check");
+  return finish_pattern(c, tr);
+}
+
+// the same two patterns built on the device from the cell -> dof table (nsg_pattern.cuh)
+int nsg_set_pattern_from_cells(nsg_ctx *c, int64_t n_own_u, int64_t n_own_p, int64_t n_ghost_u, int64_t n_ghost_p, int64_t n_cells,
+                               const int32_t *cell_dofs) {
+  if (!c || (n_cells > 0 && !cell_dofs) || n_cells < 0) return fail(NSG_ERR_ARG, "bad argument");
+  NSG_TRY(pattern_sizes(c, n_own_u, n_own_p, n_ghost_u, n_ghost_p));
+  Trace tr("nsg_set_pattern_from_cells");
+  const int64_t n = c->n_own, n_ug = n_own_u / 2, n_groups = n_ug + n_own_p, T = n_cells;
+  int32_t *d_cd = nullptr, *gcount = nullptr, *gcells = nullptr, *rowlen = nullptr, *pm_rowlen = nullptr, *err = nullptr;
+  int64_t *gptr = nullptr, *tmp = nullptr;
+  uint8_t *flag = nullptr;
+  auto cleanup = [&]() {
+    dev_free(d_cd), dev_free(gcount), dev_free(gcells), dev_free(rowlen), dev_free(pm_rowlen), dev_free(err), dev_free(gptr), dev_free(tmp);
+    dev_free(flag);
+  };
+  auto body = [&]() -> int {
+    NSG_TRY(upload(c, &d_cd, cell_dofs, 15 * T));
+    NSG_TRY(dev_alloc(&gcount, 2 * n_groups + 2));  // counts, then the fill cursors
+    NSG_TRY(dev_alloc(&gptr, n_groups + 1));
+    NSG_TRY(dev_alloc(&tmp, 3 * (std::max(n, n_groups) / SCAN_B + 2) + 256));
+    NSG_TRY(dev_alloc(&err, 1));
+    NSG_CUDA(cudaMemsetAsync(gcount, 0, 4 * (size_t)(2 * n_groups + 2), c->stream));
+    NSG_CUDA(cudaMemsetAsync(err, 0, 4, c->stream));
+    if (T > 0) {
+      k_pat_count<<<grid_for(9 * T, 256, 1 << 30), 256, 0, c->stream>>>(T, d_cd, n_own_u, n, gcount);
+      NSG_LAUNCH_CHECK(c);
+    }
+    NSG_TRY(dev_exclusive_scan<int32_t>(c, n_groups, gcount, gptr, tmp));
+    int64_t n_inc = 0;
+    NSG_CUDA(cudaMemcpyAsync(&n_inc, gptr + n_groups, 8, cudaMemcpyDeviceToHost, c->stream));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+    NSG_TRY(dev_alloc(&gcells, n_inc));
+    if (T > 0) {
+      k_pat_fill<<<grid_for(9 * T, 256, 1 << 30), 256, 0, c->stream>>>(T, d_cd, n_own_u, n, gptr, gcount + n_groups + 1, gcells);
+      NSG_LAUNCH_CHECK(c);
+    }
+    tr.mark("group -> cells lists");
+    NSG_TRY(dev_alloc(&rowlen, n + 1));
+    NSG_TRY(dev_alloc(&pm_rowlen, n + 1));
+    if (n_groups > 0) {
+      k_pat_rowlen<<<grid_for(n_groups, 128, 1 << 30), 128, 0, c->stream>>>(n_groups, n_ug, gptr, gcells, d_cd, rowlen, pm_rowlen, err);
+      NSG_LAUNCH_CHECK(c);
+    }
+    NSG_TRY(dev_alloc(&c->rowptr, n + 1 + 16));
+    NSG_CUDA(cudaMemsetAsync(c->rowptr, 0, 8 * (size_t)(n + 17), c->stream));
+    NSG_TRY(dev_alloc(&c->pm_rowptr, n + 1));
+    NSG_TRY(dev_exclusive_scan<int32_t>(c, n, rowlen, c->rowptr, tmp));
+    NSG_TRY(dev_exclusive_scan<int32_t>(c, n, pm_rowlen, c->pm_rowptr, tmp));
+    c->h_rowptr.resize((size_t)n + 1), c->h_pm_rowptr.resize((size_t)n + 1);
+    NSG_CUDA(cudaMemcpyAsync(c->h_rowptr.data(), c->rowptr, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream));
+    NSG_CUDA(cudaMemcpyAsync(c->h_pm_rowptr.data(), c->pm_rowptr, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream));
+    int32_t h_err = 0;
+    NSG_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, c->stream));
+    NSG_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h += 16 * (n + 1);
+    if (h_err) return fail(NSG_ERR_ARG, "a patch has more nodes than the device pattern builder holds (vertex valence > 32)");
+    c->nnz = c->h_rowptr[n], c->pm_nnz = c->h_pm_rowptr[n];
+    tr.mark("row lengths + scans");
+    NSG_TRY(dev_alloc(&c->col, c->nnz + 16));
+    NSG_CUDA(cudaMemsetAsync(c->col + c->nnz, 0, 4 * 16, c->stream));
+    NSG_TRY(dev_alloc(&c->pm_col, c->pm_nnz));
+    if (n_groups > 0) {
+      k_pat_cols<<<grid_for(n_groups, 128, 1 << 30), 128, 0, c->stream>>>(n_groups, n_ug, gptr, gcells, d_cd, c->rowptr, c->col, c->pm_rowptr,
+                                                                        c->pm_col);
+      NSG_LAUNCH_CHECK(c);
+    }
+    c->have_paired = true;  // by construction: rows 2g and 2g+1 get the same list
+    if (n_ghost_u + n_ghost_p > 0 && n_groups > 0) {
+      NSG_TRY(dev_alloc(&flag, n_groups));
+      k_pat_ghost_flag<<<grid_for(n_groups, 256, 1 << 30), 256, 0, c->stream>>>(n_groups, n_ug, n, c->rowptr, c->col, flag);
+      NSG_LAUNCH_CHECK(c);
+      std::vector<uint8_t> h_flag((size_t)n_groups);
+      NSG_CUDA(cudaMemcpyAsync(h_flag.data(), flag, (size_t)n_groups, cudaMemcpyDeviceToHost, c->stream));
+      NSG_CUDA(cudaStreamSynchronize(c->stream));
+      std::vector<int32_t> list;
+      for (int64_t g = 0; g < n_groups; ++g)
+        if (h_flag[g]) list.push_back((int32_t)g);
+      c->n_bgroups = (int64_t)list.size();
+      NSG_TRY(upload(c, &c->bgroups, list.data(), c->n_bgroups));
+    }
+    c->spmv_variant = 7;
+    c->pattern_on_device = true;  // no host copy of the column indices: the fan lists look their offsets up on the device
+    tr.mark("columns");
+    return NSG_OK;
+  };
+  const int rc = body();
+  cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (rc != NSG_OK) return rc;
+  return finish_pattern(c, tr);
+}
+
+int nsg_get_pattern_sizes(nsg_ctx *c, int64_t *nnz_jac, int64_t *nnz_pm) {
+  if (!c || !c->have_pattern) return fail(NSG_ERR_STATE, "no pattern");
+  if (nnz_jac) *nnz_jac = c->nnz;
+  if (nnz_pm) *nnz_pm = c->pm_nnz;
+  return NSG_OK;
+}
+int nsg_get_pattern(nsg_ctx *c, int64_t *jac_rowptr, int32_t *jac_col, int64_t *pm_rowptr, int32_t *pm_col) {
+  if (!c || !c->have_pattern) return fail(NSG_ERR_STATE, "no pattern");
+  NSG_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n_own;
+  if (jac_rowptr) NSG_CUDA(cudaMemcpy(jac_rowptr, c->rowptr, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+  if (jac_col && c->nnz > 0) NSG_CUDA(cudaMemcpy(jac_col, c->col, 4 * (size_t)c->nnz, cudaMemcpyDeviceToHost));
+  if (pm_rowptr) NSG_CUDA(cudaMemcpy(pm_rowptr, c->pm_rowptr, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+  if (pm_col && c->pm_nnz > 0) NSG_CUDA(cudaMemcpy(pm_col, c->pm_col, 4 * (size_t)c->pm_nnz, cudaMemcpyDeviceToHost));
   return NSG_OK;
 }
 
@@ -1131,6 +1273,7 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
   if (c->have_mesh) return fail(NSG_ERR_STATE, "mesh already set");
   if (n_bfaces > 0 && (!bface_cell || !bface_face || !bface_tag)) return fail(NSG_ERR_ARG, "null boundary-face arrays");
   NSG_CUDA(cudaSetDevice(c->device));
+  Trace tr("nsg_set_mesh");
   for (int64_t i = 0; i < 15 * n_cells; ++i)
     if (cell_dofs[i] < 0 || cell_dofs[i] >= c->n_loc) return fail(NSG_ERR_ARG, "cell_dofs entry out of range");
   for (int64_t i = 0; i < 3 * n_cells; ++i)
@@ -1157,8 +1300,11 @@ int nsg_set_mesh(nsg_ctx *c, int64_t n_cells, int64_t n_vertices, const double *
   // the other variants are built on demand (nsg_set_tuning key 1) or when the fan scheme cannot serve the mesh.
   {
     bool ok_u = false, ok_p = false;
+    tr.mark("checks + uploads + geometry");
     NSG_TRY(build_fanlist(c, 0, cell_dofs, &c->wl_u6, &ok_u));
+    tr.mark("fan list (velocity rows)");
     if (ok_u) NSG_TRY(build_fanlist(c, 1, cell_dofs, &c->wl_p6, &ok_p));
+    tr.mark("fan list (pressure rows)");
     const size_t s6u = 8 * (size_t)c->wl_u6.max_stage, s6p = 8 * (size_t)c->wl_p6.max_stage;
     c->fan_ok = ok_u && ok_p && s6u <= 200 * 1024 && s6p <= 200 * 1024;
     if (c->fan_ok) {

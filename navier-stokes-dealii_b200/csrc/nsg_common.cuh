@@ -177,6 +177,7 @@ struct nsg_ctx {
   int64_t nnz = 0, pm_nnz = 0;
   int64_t n_cells = 0, n_vertices = 0, n_bfaces = 0;
   bool have_pattern = false, have_mesh = false;
+  bool pattern_on_device = false;  // built by nsg_set_pattern_from_cells: no host copy of the column indices exists
   nsg_params prm{};
   // host copies of the patterns kept until nsg_set_mesh has built the work lists
   std::vector<int64_t> h_rowptr, h_pm_rowptr;

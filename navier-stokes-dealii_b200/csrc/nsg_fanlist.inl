@@ -10,6 +10,10 @@
 // <= 32; the caller then serves the mesh with variant 4.
 static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out, bool *supported) {
   *supported = false;
+  // pattern built on the device (nsg_set_pattern_from_cells): there is no host copy of the column indices; the column
+  // offsets of the lanes are looked up by a kernel after the records are uploaded, and every entry of the pattern is
+  // covered by construction (no zero-fill bookkeeping)
+  const bool dev_off = c->pattern_on_device;
   const int64_t T = c->n_cells, nu = c->n_own_u, nown = c->n_own;
   const int64_t ng = kind == 0 ? nu / 2 : c->n_own_p;
   const int nk = kind == 0 ? 6 : 3;
@@ -122,7 +126,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
     }
     ci.rec_base = b * NPC6;
     const int64_t img = kind == 0 ? (int64_t)ci.cnt : (int64_t)ci.cnt + ci.mcnt;
-    std::vector<uint8_t> touched((size_t)img, 0);
+    std::vector<uint8_t> touched(dev_off ? (size_t)0 : (size_t)img, 0);
     int64_t n_touched = 0;
     int owners_with_cells = 0;
     for (int64_t g = ci.g0; g < ci.g1; ++g) {
@@ -182,12 +186,14 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
       const int64_t len = re - rs, roff = rs - ci.rs;
       if (len >= 65535 || roff >= 65535) bad++;
       if (kind == 0 && c->h_rowptr[row + 2] - re != len) bad++;
-      const int32_t *cb = c->h_col.data() + rs, *ce = c->h_col.data() + re;
+      const int32_t *cb = dev_off ? nullptr : c->h_col.data() + rs, *ce = dev_off ? nullptr : c->h_col.data() + re;
       const int32_t *mb = cb, *me = ce;
       int64_t moff = roff, mrow_off = 0;
       if (kind == 1) {
-        mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
-        me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+        if (!dev_off) {
+          mb = c->h_pm_col.data() + c->h_pm_rowptr[row];
+          me = c->h_pm_col.data() + c->h_pm_rowptr[row + 1];
+        }
         mrow_off = c->h_pm_rowptr[row] - ci.ms;
         moff = ci.cnt + mrow_off;
         if (mrow_off >= 65535) bad++;
@@ -213,7 +219,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
           wcol[0] = true, wcol[1] = write_next, wcol[2] = true, wcol[3] = head, wcol[4] = true, wcol[5] = true;
           wp[0] = true, wp[1] = write_next, wp[2] = true;
         }
-        for (int l = 0; l < 6; ++l) {
+        for (int l = 0; l < 6 && !dev_off; ++l) {
           const int lc = l < 3 ? (l + r) % 3 : 3 + (l - 3 + r) % 3;  // canonical local node of rotated node l
           const int32_t tgt = cdc[uidx(lc)];
           const int32_t *p = std::lower_bound(cb, ce, tgt);
@@ -233,7 +239,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
               }
           }
         }
-        for (int m = 0; m < 3; ++m) {
+        for (int m = 0; m < 3 && !dev_off; ++m) {
           const int32_t tgt = cdc[3 * ((m + r) % 3) + 2];
           const int32_t *p = std::lower_bound(mb, me, tgt);
           if (p == me || *p != tgt) {
@@ -261,7 +267,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
     }
     // an entry of the pattern no cell contributes to (a pattern wider than the mesh implies) must still be written: zero-fill
     // (pressure chunks are always zero-filled: the p-p block of the Jacobian is structurally present and never written)
-    if (kind == 0) ci.pad = (n_touched == img && owners_with_cells == ci.g1 - ci.g0) ? 0 : 1;
+    if (kind == 0) ci.pad = (dev_off || (n_touched == img && owners_with_cells == ci.g1 - ci.g0)) ? 0 : 1;
     // the first 16 bytes of the header carry what the pipelined kernel needs at the end of an iteration: g0, g1, image
     // entries, zero-fill flag
     ci.n_threads = ci.cnt, ci.max_slots = (int32_t)ci.pad;
@@ -277,6 +283,18 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
   out->max_stage = max_smem;
   NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
   NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC6));
+  if (dev_off && nchunks > 0) {
+    int32_t *err = nullptr, h_err = 0;
+    NSG_TRY(dev_alloc(&err, 1));
+    NSG_CUDA(cudaMemsetAsync(err, 0, 4, c->stream));
+    k_fan_offsets<<<grid_for(nchunks * NPC6, 256, 1 << 30), 256, 0, c->stream>>>(kind, nchunks * NPC6, NPC6, out->recs, out->chunks, c->cell_dofs, nu,
+                                                                                c->rowptr, c->col, c->pm_rowptr, c->pm_col, err);
+    c->launches++;
+    cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    dev_free(err);
+    if (h_err) return fail(NSG_ERR_ARG, "cell_dofs do not match the sparsity pattern");
+  }
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   *supported = true;
   return NSG_OK;

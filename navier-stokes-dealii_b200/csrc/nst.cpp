@@ -894,6 +894,11 @@ int nst_dirichlet_values(const nst_mesh *m, const nst_dofs *d, int n_calls, cons
 // ---------------------------------------------------------------------------------------
 int nst_part_build(const nst_mesh *m, const nst_dofs *d, int n_parts, const int32_t *cell_part, int rank,
                    nst_part **out) {
+  return nst_part_build_ex(m, d, n_parts, cell_part, rank, 0, out);
+}
+
+int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const int32_t *cell_part, int rank, int flags,
+                      nst_part **out) {
   if (!m || !d || !out || n_parts != d->n_parts || rank < 0 || rank >= n_parts)
     return fail(NST_ERR_ARG, "bad argument (n_parts must match nst_dofs_distribute)");
   if (n_parts > 1 && !cell_part) return fail(NST_ERR_ARG, "cell_part required");
@@ -974,7 +979,10 @@ int nst_part_build(const nst_mesh *m, const nst_dofs *d, int n_parts, const int3
   // local patterns of the owned rows (columns ascending in local ids: owned first, then ghosts)
   const int32_t a0 = (int32_t)n_own_u, a1 = (int32_t)n_own, a2 = (int32_t)(n_own + n_gu);
   auto is_p = [a0, a1, a2](int32_t l) { return (l >= a0 && l < a1) || l >= a2; };
-  {
+  if (flags & NST_PART_NO_PATTERNS) {  // the device builds them from cell_dofs (nsg_set_pattern_from_cells)
+    P->jac_rowptr.assign((size_t)n_own + 1, 0);
+    P->pm_rowptr.assign((size_t)n_own + 1, 0);
+  } else {
     DofCells dc;  // shared by the two patterns
     dof_to_cells(n_own, nc, P->cell_dofs.data(), dc);
     build_pattern(n_own, nc, P->cell_dofs.data(), 0, is_p, P->jac_rowptr, &P->jac_col, &dc);

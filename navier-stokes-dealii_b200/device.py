@@ -22,8 +22,15 @@ class DeviceProblem:
         self.pm_nnz = part.nnz_pm
         if stream is not None:
             nsg_check(L.nsg_set_stream(h, C.c_void_p(int(stream))))
-        nsg_check(L.nsg_set_pattern(h, part.n_own_u, part.n_own_p, part.n_ghost_u, part.n_ghost_p, part.jac_rowptr,
-                                    _nz(part.jac_col), part.pm_rowptr, _nz(part.pm_col)))
+        if getattr(part, "has_patterns", True):
+            nsg_check(L.nsg_set_pattern(h, part.n_own_u, part.n_own_p, part.n_ghost_u, part.n_ghost_p, part.jac_rowptr,
+                                        _nz(part.jac_col), part.pm_rowptr, _nz(part.pm_col)))
+        else:   # Part(..., patterns=False): the device builds the two sparsity patterns from the cell -> dof table (N4)
+            nsg_check(L.nsg_set_pattern_from_cells(h, part.n_own_u, part.n_own_p, part.n_ghost_u, part.n_ghost_p, part.n_cells,
+                                                   _nz(part.cell_dofs)))
+            a, b = C.c_int64(), C.c_int64()
+            nsg_check(L.nsg_get_pattern_sizes(h, C.byref(a), C.byref(b)))
+            self.nnz, self.pm_nnz = a.value, b.value
         nsg_check(L.nsg_set_mesh(h, part.n_cells, part.n_vertices, part.xy, part.cell_vertices, part.cell_dofs,
                                  len(part.bface_cell), _nz(part.bface_cell), _nz(part.bface_face), _nz(part.bface_tag)))
         self.params = NsgParams()
@@ -124,6 +131,13 @@ class DeviceProblem:
         out = np.zeros(4, np.int32)
         nsg_check(self._L.nsg_last_solve_info(self._h, out))
         return {"fused": bool(out[0]), "graph_replays": int(out[1]), "spmv_variant": int(out[2]), "orthogonalization": int(out[3])}
+
+    def get_pattern(self):
+        """(jac_rowptr, jac_col, pm_rowptr, pm_col) as the device holds them."""
+        rp, prp = np.zeros(self.n_own + 1, np.int64), np.zeros(self.n_own + 1, np.int64)
+        col, pcol = np.zeros(max(self.nnz, 1), np.int32), np.zeros(max(self.pm_nnz, 1), np.int32)
+        nsg_check(self._L.nsg_get_pattern(self._h, rp, col, prp, pcol))
+        return rp, col[: self.nnz], prp, pcol[: self.pm_nnz]
 
     def update_solution(self):
         nsg_check(self._L.nsg_update_solution(self._h))

@@ -191,11 +191,14 @@ def _view(ptr, n, dtype):
 class Part:
     """One rank's local problem: owned rows + one ghost layer (cpp:19-21, 75-91)."""
 
-    def __init__(self, dofs, rank=0):
+    def __init__(self, dofs, rank=0, patterns=True):
+        """patterns=False: leave the two sparsity patterns to the device (DeviceProblem builds them from cell_dofs)."""
         self.dofs = dofs
         self.rank = int(rank)
+        self.has_patterns = bool(patterns)
         h = C.c_void_p()
-        nst_check(nst().nst_part_build(dofs.mesh._h, dofs._h, dofs.n_parts, dofs.cell_part, self.rank, C.byref(h)))
+        nst_check(nst().nst_part_build_ex(dofs.mesh._h, dofs._h, dofs.n_parts, dofs.cell_part, self.rank, 0 if patterns else 1,
+                                          C.byref(h)))
         self._h = h
         info = PartInfo()
         nst_check(nst().nst_part_get_info(h, C.byref(info)))

@@ -52,28 +52,30 @@ def test_config2_stokes_initialised_steady_ns(pkg):
     assert xs[:s.dofs.n_u:2][mid].min() > 0.5                        # developed channel flow
 
 
-def test_config3_unsteady_cylinder_drag_lift(pkg):
-    """configs[2] in miniature: flow past the cylinder (surface entity 5 of mesh2d.msh, Re = 20), inlet on,
-    two implicit-Euler steps of Newton + GMRES(28, identity), drag/lift on the cylinder after every step.
-    The linear solves run to 1e-12 instead of the reference's 1e-2 so that the comparison is not limited
-    by where two implementations stop along thousands of restarted steps: the default assembly
-    kernel sums the quadrature in a different (factored) order than the oracle's literal loop, the two GMRES
-    paths then differ at the 1e-16 level and may stop one step apart, which leaves (condition number x solver
-    tolerance) in the iterate - 1.1e-8 at a solver tolerance of 1e-10, hence 1e-12 here."""
-    prm = pkg.Parameters(mesh_path=mesh_path("cylinder_mesh2d.msh"), surface_entity=5, nu=0.05, u_m=1.0, H=4.1, inlet_y0=-2.0,
+def test_config1_unsteady_cylinder_re20_ten_steps(pkg):
+    """configs[0] at its stated length: flow past the cylinder (surface entity 5 of mesh2d.msh), Re = 20 (nu = 0.05, mean inflow 1,
+    D = 1), inlet on, TEN implicit-Euler steps of Newton + GMRES(28, identity), drag/lift on the cylinder after every step.
+    The linear solves run to 1e-12 instead of the reference's 1e-2 (cpp:566): with the inlet on, the reference's own settings do
+    not give a usable Newton iteration - the oracle needs 4, 5, 7, 9, 10+ Newton iterations in time steps 1..5 and stalls above
+    the 1e-2 Newton tolerance from step 5 on (profiles/r02_summary.md) - and a comparison at 1e-8 must not be limited by where
+    two implementations stop along 50 000-step restarted solves (at a solver tolerance of 1e-10 that leaves 1.1e-8 in the
+    iterate).  33 Newton iterations, 1.15 million GMRES steps on either side."""
+    prm = pkg.Parameters(mesh_path=mesh_path("cylinder_mesh2d.msh"), surface_entity=5, nu=0.05, u_m=1.5, H=4.1, inlet_y0=-2.0,
                          inlet_time_mode="constant", preconditioner="identity", force_boundary_id=3, p_out=0.0,
                          increment_bc="consistent", neumann_id=1, inlet_id=0, wall_ids=(2, 3), newton_max_iters=8,
-                         gmres_rel_tol=1e-12, gmres_max_iters=400000)
-    s, o = run_both(pkg, prm, T=0.1, dt=0.05, box_tags=(0, 1, 2, 3))
-    assert len(s.force_history) == len(o.force_history) == 2
+                         gmres_rel_tol=1e-12, gmres_max_iters=1000000)
+    s, o = run_both(pkg, prm, T=0.5, dt=0.05, box_tags=(0, 1, 2, 3))
+    assert len(s.force_history) == len(o.force_history) == 10
     assert [(a, b, d is None) for a, b, _, d in s.history] == [(a, b, d is None) for a, b, _, d in o.history]
+    assert max(a for a, _, _, _ in s.history) == 10 and all(r <= 1e-2 for _, _, r, d in s.history if d is None)   # every step converged
     fs, fo = np.array(s.force_history), np.array(o.force_history)
-    print("forces", fs.tolist(), fo.tolist())
-    assert np.abs(fs[:, 1:] - fo[:, 1:]).max() <= 1e-8 * np.abs(fo[:, 1]).max()      # drag and lift
+    print("forces", fs[-1].tolist(), fo[-1].tolist())
+    assert np.abs(fs[:, 1:] - fo[:, 1:]).max() <= 1e-8 * np.abs(fo[:, 1]).max()      # drag and lift history
     for (_, _, r1, _), (_, _, r2, _) in zip(s.history, o.history):
         assert abs(r1 - r2) <= 1e-8 * max(r2, 1.0)
     xs, xo = s.dev.get_solution(), o.dev.get_solution()
     assert np.abs(xs - xo).max() <= 1e-8 * np.abs(xo).max()
+    assert s.dev.last_solve_info()["fused"]          # 1 451 unknowns: the cooperative single-kernel solver
 
 
 def test_error_paths(pkg):
