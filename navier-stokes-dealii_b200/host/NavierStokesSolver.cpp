@@ -153,7 +153,11 @@ void NavierStokesSolver::setup() {
   pcout << "    total    = " << n_u_global + n_p_global << std::endl;
   pcout << "-----------------------------------------------" << std::endl;
   pcout << "  Initializing the linear system" << std::endl;
-  NST_CALL(nst_part_build(mesh, dofs, (int)mpi_size, mpi_size > 1 ? cell_part.data() : nullptr, (int)mpi_rank, &part));
+  // the three sparsity patterns of cpp:101-158 are built on the device from the cell -> dof table;
+  // NS_HOST_PATTERNS=1 builds them in libnst and uploads them instead (bit-identical, slower)
+  const bool host_patterns = env_int("NS_HOST_PATTERNS", nullptr, 0) != 0;
+  NST_CALL(nst_part_build_ex(mesh, dofs, (int)mpi_size, mpi_size > 1 ? cell_part.data() : nullptr, (int)mpi_rank,
+                             host_patterns ? 0 : NST_PART_NO_PATTERNS, &part));
   nst_part_info I;
   NST_CALL(nst_part_get_info(part, &I));
   n_own_u = I.n_own_u, n_own = I.n_own_u + I.n_own_p;
@@ -161,8 +165,11 @@ void NavierStokesSolver::setup() {
   const int device = env_int("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", 0);
   NSG_CALL(nsg_create(device, &dev));
   pcout << "  Initializing the sparsity pattern" << std::endl;
-  NSG_CALL(nsg_set_pattern(dev, I.n_own_u, I.n_own_p, I.n_ghost_u, I.n_ghost_p, nst_part_jac_rowptr(part), nst_part_jac_col(part),
-                           nst_part_pm_rowptr(part), nst_part_pm_col(part)));
+  if (host_patterns)
+    NSG_CALL(nsg_set_pattern(dev, I.n_own_u, I.n_own_p, I.n_ghost_u, I.n_ghost_p, nst_part_jac_rowptr(part), nst_part_jac_col(part),
+                             nst_part_pm_rowptr(part), nst_part_pm_col(part)));
+  else
+    NSG_CALL(nsg_set_pattern_from_cells(dev, I.n_own_u, I.n_own_p, I.n_ghost_u, I.n_ghost_p, I.n_cells, nst_part_cell_dofs(part)));
   pcout << "  Initializing the matrices" << std::endl;
   NSG_CALL(nsg_set_mesh(dev, I.n_cells, I.n_vertices, nst_part_xy(part), nst_part_cell_vertices(part), nst_part_cell_dofs(part),
                         nst_part_n_boundary_faces(part), nst_part_bface_cell(part), nst_part_bface_face(part),

@@ -118,7 +118,7 @@ class NavierStokesSolver:
         self.pcout(f"    total    = {self.dofs.n}")
         self.pcout("-----------------------------------------------")
         self.pcout("  Initializing the linear system")
-        self.part = Part(self.dofs, self.rank)
+        self.part = Part(self.dofs, self.rank, patterns=False)   # the device builds the sparsity patterns
         self.dev = DeviceProblem(self.part, self.device, self._stream)
         if self.world_size > 1:
             self.dev.comm_init(self.rank, self.world_size, self._uid)

@@ -17,8 +17,9 @@ def run_both(pkg, prm, T, dt, stokes_init=False, box_tags=None):
     s = pkg.NavierStokesSolver(2, 1, T, dt, prm, verbose=False)
     s.setup(mesh)
     o = pkg.NavierStokesSolver(2, 1, T, dt, prm, verbose=False)
-    o.mesh, o.dofs, o.part = s.mesh, s.dofs, s.part
-    o.dev = Oracle(s.part)                 # same driver, CPU oracle behind it
+    o.mesh, o.dofs = s.mesh, s.dofs
+    o.part = pkg.Part(s.dofs, 0)           # with the host-built patterns (the device builds its own from the cells)
+    o.dev = Oracle(o.part)                 # same driver, CPU oracle behind it
 
     def checked(solve):
         def f(*a, **k):
