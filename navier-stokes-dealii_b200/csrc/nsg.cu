@@ -1539,18 +1539,30 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
     if (dofs[i] < 0 || dofs[i] >= c->n_own) return fail(NSG_ERR_ARG, "Dirichlet dof is not a locally owned row");
   if (c->dir_cap < n) {
     dev_free(c->dir_dofs), dev_free(c->dir_vals);
+    c->h_dir_dofs.clear(), c->h_dir_vals.clear();
     NSG_TRY(dev_alloc(&c->dir_dofs, n));
     NSG_TRY(dev_alloc(&c->dir_vals, n));
     c->dir_cap = n;
   }
   NSG_CUDA(cudaEventRecord(c->ev0, c->stream));
-  NSG_CUDA(cudaMemcpyAsync(c->dir_dofs, dofs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  NSG_CUDA(cudaMemcpyAsync(c->dir_vals, values, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  c->h2d += 12 * n;
+  // the list is the same in every Newton iteration unless the inlet changes (frozen / constant inlet): the copy on the
+  // device is reused when the caller passes the same dofs and values again (two small pageable copies cost more than the kernels)
+  const bool same_dofs = (int64_t)c->h_dir_dofs.size() == n && std::memcmp(c->h_dir_dofs.data(), dofs, 4 * (size_t)n) == 0;
+  const bool same_vals = same_dofs && (int64_t)c->h_dir_vals.size() == n && std::memcmp(c->h_dir_vals.data(), values, 8 * (size_t)n) == 0;
+  if (!same_dofs) {
+    c->h_dir_dofs.assign(dofs, dofs + n);
+    NSG_CUDA(cudaMemcpyAsync(c->dir_dofs, c->h_dir_dofs.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += 4 * n;
+  }
+  if (!same_vals) {
+    c->h_dir_vals.assign(values, values + n);
+    NSG_CUDA(cudaMemcpyAsync(c->dir_vals, c->h_dir_vals.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += 8 * n;
+  }
   // d_b = |first non-zero diagonal entry of block (b,b) in the local range|, only for blocks that
   // have constrained rows (the per-block apply_boundary_values returns early otherwise)
   bool has_blk[2] = {false, false};
-  for (int64_t i = 0; i < n; ++i) has_blk[dofs[i] < c->n_own_u ? 0 : 1] = true;
+  for (int64_t i = 0; i < n && !(has_blk[0] && has_blk[1]); ++i) has_blk[dofs[i] < c->n_own_u ? 0 : 1] = true;
   NSG_CUDA(cudaMemsetAsync(c->first_idx, 0xff, 16, c->stream));
   for (int b = 0; b < 2; ++b) {
     if (!has_blk[b]) continue;

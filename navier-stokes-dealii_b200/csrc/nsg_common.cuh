@@ -232,6 +232,8 @@ struct nsg_ctx {
   int32_t *dir_dofs = nullptr;
   double *dir_vals = nullptr;
   int64_t dir_cap = 0;
+  std::vector<int32_t> h_dir_dofs;  // what dir_dofs / dir_vals hold (host copies: an unchanged list is not uploaded again)
+  std::vector<double> h_dir_vals;
   // halo
   int32_t n_neighbors = 0;
   std::vector<int32_t> neighbors;

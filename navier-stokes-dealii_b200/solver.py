@@ -145,8 +145,16 @@ class NavierStokesSolver:
         walls = p.stokes_wall_ids if stokes else p.wall_ids
         second = {} if (stokes or p.clear_inlet_before_walls) else {inlet_id: True}
         second.update({w: False for w in walls})
-        gd, gv = self.dofs.dirichlet_values([{inlet_id: True}, second], self._inlet())
-        ld, lv = self.part.localize_dirichlet(gd, gv)
+        # interpolate_boundary_values walks the whole mesh (cpp:351-373): with a frozen / constant inlet the list is the same in
+        # every Newton iteration of every time step, so it is evaluated once per (path, inlet factor)
+        inlet = self._inlet()
+        key = (bool(stokes), inlet["time_factor"])
+        cache = self.__dict__.setdefault("_dirichlet_cache", {})
+        if key not in cache:
+            gd, gv = self.dofs.dirichlet_values([{inlet_id: True}, second], inlet)
+            cache.clear()
+            cache[key] = self.part.localize_dirichlet(gd, gv)
+        ld, lv = cache[key]
         if not stokes and p.increment_bc == "consistent" and len(ld):
             lv = lv - self.dev.get_solution()[ld]
         return ld, lv
