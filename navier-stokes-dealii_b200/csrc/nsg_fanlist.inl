@@ -111,7 +111,10 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
   PairRec no_work;
   std::memset(&no_work, 0, sizeof no_work);
   no_work.cell = -1;
-  std::vector<PairRec> recs((size_t)nchunks * NPC6, no_work);
+  // 32 bytes per lane, gigabytes at bench size: allocated untouched and initialised chunk by chunk inside the parallel loop
+  // (a std::vector would fill it on one thread first)
+  std::unique_ptr<PairRec[]> recs_mem(new PairRec[(size_t)std::max<int64_t>(nchunks * NPC6, 1)]);
+  PairRec *recs = recs_mem.get();
   int bad = 0, unsupported = 0;
   int64_t max_smem = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_smem) reduction(+ : bad, unsupported)
@@ -125,6 +128,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
       ci.cnt = (int32_t)(c->h_rowptr[nu + ci.g1] - ci.rs), ci.mcnt = (int32_t)(c->h_pm_rowptr[nu + ci.g1] - ci.ms);
     }
     ci.rec_base = b * NPC6;
+    for (int l = 0; l < NPC6; ++l) recs[(size_t)(b * NPC6 + l)] = no_work;
     const int64_t img = kind == 0 ? (int64_t)ci.cnt : (int64_t)ci.cnt + ci.mcnt;
     std::vector<uint8_t> touched(dev_off ? (size_t)0 : (size_t)img, 0);
     int64_t n_touched = 0;
@@ -282,7 +286,7 @@ static int build_fanlist(nsg_ctx *c, int kind, const int32_t *cd, WorkList *out,
   out->n_recs = nchunks * NPC6;
   out->max_stage = max_smem;
   NSG_TRY(upload(c, &out->chunks, chunks.data(), nchunks));
-  NSG_TRY(upload(c, &out->recs, recs.data(), nchunks * NPC6));
+  NSG_TRY(upload(c, &out->recs, recs, nchunks * NPC6));
   if (dev_off && nchunks > 0) {
     int32_t *err = nullptr, h_err = 0;
     NSG_TRY(dev_alloc(&err, 1));
