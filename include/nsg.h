@@ -141,13 +141,11 @@ int nsg_solve(nsg_ctx *ctx, int32_t precond, double rel_tol, int32_t max_it, int
 /* residual estimate after every GMRES step of the last nsg_solve (returns how many exist). */
 int64_t nsg_gmres_history(nsg_ctx *ctx, double *out, int64_t cap);
 /* Which code path the last nsg_solve took (so that a test can assert that the knob it set was the one exercised):
- * out5[0] = 1 the whole solve ran as the ONE cooperative kernel (tuning key 5), 0 the multi-kernel solver;
- * out5[1] = number of CUDA-graph replays of restart-cycle segments (tuning key 2; 0 = plain launches);
- * out5[2] = SpMV kernel variant used by the operator (tuning key 0; -1 for the cooperative kernel, which has its own);
- * out5[3] = Gram-Schmidt variant (tuning key 3);
- * out5[4] = number of modified Gram-Schmidt sweeps that ran as ONE cooperative kernel (tuning key 8; 0 = the chain of
- *           add_and_dot kernels). */
-int nsg_last_solve_info(nsg_ctx *ctx, int32_t *out5);
+ * out4[0] = 1 the whole solve ran as the ONE cooperative kernel (tuning key 5), 0 the multi-kernel solver;
+ * out4[1] = number of CUDA-graph replays of restart-cycle segments (tuning key 2; 0 = plain launches);
+ * out4[2] = SpMV kernel variant used by the operator (tuning key 0; -1 for the cooperative kernel, which has its own);
+ * out4[3] = Gram-Schmidt variant (tuning key 3). */
+int nsg_last_solve_info(nsg_ctx *ctx, int32_t *out4);
 
 /* solution_owned += delta_owned; solution = solution_owned (cpp:616-618). */
 int nsg_update_solution(nsg_ctx *ctx);
@@ -213,9 +211,6 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * frame (owner = local vertex 0 / edge 0: all tables are immediates), the lanes of an owner in one warp in fan order,
  * shared-edge contributions combined by warp shuffles, every entry stored exactly once (no read-modify-write, no
  * commit rounds). Needs an oriented manifold triangulation; other meshes are served by 4 automatically.
- * key 8 = the modified Gram-Schmidt sweep of a GMRES step (dim + 1 dependent reductions) as ONE cooperative kernel instead of a chain of
- * add_and_dot kernels (same chain, same arithmetic per entry; stamped-slot grid reductions, rank sums through the peer mailboxes at
- * P > 1): 0 off, 1 (default) for 262 144 unknowns per rank and more (the bench sizes), 2 always.
  * key 6 = L2 prefetch distances of variant 5 in chunks: records (low 16 bits, default 600), packets (high 16 bits, default 0). */
 int nsg_set_tuning(nsg_ctx *ctx, int32_t key, int32_t value);
 

@@ -632,38 +632,6 @@ static int dev_add_and_dot(nsg_ctx *c, int64_t n, double *vv, const double *aptr
   return fused_ar(c) ? NSG_OK : allreduce_scalar(c, out);
 }
 // classical Gram-Schmidt building blocks (global over ranks)
-// the whole modified Gram-Schmidt sweep of one GMRES step in one cooperative kernel (tuning key 8)
-static bool mgs_sweep_on(const nsg_ctx *c, int64_t n) {
-  if (c->mgs_sweep == 0 || c->orthogonalization != 0) return false;
-  if (c->n_ranks > 1 && !fused_ar(c)) return false;  // the rank sums travel through the peer mailboxes
-  static int coop = -1;
-  if (coop < 0) {
-    int v = 0;
-    coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, c->device) == cudaSuccess && v) ? 1 : 0;
-  }
-  if (!coop) return false;
-  return c->mgs_sweep == 2 || n >= c->mgs_sweep_min_n;
-}
-static int dev_mgs_sweep(nsg_ctx *c, int64_t n, double *vv, const double *basis, int dim, bool consider, double *h_out, double *nrm2_out,
-                         double *norm_start2_out, const int32_t *state) {
-  if (!c->sweep_slots) {  // [2][SWEEP_MAX_GRID] {partial, epoch} words + the epoch counter, zeroed once
-    NSG_TRY(dev_alloc(&c->sweep_slots, 2 * (2 * SWEEP_MAX_GRID) + 8));
-    NSG_CUDA(cudaMemsetAsync(c->sweep_slots, 0, sizeof(double) * (2 * (2 * SWEEP_MAX_GRID) + 8), c->stream));
-  }
-  static int per_sm = 0;
-  if (!per_sm) NSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_sweep, SWEEP_THREADS, 0));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)sm_count() * std::max(per_sm, 1), SWEEP_MAX_GRID),
-                                                               ((n >> 1) + SWEEP_THREADS - 1) / SWEEP_THREADS));
-  int64_t stride = c->stride;
-  int cons = consider ? 1 : 0;
-  ulonglong2 *slots = reinterpret_cast<ulonglong2 *>(c->sweep_slots);
-  unsigned long long *epoch_ctr = reinterpret_cast<unsigned long long *>(c->sweep_slots + 2 * (2 * SWEEP_MAX_GRID));
-  PeerComm pc = c->peer;
-  void *args[] = {&n, &vv, &basis, &stride, &dim, &cons, &h_out, &nrm2_out, &norm_start2_out, &slots, &epoch_ctr, &state, &pc};
-  NSG_CUDA(cudaLaunchCooperativeKernel((const void *)k_mgs_sweep, dim3(grid), dim3(SWEEP_THREADS), args, 0, c->stream));
-  c->launches++;
-  return NSG_OK;
-}
 static int dev_multi_dot(nsg_ctx *c, int64_t n, const double *w, const double *basis, int k, double *out, const int32_t *state) {
   k_multi_dot<<<red_grid(n), RED_THREADS, 0, c->stream>>>(n, w, basis, c->stride, k, c->partials_k, c->ticket, out, state, c->peer);
   NSG_LAUNCH_CHECK(c);
@@ -1072,7 +1040,6 @@ void nsg_destroy(nsg_ctx *c) {
   for (void *m : c->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
   dev_free(c->mailbox), dev_free(c->ar_seq), dev_free(c->gf_partials);
-  dev_free(c->sweep_slots);
   dev_free(c->send_dst), dev_free(c->halo_ctr), dev_free(c->halo_ticket), dev_free(c->halo_err), dev_free(c->bgroups);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   dev_free(c->rowptr), dev_free(c->pm_rowptr), dev_free(c->col), dev_free(c->pm_col), dev_free(c->vals), dev_free(c->pm_vals);
@@ -1664,7 +1631,6 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   c->inner_its = 0;
   const bool fused = gmres_fused_applicable(c, precond);
   c->last_solve[0] = fused ? 1 : 0, c->last_solve[1] = 0, c->last_solve[2] = fused ? -1 : c->spmv_variant, c->last_solve[3] = c->orthogonalization;
-  c->last_solve_sweeps = 0;
   if (fused)
     NSG_TRY(gmres_fused(c, x, rel_tol, max_it, n_tmp, (int)hist_cap, &r));
   else
@@ -1692,10 +1658,9 @@ int nsg_solve(nsg_ctx *c, int32_t precond, double rel_tol, int32_t max_it, int32
   return NSG_OK;
 }
 
-int nsg_last_solve_info(nsg_ctx *c, int32_t *out5) {
-  if (!c || !out5) return fail(NSG_ERR_ARG, "null argument");
-  for (int i = 0; i < 4; ++i) out5[i] = c->last_solve[i];
-  out5[4] = (int32_t)std::min<int64_t>(c->last_solve_sweeps, INT32_MAX);
+int nsg_last_solve_info(nsg_ctx *c, int32_t *out4) {
+  if (!c || !out4) return fail(NSG_ERR_ARG, "null argument");
+  for (int i = 0; i < 4; ++i) out4[i] = c->last_solve[i];
   return NSG_OK;
 }
 
@@ -1854,10 +1819,6 @@ int nsg_set_tuning(nsg_ctx *c, int32_t key, int32_t value) {
       return NSG_OK;
     case 2:
       c->use_graphs = value != 0;
-      return NSG_OK;
-    case 8:  // modified Gram-Schmidt sweep as one cooperative kernel: 0 off, 1 (default) from mgs_sweep_min_n unknowns per rank, 2 always
-      if (value < 0 || value > 2) return fail(NSG_ERR_ARG, "mgs sweep must be 0, 1 or 2");
-      c->mgs_sweep = value;
       return NSG_OK;
     case 6:  // L2 prefetch distances of assembly variant 5, in chunks: records (low 16 bits), packets (high 16 bits); 0 = off
       if (value < 0) return fail(NSG_ERR_ARG, "prefetch distances must be >= 0");

@@ -196,10 +196,6 @@ struct nsg_ctx {
   int ilu_variant = 1;  // 0: one launch per dependency level; 1: single launch, rows wait on completion stamps
   bool use_graphs = true;
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
-  int mgs_sweep = 1;           // tuning key 8: the modified Gram-Schmidt sweep of a GMRES step as one cooperative kernel: 0 off, 1 from
-  int64_t mgs_sweep_min_n = 262144;  //   this many unknowns per rank (below, launch-bound solves replay CUDA graphs instead), 2 always
-  double *sweep_slots = nullptr;
-  int64_t last_solve_sweeps = 0;
   std::vector<nsg::GraphEntry> graphs;
   int32_t last_solve[4] = {0, 0, 0, 0};  // nsg_last_solve_info
   bool have_paired = false;  // rows 2g, 2g+1 of every velocity node have the same column list (SpMV variant 7)

@@ -62,7 +62,6 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
   NSG_LAUNCH_CHECK(c);
   bool re_orth = false;
   const bool classical = c->orthogonalization == 1;
-  const bool sweep = !classical && mgs_sweep_on(c, n);  // one cooperative kernel per modified Gram-Schmidt sweep
 
   // ---- the pieces of one restart cycle ----
   auto cycle_start = [&]() -> int {  // p = b - A x ; v0 = P^-1 p ; rho = ||v0|| ; v0 /= rho
@@ -89,10 +88,6 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
       NSG_TRY(A(p, V(inner), state));
       NSG_TRY((*Pinv)(vv, p, state));
     }
-    if (sweep) {
-      c->last_solve_sweeps++;
-      return dev_mgs_sweep(c, n, vv + o, basis + o, dim, consider, &ctl->h[0], &ctl->nrm2, &ctl->norm_start2, state);
-    }
     if (consider) NSG_TRY(dev_dot(c, n, vv + o, vv + o, &ctl->norm_start2, state));
     if (classical && dim <= CGS_MAXK) {  // h = V^T vv ; vv -= V h ; ||vv||  (two passes over the basis)
       NSG_TRY(dev_multi_dot(c, n, vv + o, basis + o, dim, &ctl->h[0], state));
@@ -111,8 +106,6 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
     if (reorth_now && classical && dim <= CGS_MAXK) {
       NSG_TRY(dev_multi_dot(c, n, vv + o, basis + o, dim, &ctl->h2[0], state));
       NSG_TRY(dev_multi_axpy_norm(c, n, vv + o, basis + o, &ctl->h2[0], dim, &ctl->nrm2, state));
-    } else if (reorth_now && sweep) {
-      NSG_TRY(dev_mgs_sweep(c, n, vv + o, basis + o, dim, false, &ctl->h2[0], &ctl->nrm2, &ctl->norm_start2, state));
     } else if (reorth_now) {
       NSG_TRY(dev_dot(c, n, vv + o, V(0) + o, &ctl->h2[0], state));
       for (int i = 1; i < dim; ++i)
@@ -140,8 +133,7 @@ static int gmres_core(nsg_ctx *c, Range rg, const Op &A, const Op *Pinv, double 
   // run `body` either directly or as a cached graph (captured on first use)
   // graphs need launch segments made of kernels only: one rank, or all inter-rank traffic in peer-memory kernels
   // (fused all-reduce + peer-store halo; their sequence counters live on the device, so a replay stays in step)
-  // (cooperative launches are not captured: with the sweep kernel a GMRES step is 5 launches, not 20)
-  const bool use_graphs = lazy && !sweep && c->use_graphs && (c->n_ranks == 1 || (c->halo_peer && c->peer.n_ranks > 1));
+  const bool use_graphs = lazy && c->use_graphs && (c->n_ranks == 1 || (c->halo_peer && c->peer.n_ranks > 1));
   auto run_segment = [&](int seg, const std::function<int()> &body) -> int {
     if (!use_graphs || seg < 0) return body();
     const GraphKey key{seg, n_tmp, n, o, x, b, basis, hist};

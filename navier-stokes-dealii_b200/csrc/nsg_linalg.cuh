@@ -478,159 +478,6 @@ k_add_and_dot(int64_t n, double *vv, const double *aptr, double sign, const doub
   finish_reduce(acc, partials, ticket, out, pc);
 }
 
-// ---- the whole modified Gram-Schmidt sweep of one GMRES step as ONE persistent kernel (tuning key 8) ---------------------
-// deal.II's sweep is a chain of dim + 1 dependent reductions: h_0 = vv.v_0; vv -= h_(i-1) v_(i-1), h_i = vv.v_i;
-// finally vv -= h_(dim-1) v_(dim-1), ||vv||^2.  As dim + 1 kernels every link pays a launch boundary, the ramp-up and the
-// two-stage reduction tail of a short kernel and - at P > 1 - an all-reduce: +18 us per link at 8 GPUs against 49 us of
-// memory time.  Here one cooperative launch runs the whole chain.  Every thread owns the same entries of vv in every pass
-// (it re-reads only what it wrote itself: no fence, no grid barrier for vector data); a reduction is a block sum, one
-// 16-byte {partial, epoch} word per CTA and ONE warp per CTA polling the G words of the epoch and adding them in index order
-// (the scheme of nsg_gmres_fused.cuh), so every CTA holds the sum without a broadcast.  At P > 1 CTA 0 then stores the rank's
-// sum as a stamped word into every peer's mailbox and every CTA polls the P words of its own rank's mailbox and adds them in
-// rank order: bit-identical on all ranks.  Same arithmetic per entry and the same chain as the multi-kernel form; the
-// inner products are partitioned differently (agreement to rounding, not bitwise).
-constexpr int SWEEP_THREADS = 256;
-constexpr int SWEEP_MAX_GRID = 4096;
-__device__ __forceinline__ double sweep_allsum(double v, ulonglong2 *slots, const unsigned long long epoch, const PeerComm &pc,
-                                               const unsigned long long seq, double *s_red /* [2][SWEEP_THREADS / 32 + 1] */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  ulonglong2 *half = slots + (epoch & 1ull) * SWEEP_MAX_GRID;
-  double *buf = s_red + (epoch & 1ull) * (SWEEP_THREADS / 32 + 1);  // alternating: no barrier needed before the next reduction
-  v = warp_sum(v);
-  if (lane == 0) buf[wid] = v;
-  __syncthreads();
-  if (wid == 0) {
-    double a = lane < SWEEP_THREADS / 32 ? buf[lane] : 0.0;
-    a = warp_sum(a);
-    if (lane == 0)
-      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(half + blockIdx.x), "l"((unsigned long long)__double_as_longlong(a)), "l"(epoch)
-                   : "memory");
-    double t = 0.0;
-    bool bad = false;
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      ulonglong2 w;
-      long long t0 = 0;
-      unsigned spins = 0;
-      do {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(half + i) : "memory");
-        if (w.y == epoch) break;
-        if ((++spins & 1023u) == 0u) {  // bounded: a lost CTA turns into NaN (solver failure), not into a hung GPU
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
-            bad = true;
-            break;
-          }
-        }
-      } while (true);
-      t += __longlong_as_double((long long)w.x);
-    }
-    // index order: lane l holds slots l, l + 32, ...; the tree below is the same on every CTA
-    t = warp_sum(t);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (pc.n_ranks > 1) {
-      const int64_t par = (int64_t)(seq & 1ull) * PEER_MAX_RANKS * PEER_MAX_VALS;
-      if (blockIdx.x == 0 && lane < pc.n_ranks) st_volatile_word(pc.ar[lane] + par + (int64_t)pc.rank * PEER_MAX_VALS, t, seq);
-      double mine = 0.0;
-      if (lane < pc.n_ranks) {
-        const PeerWord *w = pc.ar[pc.rank] + par + (int64_t)lane * PEER_MAX_VALS;
-        ulonglong2 x = ld_volatile_word(w);
-        long long t0 = 0;
-        unsigned spins = 0;
-        while (x.y != seq) {
-          x = ld_volatile_word(w);
-          if ((++spins & 1023u) == 0u) {
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
-              bad = true;
-              break;
-            }
-          }
-        }
-        mine = __longlong_as_double((long long)x.x);
-      }
-      double g = 0.0;
-      for (int q = 0; q < pc.n_ranks; ++q) g += __shfl_sync(0xffffffffu, mine, q);  // rank order
-      t = g;
-    }
-    if (__any_sync(0xffffffffu, bad)) t = nan("");
-    if (lane == 0) buf[SWEEP_THREADS / 32] = t;
-  }
-  __syncthreads();
-  return buf[SWEEP_THREADS / 32];
-}
-
-__global__ void __launch_bounds__(SWEEP_THREADS)
-k_mgs_sweep(int64_t n, double *vv, const double *basis, int64_t stride, int dim, int consider, double *h_out, double *nrm2_out,
-            double *norm_start2_out, ulonglong2 *slots, unsigned long long *epoch_ctr, const int32_t *__restrict__ state, const PeerComm pc) {
-  if (state && *state != 0) return;
-  __shared__ double s_red[2 * (SWEEP_THREADS / 32 + 1)];
-  const unsigned long long epoch0 = *(volatile unsigned long long *)epoch_ctr;
-  const unsigned long long seq0 = pc.n_ranks > 1 ? *(volatile unsigned long long *)pc.seq_ctr : 0ull;
-  unsigned long long r = 0;
-  const int64_t n2 = n >> 1, gsize = (int64_t)gridDim.x * SWEEP_THREADS, gtid = blockIdx.x * (int64_t)SWEEP_THREADS + threadIdx.x;
-  const bool tail = (n & 1) && gtid == 0;
-  double2 *v2 = reinterpret_cast<double2 *>(vv);
-  auto V2 = [&](int j) { return reinterpret_cast<const double2 *>(basis + (int64_t)j * stride); };
-  auto V1 = [&](int j) { return basis + (int64_t)j * stride; };
-  if (consider) {  // ||vv||^2 before the sweep (the every-5th-step re-orthogonalisation test)
-    double acc = 0.0;
-    for (int64_t i = gtid; i < n2; i += gsize) {
-      const double2 x = v2[i];
-      acc += x.x * x.x;
-      acc += x.y * x.y;
-    }
-    if (tail) acc += vv[n - 1] * vv[n - 1];
-    ++r;
-    const double s = sweep_allsum(acc, slots, epoch0 + r, pc, seq0 + r, s_red);
-    if (gtid == 0) *norm_start2_out = s;
-  }
-  double h;
-  {
-    double acc = 0.0;
-    const double2 *W = V2(0);
-    for (int64_t i = gtid; i < n2; i += gsize) {
-      const double2 x = v2[i], w = __ldcs(W + i);
-      acc += x.x * w.x;
-      acc += x.y * w.y;
-    }
-    if (tail) acc += vv[n - 1] * V1(0)[n - 1];
-    ++r;
-    h = sweep_allsum(acc, slots, epoch0 + r, pc, seq0 + r, s_red);
-    if (gtid == 0) h_out[0] = h;
-  }
-  for (int j = 1; j <= dim; ++j) {  // vv -= h_(j-1) v_(j-1);  then vv . v_j  (j < dim)  or  vv . vv  (j == dim)
-    const double a = -h;
-    const bool self = j == dim;
-    const double2 *Vp = V2(j - 1), *W = V2(self ? 0 : j);
-    double acc = 0.0;
-    for (int64_t i = gtid; i < n2; i += gsize) {
-      double2 x = v2[i];
-      const double2 y = __ldcs(Vp + i);
-      x.x += a * y.x;
-      x.y += a * y.y;
-      v2[i] = x;
-      const double2 w = self ? x : __ldcs(W + i);
-      acc += x.x * w.x;
-      acc += x.y * w.y;
-    }
-    if (tail) {
-      const double x = vv[n - 1] + a * V1(j - 1)[n - 1];
-      vv[n - 1] = x;
-      acc += x * (self ? x : V1(j)[n - 1]);
-    }
-    ++r;
-    h = sweep_allsum(acc, slots, epoch0 + r, pc, seq0 + r, s_red);
-    if (gtid == 0) {
-      if (self) *nrm2_out = h;
-      else h_out[j] = h;
-    }
-  }
-  if (gtid == 0) {
-    *epoch_ctr = epoch0 + r;
-    if (pc.n_ranks > 1) *pc.seq_ctr = seq0 + r;
-  }
-}
-
 // ---- classical Gram-Schmidt sweep (tuning key 3): two passes over the basis instead of k dependent ones ----
 constexpr int CGS_MAXK = 32;
 // out[j] = w . v_j for j < k, one pass over w and the k basis vectors: (8k + 8) bytes per entry.

@@ -128,10 +128,9 @@ class DeviceProblem:
 
     def last_solve_info(self):
         """Which path the last solve() took: dict(fused, graph_replays, spmv_variant, orthogonalization)."""
-        out = np.zeros(5, np.int32)
+        out = np.zeros(4, np.int32)
         nsg_check(self._L.nsg_last_solve_info(self._h, out))
-        return {"fused": bool(out[0]), "graph_replays": int(out[1]), "spmv_variant": int(out[2]), "orthogonalization": int(out[3]),
-                "mgs_sweeps": int(out[4])}
+        return {"fused": bool(out[0]), "graph_replays": int(out[1]), "spmv_variant": int(out[2]), "orthogonalization": int(out[3])}
 
     def get_pattern(self):
         """(jac_rowptr, jac_col, pm_rowptr, pm_col) as the device holds them."""

@@ -193,12 +193,11 @@ def test_spmv_parity_and_linearity(pkg):
     dev.close()
 
 
-# The identity-preconditioned solve has four code paths (include/nsg.h, tuning keys 5, 2 and 8): the whole solve as ONE
+# The identity-preconditioned solve has three code paths (include/nsg.h, tuning keys 5 and 2): the whole solve as ONE
 # cooperative kernel (default up to 65 536 unknowns), the multi-kernel solver replaying CUDA graphs of the restart-cycle
-# segments (default up to 262 144 unknowns per rank), the same with plain launches, and the multi-kernel solver with every
-# modified Gram-Schmidt sweep as one cooperative kernel (default above 262 144 unknowns per rank: the path bench.py times).
-# Every GMRES parity test runs on all four and asserts through nsg_last_solve_info that the path it asked for is the one that ran.
-PATHS = {"fused": {5: 1}, "graphs": {5: 0, 2: 1, 8: 0}, "plain": {5: 0, 2: 0, 8: 0}, "sweep": {5: 0, 8: 2}}
+# segments (default above that: the path bench.py times), and the same with plain launches.  Every GMRES parity test
+# runs on all three and asserts through nsg_last_solve_info that the path it asked for is the one that ran.
+PATHS = {"fused": {5: 1}, "graphs": {5: 0, 2: 1}, "plain": {5: 0, 2: 0}}
 
 
 def set_path(dev, path):
@@ -210,11 +209,9 @@ def check_path(dev, path, spmv=None):
     info = dev.last_solve_info()
     assert info["fused"] == (path == "fused"), (path, info)
     if path == "graphs":
-        assert info["graph_replays"] > 0 and info["mgs_sweeps"] == 0, info
+        assert info["graph_replays"] > 0, info
     if path == "plain":
-        assert info["graph_replays"] == 0 and info["mgs_sweeps"] == 0, info
-    if path == "sweep":
-        assert info["mgs_sweeps"] > 0 and info["graph_replays"] == 0, info
+        assert info["graph_replays"] == 0, info
     if path != "fused" and spmv is not None:
         assert info["spmv_variant"] == spmv, info
 
@@ -329,17 +326,15 @@ def test_multikernel_gmres_above_the_fused_limit(pkg):
     ro = o.solve(0, 1e-10, 84, 30, 0)
     h2, xo = o.gmres_history(), o.get_delta()
     assert ro[0] == 84 and ro[2] != 0
-    for path in ("graphs", "plain", "sweep"):
+    for path in ("graphs", "plain"):
         if path == "plain":
             dev.set_tuning(2, 0)
-        if path == "sweep":
-            dev.set_tuning(8, 2)   # what the default tuning does from 262 144 unknowns per rank on
         for rep in range(2):       # the second solve replays the graphs captured by the first
             dev.set_delta(x0)
             rd = dev.solve(0, 1e-10, 84, 30, 0, check=False)
             info = dev.last_solve_info()
             assert not info["fused"] and info["spmv_variant"] == 7 and info["orthogonalization"] == 0, info
-            assert (info["graph_replays"] > 0) == (path == "graphs") and (info["mgs_sweeps"] > 0) == (path == "sweep"), info
+            assert (info["graph_replays"] > 0) == (path == "graphs"), info
             assert rd[0] == 84 and rd[2] == -3
             h1 = dev.gmres_history()
             assert np.abs(h1[:28] / h2[:28] - 1).max() <= 1e-9, (path, rep)
