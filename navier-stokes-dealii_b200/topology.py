@@ -178,14 +178,27 @@ class _PartHandle:
             pass
 
 
-def _view(ptr, n, dtype):
-    """Read-only zero-copy view of a library-owned buffer (empty array for n == 0)."""
+class _OwnedView(np.ndarray):
+    """ndarray over a library-owned buffer that keeps the owner of the buffer alive: every view / slice derived from it
+    inherits the reference (`__array_finalize__`), so an array that outlives its Part does not read freed memory."""
+
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
+def _view(ptr, n, dtype, owner=None):
+    """Read-only zero-copy view of a library-owned buffer (empty array for n == 0); `owner` is kept alive by the view."""
     if n == 0:
         return np.zeros(0, dtype=dtype)
     a = np.ctypeslib.as_array(ptr, shape=(int(n),))
     assert a.dtype == np.dtype(dtype), (a.dtype, dtype)
     a.flags.writeable = False
-    return a
+    v = a.view(_OwnedView)
+    v._owner = owner
+    return v
 
 
 class Part:
@@ -210,7 +223,9 @@ class Part:
         # the big arrays are VIEWS of the library-owned buffers (no second copy of hundreds of millions of pattern
         # entries); the holder keeps the nst_part alive for as long as any (shallow copy of this) Part refers to it
         self._keep = _PartHandle(h)
-        view = _view
+
+        def view(ptr, n, dtype):
+            return _view(ptr, n, dtype, self._keep)
         self.l2g = view(L.nst_part_l2g(h), self.n_loc, np.int64)
         self.cell_ids = view(L.nst_part_cell_ids(h), self.n_cells, np.int32)
         self.cell_dofs = view(L.nst_part_cell_dofs(h), 15 * self.n_cells, np.int32)

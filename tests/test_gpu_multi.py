@@ -54,3 +54,30 @@ def test_multi_rank_parity(world, category, tmp_path_factory):
     if world == 4 and category == "assembly":
         assert max(rk["neighbors"] for rk in ranks) >= 2      # RCB corners: more than one neighbour
     assert "MGPU_CHECK PASS" in out.stdout
+
+
+def test_two_rank_shim_twice_in_a_row(pkg):
+    """The C++ shim (host/ns_app, the reference's main.cpp flow) on 2 ranks, started twice with the same MASTER_PORT: the NCCL id
+    travels through a rendezvous file that belongs to one launch (nonce of the launcher, O_EXCL, removed when the communicator is
+    up), so the second run cannot pick up the first run's id and hang; both runs give the 1-rank record."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import glob
+    from conftest import mesh_path
+    app = os.path.join(ROOT, "navier-stokes-dealii_b200", "host", "ns_app")
+    env = dict(os.environ, NS_MESH=mesh_path("square_h0.1.msh"), NS_T="0.05", NS_NEUMANN_ID="1", NS_INLET_ID="0", NS_WALL_IDS="2,3")
+    one = subprocess.run([app, "--history"], capture_output=True, text=True, env=env, timeout=300)
+    assert one.returncode == 0, one.stderr[-1500:]
+    ref = [json.loads(l) for l in one.stdout.splitlines() if l.startswith("{")]
+    for attempt in range(2):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29577", app, "--history"]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, (attempt, r.stdout[-1500:], r.stderr[-1500:])
+        recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        assert len(recs) == len(ref) >= 1
+        for a, b in zip(recs, ref):
+            assert (a["time_step"], a["newton"]) == (b["time_step"], b["newton"])
+            assert abs(a["residual"] - b["residual"]) <= 1e-9 * max(b["residual"], 1e-12)
+        assert not glob.glob("/tmp/ns_nccl_id.29577*"), "the rendezvous file must be removed once the communicator is up"

@@ -227,3 +227,23 @@ def test_part_arrays_are_views_kept_alive_by_copies(pkg):
     junk = [np.ones(1 << 16) for _ in range(64)]      # churn the allocator: freed memory would be overwritten
     assert np.array_equal(clone.jac_col, ref_col) and np.array_equal(clone.cell_dofs, ref_dofs)
     del junk
+
+
+def test_part_views_outlive_the_part(pkg):
+    """The big Part arrays are zero-copy views of library-owned buffers: a slice that outlives its Part must keep the buffers
+    alive (it holds the handle), and a Part built without the sparsity patterns (they are built on the device) has none."""
+    import gc
+    m = pkg.Mesh.read_msh(mesh_path("square_h0.1.msh"))
+    d = pkg.Dofs(m)
+    part = pkg.Part(d, 0)
+    keep = part.jac_col[5:50]
+    want = np.array(keep)
+    cd = np.array(part.cell_dofs)
+    lean = pkg.Part(d, 0, patterns=False)
+    assert not lean.has_patterns and lean.nnz_jac == 0 and lean.nnz_pm == 0 and not lean.jac_rowptr.any()
+    assert np.array_equal(lean.cell_dofs, cd) and lean.n_own == part.n_own and np.array_equal(lean.l2g, part.l2g)
+    del part
+    gc.collect()
+    junk = [np.zeros(1 << 16) for _ in range(8)]      # churn the allocator
+    assert np.array_equal(keep, want) and keep._owner is not None
+    del junk
