@@ -1569,8 +1569,15 @@ int nsg_apply_dirichlet(nsg_ctx *c, int64_t n, const int32_t *dofs, const double
     if (!has_blk[b]) continue;
     const int64_t r0 = b == 0 ? 0 : c->n_own_u, r1 = b == 0 ? c->n_own_u : c->n_own;
     if (r1 > r0) {
-      k_first_nonzero_diag_index<<<grid_for(r1 - r0, 256, sm_count() * 8), 256, 0, c->stream>>>(r0, r1, c->diag_pos, c->vals, c->first_idx + b);
+      // the answer is almost always among the first rows: a 16-block launch looks at the first 4 096 rows, the launch over the rest
+      // returns at once when that found one (every block first compares its base row with the index found so far)
+      const int64_t rh = std::min<int64_t>(r0 + 4096, r1);
+      k_first_nonzero_diag_index<<<16, 256, 0, c->stream>>>(r0, rh, c->diag_pos, c->vals, c->first_idx + b);
       NSG_LAUNCH_CHECK(c);
+      if (r1 > rh) {
+        k_first_nonzero_diag_index<<<grid_for(r1 - rh, 256, sm_count() * 8), 256, 0, c->stream>>>(rh, r1, c->diag_pos, c->vals, c->first_idx + b);
+        NSG_LAUNCH_CHECK(c);
+      }
     }
     k_first_nonzero_diag_value<<<1, 1, 0, c->stream>>>(c->diag_pos, c->vals, c->first_idx + b, c->scal + 8 + b);
     NSG_LAUNCH_CHECK(c);

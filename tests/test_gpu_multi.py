@@ -77,7 +77,8 @@ def test_two_rank_shim_twice_in_a_row(pkg):
         assert r.returncode == 0, (attempt, r.stdout[-1500:], r.stderr[-1500:])
         recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
         assert len(recs) == len(ref) >= 1
-        for a, b in zip(recs, ref):
+        for i, (a, b) in enumerate(zip(recs, ref)):
             assert (a["time_step"], a["newton"]) == (b["time_step"], b["newton"])
-            assert abs(a["residual"] - b["residual"]) <= 1e-9 * max(b["residual"], 1e-12)
+            # the first residual is a pure assembly result (rounding only); later ones follow GMRES solves stopped at 1e-2
+            assert abs(a["residual"] - b["residual"]) <= (1e-9 if i == 0 else 0.2) * max(b["residual"], 1e-12), (i, a, b)
         assert not glob.glob("/tmp/ns_nccl_id.29577*"), "the rendezvous file must be removed once the communicator is up"
