@@ -222,8 +222,8 @@ def main():
     ap.add_argument("--cpu-level", type=int, default=None, help="refinement level of the CPU-baseline sample")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="weak (BASELINE.json configs[4]): --levels is the 1-GPU level, N GPUs refine floor(log4 N) more")
-    ap.add_argument("--nu", type=float, default=0.001, help="viscosity (reference hpp:703; configs[4]: 5e-4 = Re 200)")
-    ap.add_argument("--deltat", type=float, default=0.05, help="time step (reference main.cpp:13; configs[4]: small)")
+    ap.add_argument("--viscosity", dest="nu", type=float, default=0.001, help="viscosity (reference hpp:703; configs[4]: 5e-4 = Re 200)")
+    ap.add_argument("--time-step", dest="deltat", type=float, default=0.05, help="time step (reference main.cpp:13; configs[4]: small)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-patterns", action="store_true", help="build the sparsity patterns on the host (libnst) and upload them")
     args = ap.parse_args()
