@@ -35,9 +35,9 @@
 namespace nsg {
 
 #ifndef NSG_NPC6
-#define NSG_NPC6 128
+#define NSG_NPC6 64
 #endif
-constexpr int NPC6 = NSG_NPC6;  // lanes (pairs) per CTA
+constexpr int NPC6 = NSG_NPC6;  // lanes (pairs) per CTA: two warps (measured: 64 lanes 0.943 ms, 128 lanes 0.965 ms, 256 lanes 1.099 ms at 1.65 M cells)
 constexpr int PK6 = 24;    // doubles per cell packet: [0..11] nodal velocities u_i, [12..23] local residual of the 6 velocity nodes
 constexpr int PK6S = 26;   // row stride of the pre-pass' transposition buffer (208 bytes: 16-byte aligned, conflict-free 128-bit stores)
 
