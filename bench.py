@@ -58,28 +58,63 @@ def build_problem(pkg, mesh, levels, world, rank, patterns=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons of one GPU DURING the timed region (B200_PROFILING.md's clocks line). Polls NVML in-process every
+    10 ms (the timed region of the 8-GPU run lasts half a second: an `nvidia-smi -lms` child does not deliver its first row in that
+    time on an 8-GPU host); falls back to the nvidia-smi loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.nvml, self.stop_flag = gpu, [], None, None, threading.Event()
+        self.sm, self.mask, self.sm_max, self.source = [], 0, None, None
 
     def start(self):
         try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml, 10 ms"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001  (no NVML: try the command-line tool)
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi -lms 100"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.handle))
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.010)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([s.strip() for s in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "samples": len(self.sm),
+                    "reasons": sorted(n for n, bit in self.REASONS if self.mask & bit), "source": self.source}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -94,31 +129,48 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(self.rows[0][2]) if self.rows and len(self.rows[0]) >= 9 else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
+
+
+def _cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
 
 
 def bind_to_gpu_numa_node(local_rank):
-    """Pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs of the NUMA node the GPU
-    hangs off: with 8 ranks on a two-socket host the H2D copies of the e2e step otherwise cross the socket link.
-    Returns a short description for the JSON line; a no-op when sysfs does not tell."""
+    """Pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs next to its GPU: with 8 ranks on a
+    two-socket host the H2D copies of the e2e step otherwise cross the socket link. Sources, in order: sysfs numa_node of the GPU's
+    PCI device, the "CPU Affinity" column of `nvidia-smi topo -m`. Returns a short description for the JSON line; a no-op when
+    neither tells."""
+    import re
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
-        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        prop = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0/numa_node"
         node = int(open(path).read().strip())
-        if node < 0:
-            return "numa node unknown"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        allowed = cpus & os.sched_getaffinity(0)
-        if not allowed:
-            return f"numa node {node}: no allowed cpu"
-        os.sched_setaffinity(0, allowed)
-        return f"numa node {node}, {len(allowed)} cpus"
+        if node >= 0:
+            allowed = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                return f"numa node {node} (sysfs), {len(allowed)} cpus"
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            cols = re.split(r"\s{2,}|\t", re.sub(r"\x1b\[[0-9;]*m", "", line.strip()))
+            if not cols or cols[0] != f"GPU{local_rank}":
+                continue
+            for tok in cols[1:]:
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", tok) and ("-" in tok or "," in tok):
+                    allowed = _cpulist(tok) & os.sched_getaffinity(0)
+                    if allowed:
+                        os.sched_setaffinity(0, allowed)
+                        return f"cpu affinity {tok} (nvidia-smi topo), {len(allowed)} cpus"
+        return "not bound (no affinity information)"
     except Exception as e:  # noqa: BLE001
         return f"not bound ({type(e).__name__})"
 
@@ -201,7 +253,7 @@ def workload_config(args, d):
                        "P2-P1, state u=(sin(pi x)cos(pi y), -cos(pi x)sin(pi y)), p=xy, u_old=0.9u",
            "mesh": args.mesh, "levels": args.levels, "gmres_its_cap": args.gmres_its, "nu": args.nu, "deltat": args.deltat,
            "preconditioner": "identity (reference cpp:570)", "l2": "inputs larger than L2 (no flush needed)",
-           "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, NCCL halo, Krylov all-reduce fused "
+           "parallelism": f"mesh partition x{args.gpus} (RCB), ghost-layer owner-computes assembly, halo exchange by NVLink peer stores, Krylov all-reduce fused "
                           "into the reduction kernels (NVLink peer memory)"}
     if d is not None:
         cfg.update({"cells": int(d.mesh.n_cells), "dofs": int(d.n)})
