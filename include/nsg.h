@@ -184,7 +184,8 @@ int nsg_ilu_apply(nsg_ctx *ctx, int32_t which, const double *x, double *y);
  * launch in milliseconds (CUDA events on the context's stream). what: 0 = assembly (cells +
  * Neumann, no Dirichlet), 1 = SpMV J*delta, 2 = add_and_dot, 3 = dot, 4 = one halo exchange, 5 = FP64 pipe
  * micro-benchmark (SM count x 16 CTAs x 256 threads x 8 chains x 2048 dependent DFMA = SMs x 67 108 864 DFMA per launch,
- * 2 flop each: the measured FP64 peak the assembly's FP64-pipe share is quoted against). */
+ * 2 flop each: the measured FP64 peak the assembly's FP64-pipe share is quoted against), 6 / 7 = one ILU(0) apply (forward +
+ * backward triangular solve, tuning key 4) of the velocity / pressure-mass block, factorised before the timed region. */
 int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_launch);
 
 /* Tuning knobs that do not change what is computed (only the summation order inside a row):
@@ -200,8 +201,12 @@ int nsg_time_kernel(nsg_ctx *ctx, int32_t what, int32_t reps, double *ms_per_lau
  * key 3 = Gram-Schmidt variant of SolverGMRES: 0 (default) modified, the chain of add_and_dot that deal.II
  * <= 9.4 runs; 1 classical (h = V^T w, w -= V h: two passes and two all-reduces per step
  * instead of k+1; deal.II >= 9.5 offers it as OrthogonalizationStrategy::classical_gram_schmidt).
- * key 4 = triangular solves of the ILU(0) preconditioners: 0 one launch per dependency level; 1 (default) one
- * launch per solve, rows wait on the completion stamps of the rows they depend on (bitwise the same result).
+ * key 4 = triangular solves of the ILU(0) preconditioners: 0 one launch per dependency level; 1 one launch per
+ * solve on all SMs, rows wait on the completion stamps of the rows they depend on; 2 one CTA walks the levels, rows
+ * and factors stream through shared-memory rings in level order and the unknowns sit in a shared-memory window
+ * (a dependency hop is a CTA barrier instead of an L2 round trip: the fast choice for the long, narrow level
+ * structure of 2-D meshes); -1 (default) the library picks 1 or 2 per block from the level count and the size of
+ * the factors.  All four give bitwise the same result.
  * key 5 = the whole identity-preconditioned GMRES solve as ONE cooperative kernel (vector entries in registers across
  * the Gram-Schmidt chain, one stamped-slot exchange per inner product; one rank, modified Gram-Schmidt): 0 off, 1 (default) for systems
  * of up to 65 536 unknowns (the meshes the reference ships: 2x faster there), 2 whenever the system fits (up to 148 x 256 x 8 unknowns). Same algorithm and scalars as

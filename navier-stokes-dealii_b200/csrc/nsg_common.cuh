@@ -165,6 +165,22 @@ struct CsrBlock {  // a sub-matrix held separately (A, Mp, B of the block precon
   unsigned long long epoch = 0;
   unsigned long long tickets_l = 0, tickets_u = 0;    // host mirror: tickets handed out so far
   int32_t *sf_error = nullptr;                        // set if a wait ran into its time limit
+  // one-CTA triangular solves (tuning key 4 = 2): rows, entries and unknowns stored in level order ("positions"), so the
+  // kernel streams them through shared-memory rings and a dependency hop is a CTA barrier, not an L2 round trip
+  struct Tri {
+    int32_t n_levels = 0;
+    int64_t nq = 0;             // slots (entries incl. padding)
+    int4 *info = nullptr;       // [n_levels+1] {first slot, slabs per group, 1 = staged through the rings / 0 = read in place, first position}
+    int4 *slots = nullptr;      // [nq] {factor (refreshed after every factorisation), position of the entry's unknown or ~position
+                                //       once it has left the shared-memory window, 0}
+    int64_t *fsrc = nullptr;    // [nq] where the entry sits in fval; -1 = padding
+    int32_t *rowid = nullptr;   // [n] row index of each position
+    int32_t *ra_src = nullptr;  // [n] forward: row index (gathers the right-hand side); backward: position in the forward layout
+    double2 *rows = nullptr;    // [n] by position: {gathered right-hand side, inverse pivot}
+    double *yg = nullptr;       // [n] unknowns by position
+  } triL, triU;
+  bool tri_ok = false;          // the layouts exist (block small enough for 32-bit entry indices)
+  bool tri_pick = false;        // ... and the one-CTA solve is estimated faster than the stamped single launch
 };
 
 }  // namespace nsg
@@ -193,7 +209,8 @@ struct nsg_ctx {
   int gmres_fused = 1;  // tuning key 5: 0 off, 1 systems up to gmres_fused_max_n unknowns, 2 whenever the vectors fit the grid's registers
   int64_t gmres_fused_max_n = 65536;  // measured: 2.0x faster at 29 646 unknowns, 1.08x at 117 324, 0.86x at 232 003
   double *gf_partials = nullptr;
-  int ilu_variant = 1;  // 0: one launch per dependency level; 1: single launch, rows wait on completion stamps
+  int ilu_variant = -1;  // -1: choose per block (1 or 2); 0: one launch per dependency level; 1: single launch, rows wait on
+                         // completion stamps; 2: one CTA, level order, unknowns in a shared-memory window
   bool use_graphs = true;
   int orthogonalization = 0;  // 0 modified Gram-Schmidt (deal.II <= 9.4 default), 1 classical
   std::vector<nsg::GraphEntry> graphs;

@@ -188,6 +188,222 @@ k_ilu_solve_sf(const int32_t *__restrict__ rows, int64_t n, const int64_t *__res
     (void)ok;
   }
 }
+// ---- one-CTA triangular solves ----------------------------------------------------------------------------------
+// A 2-D P2 mesh in the reference's DoF order gives ~50 independent rows per dependency level and thousands of levels:
+// the solve is one long chain, and what it costs is the latency of a dependency hop.  Through L2 (the stamped words
+// above) a hop costs ~1.6 us.  Here ONE CTA walks the levels and a hop is a CTA barrier + a shared-memory load:
+//  * rows are renumbered in level order ("positions"; inside a level by falling row length) and packed in groups of 4
+//    consecutive positions = one warp, 8 lanes per row; lane c of a row owns its entries c, c + 8, c + 16, ...; a group's
+//    entries are stored slab by slab (32 {factor, position} records, one per lane); every group of a level has the
+//    level's slab count (short rows are padded with zero factors), so a group finds its records without a header;
+//  * slabs and {right-hand side, inverse pivot} records stream through shared-memory rings: one producer thread hands
+//    the TMA engine two bulk copies per level, TRI_DEPTH levels ahead, and waits on the level's mbarrier before it joins
+//    the level barrier;
+//  * the unknowns of the last TRI_W positions live in a shared-memory window and leave it through bulk copies,
+//    TRI_FLUSH positions at a time; a column that has already left the window (the host stores ~position) is read back
+//    from global memory.  Levels that do not fit the rings next to their TRI_DEPTH predecessors are read in place.
+// The 8 lanes of a row hold the 32 partial sums a warp of the kernels above holds in its 32 lanes (4 each: entry j and
+// j + 32 accumulate in "lane" j mod 32) and add them in the order of the xor-shuffle tree as lane 0 sees it (steps 16
+// and 8 inside the thread, 4, 2, 1 by shuffles): the result is bitwise the same.  Measured on the 51 842-row block
+// (1 120 + 1 120 levels), per apply: stamped solve 3.46 ms; a warp per row 3.67 ms, a thread per row 6.39 ms (one warp
+// crawling through ~1 000 dependent instructions per level), 8 lanes per row with per-group headers and cp.async
+// staging by 8 producer warps 2.0 ms (2 150 warp instructions per level on one SM).
+constexpr int TRI_W = 8192, TRI_RQ = 8192, TRI_RK = 1024;
+constexpr int TRI_CW = 12, TRI_THREADS = 32 * (TRI_CW + 1);  // compute warps + the producer warp
+constexpr int TRI_DEPTH = 4;                                 // levels the producer runs ahead (a power of two)
+constexpr int TRI_FLUSH = 512, TRI_MAX_LEVEL_ROWS = 2048;    // write-out granularity; widest level the window can take
+constexpr size_t TRI_SMEM = sizeof(double) * TRI_W + 16 * (size_t)(TRI_RQ + TRI_RK);
+struct TriArgs {
+  int32_t n_levels;
+  const int4 *info;     // [n_levels+1] {first slot, slabs per group, staged, first position}
+  const int4 *slots;    // [slots] {factor (2 words), position of the column's unknown or ~position outside the window, 0}
+  const double2 *rows;  // [n] by position: {right-hand side, inverse pivot}
+  double *yg;           // [n] unknowns by position
+  int32_t n;
+};
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
+  }
+}
+// one group of 4 rows (8 lanes each) of a level with S slabs per group; S = 5 stands for "5 or more" (n_slabs says how many)
+template <bool UPPER, bool STAGED, int S>
+__device__ __forceinline__ void tri_group(const TriArgs &A, uint32_t sm_y, uint32_t sm_slots, uint32_t sm_rows, int q0, int n_slabs, int k0,
+                                          int nr, int lane) {
+  const int sub = lane >> 3, k = k0 + sub;
+  const bool writer = sub < nr && (lane & 7) == 0;
+  double2 rr = make_double2(0.0, 1.0);
+  if (writer) {
+    if (STAGED) {
+      const int4 w = lds128(sm_rows + 16u * (uint32_t)(k & (TRI_RK - 1)));
+      rr = make_double2(__hiloint2double(w.y, w.x), __hiloint2double(w.w, w.z));
+    } else {
+      rr = A.rows[k];
+    }
+  }
+  auto product_terms = [&](int i, double &f, double &yv) {
+    const int q = q0 + 32 * i + lane;
+    const int4 e = STAGED ? lds128(sm_slots + 16u * (uint32_t)(q & (TRI_RQ - 1))) : __ldg(A.slots + q);
+    f = __hiloint2double(e.y, e.x);
+    yv = lds64(sm_y + 8u * (uint32_t)(e.z & (TRI_W - 1)));
+    if (e.z < 0) yv = __ldcg(A.yg + ~e.z);
+  };
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < (S < 4 ? S : 4); ++i) {
+    double f, yv;
+    product_terms(i, f, yv);
+    t[i] = __dmul_rn(f, yv);
+  }
+  if (S > 4) {  // rows with more than 32 entries: entry j + 32 accumulates on entry j
+    for (int i0 = 4; i0 < n_slabs; i0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u < n_slabs) {
+          double f, yv;
+          product_terms(i0 + u, f, yv);
+          t[u] = __fma_rn(f, yv, t[u]);
+        }
+    }
+  }
+  // the xor-16 and xor-8 steps of the tree; a step whose second operand is an untouched +0 is skipped (x + 0 = x)
+  if (S > 2) t[0] = __dadd_rn(t[0], t[2]);
+  if (S > 3) t[1] = __dadd_rn(t[1], t[3]);
+  if (S > 1) t[0] = __dadd_rn(t[0], t[1]);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) t[0] = __dadd_rn(t[0], __shfl_xor_sync(0xffffffffu, t[0], o));
+  if (writer) {
+    const double v = UPPER ? __fma_rn(rr.x, rr.y, -t[0]) : __dsub_rn(rr.x, t[0]);
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm_y + 8u * (uint32_t)(k & (TRI_W - 1))), "d"(v) : "memory");
+  }
+}
+template <bool UPPER, bool STAGED, int S>
+__device__ __forceinline__ void tri_level(const TriArgs &A, uint32_t sm_y, uint32_t sm_slots, uint32_t sm_rows, const int4 lv, int warp, int lane) {
+  const int n_slabs = lv.y & 0xffff, rows_in_level = lv.w - lv.z;
+  for (int gi = warp; 4 * gi < rows_in_level; gi += TRI_CW)
+    tri_group<UPPER, STAGED, S>(A, sm_y, sm_slots, sm_rows, lv.x + gi * n_slabs * 32, n_slabs, lv.z + 4 * gi, min(4, rows_in_level - 4 * gi), lane);
+}
+template <bool UPPER>
+__global__ void __launch_bounds__(TRI_THREADS, 1) k_ilu_solve_cta(const TriArgs A) {
+  extern __shared__ __align__(16) unsigned char tri_smem[];
+  __shared__ int4 s_info[2 * TRI_DEPTH];  // {first slot, slabs | staged << 16, first position, one past the last position}
+  __shared__ __align__(8) unsigned long long s_full[TRI_DEPTH];  // mbarriers: the copies of a level have landed
+  const uint32_t sm_y = smem_addr_u32(tri_smem), sm_slots = sm_y + 8u * TRI_W, sm_rows = sm_slots + 16u * TRI_RQ;
+  double *s_y = reinterpret_cast<double *>(tri_smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = tid == 32 * TRI_CW;  // lane 0 of the last warp
+  if (producer) {
+    for (int i = 0; i < TRI_DEPTH; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(s_full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto ring_copy = [&](uint32_t ring, int mask, const void *src, int first, int count, uint32_t bar) {  // 16-byte records
+    const int s0 = first & mask, n1 = min(count, mask + 1 - s0);
+    const char *g = reinterpret_cast<const char *>(src) + 16ll * first;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + 16u * (uint32_t)s0),
+                 "l"(g), "r"(16 * n1), "r"(bar)
+                 : "memory");
+    if (n1 < count)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring), "l"(g + 16ll * n1),
+                   "r"(16 * (count - n1)), "r"(bar)
+                   : "memory");
+  };
+  auto stage_level = [&](int l) {  // producer: start the copies of level l and leave its extent for the compute warps
+    const int4 a = __ldg(A.info + l), b = __ldg(A.info + l + 1);
+    s_info[l & (2 * TRI_DEPTH - 1)] = make_int4(a.x, a.y | (a.z << 16), a.w, b.w);
+    if (!a.z) return;
+    const uint32_t bar = smem_addr_u32(s_full + (l & (TRI_DEPTH - 1)));
+    const int n_slots = b.x - a.x, n_rows = b.w - a.w;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(16 * (n_slots + n_rows)) : "memory");
+    if (n_slots > 0) ring_copy(sm_slots, TRI_RQ - 1, A.slots, a.x, n_slots, bar);
+    ring_copy(sm_rows, TRI_RK - 1, A.rows, a.w, n_rows, bar);
+  };
+  // Unknowns leave the window through the bulk-copy engine, TRI_FLUSH positions at a time (a plain global store per row
+  // costs more instructions and has to drain at the level barriers).
+  int flushed = 0;
+  auto flush = [&](int upto) {  // producer; positions [flushed, upto) are final and visible (barrier), both even
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the previous write-out is complete: far readers may rely on it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int sa = flushed & (TRI_W - 1), cnt = upto - flushed, n1 = min(cnt, TRI_W - sa);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.yg + flushed), "r"(sm_y + 8u * (uint32_t)sa), "r"(8 * n1)
+                 : "memory");
+    if (n1 < cnt)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.yg + flushed + n1), "r"(sm_y), "r"(8 * (cnt - n1))
+                   : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    flushed = upto;
+  };
+  uint32_t parities = 0;
+  if (producer)
+    for (int l = 0; l < TRI_DEPTH && l < A.n_levels; ++l) stage_level(l);
+  for (int l = 0; l < A.n_levels; ++l) {
+    if (producer && (s_info[l & (2 * TRI_DEPTH - 1)].y >> 16)) {  // the copies of level l have landed ...
+      const int st = l & (TRI_DEPTH - 1);  // a level read in place does not use its mbarrier: count the phases per stage
+      mbar_wait(smem_addr_u32(s_full + st), (parities >> st) & 1u);
+      parities ^= 1u << st;
+    }
+    __syncthreads();  // ... and so have the unknowns of level l - 1; the rings of level l - 1 are free
+    if (warp == TRI_CW) {
+      if (producer) {
+        const int final_below = s_info[l & (2 * TRI_DEPTH - 1)].z & ~1;  // the levels before l are complete
+        if (final_below - flushed >= TRI_FLUSH) flush(final_below);
+        if (l + TRI_DEPTH < A.n_levels) stage_level(l + TRI_DEPTH);
+      }
+    } else {
+      const int4 lv = s_info[l & (2 * TRI_DEPTH - 1)];
+      const int S = min(lv.y & 0xffff, 5);
+#define NSG_TRI_CASE(n)                                                              \
+  case n:                                                                            \
+    if (lv.y >> 16) tri_level<UPPER, true, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane); \
+    else tri_level<UPPER, false, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane);     \
+    break;
+      switch (S) {
+        NSG_TRI_CASE(0)
+        NSG_TRI_CASE(1)
+        NSG_TRI_CASE(2)
+        NSG_TRI_CASE(3)
+        NSG_TRI_CASE(4)
+        NSG_TRI_CASE(5)
+      }
+#undef NSG_TRI_CASE
+    }
+  }
+  __syncthreads();
+  if (producer) {
+    flush((A.n + 1) & ~1);  // yg has room for the odd one
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  (void)s_y;
+}
+__global__ void k_scatter_by_index(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ src, double *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[idx[i]] = src[i];
+}
+// out[2 i] = vals[src[i]] (0 for padding): the factor word of the 16-byte slot records
+__global__ void k_gather_slot_factors(int64_t n, const int64_t *__restrict__ src, const double *__restrict__ vals, double *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[2 * i] = src[i] >= 0 ? vals[src[i]] : 0.0;
+}
+// out[2 i + off] = src[idx[i]]: one word of the {right-hand side, inverse pivot} row records
+__global__ void k_gather_row_word(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ src, double *__restrict__ out, int off) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[2 * i + off] = src[idx[i]];
+}
 // y[off + i] = -y[off + i] + x[off + i]  (tmp.sadd(-1, src1), hpp:609)
 __global__ void k_neg_add(int64_t n, double *__restrict__ y, const double *__restrict__ x) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = -y[i] + x[i];
@@ -256,6 +472,79 @@ static int build_block(nsg_ctx *c, CsrBlock &B, const std::vector<int64_t> &rp, 
   NSG_CUDA(cudaMemsetAsync(B.ticket, 0, 2 * sizeof(unsigned long long), c->stream));
   NSG_CUDA(cudaMemsetAsync(B.sf_error, 0, sizeof(int32_t), c->stream));
   B.epoch = 0, B.tickets_l = B.tickets_u = 0;
+  // level-order layouts of the one-CTA solves
+  B.tri_ok = B.tri_pick = false;
+  int32_t widest = 0;  // a level wider than TRI_MAX_LEVEL_ROWS would overrun the window before it is written out
+  for (int32_t l = 0; l < nL; ++l) widest = std::max(widest, B.h_level_ptr[l + 1] - B.h_level_ptr[l]);
+  for (int32_t l = 0; l < nU; ++l) widest = std::max(widest, B.h_ulevel_ptr[l + 1] - B.h_ulevel_ptr[l]);
+  if (n > 0 && B.nnz < (int64_t)1 << 28 && widest <= TRI_MAX_LEVEL_ROWS) {
+    double t_cta = 0.0;
+    auto layout = [&](bool upper, const std::vector<int32_t> &rows_by_level, const std::vector<int32_t> &ptr,
+                      const std::vector<int32_t> *pos_fwd, CsrBlock::Tri &T, std::vector<int32_t> &pos) -> int {
+      const int32_t nl = (int32_t)ptr.size() - 1;
+      auto len = [&](int64_t i) { return upper ? rowptr[i + 1] - diag[i] - 1 : diag[i] - rowptr[i]; };
+      // positions: level by level, inside a level by falling row length
+      std::vector<int32_t> rows(rows_by_level);
+      for (int32_t l = 0; l < nl; ++l)
+        std::stable_sort(rows.begin() + ptr[l], rows.begin() + ptr[l + 1], [&](int32_t x, int32_t y) { return len(x) > len(y); });
+      pos.resize(n);
+      for (int64_t k = 0; k < n; ++k) pos[rows[k]] = (int32_t)k;
+      std::vector<int4> info(nl + 1), slots;
+      std::vector<int32_t> ra_src(n);
+      std::vector<int64_t> fsrc;  // -1: padding (factor 0)
+      slots.reserve(2 * B.nnz), fsrc.reserve(2 * B.nnz);
+      for (int32_t l = 0; l < nl; ++l) {
+        const int32_t k0 = ptr[l], k1 = ptr[l + 1];
+        const int32_t slabs = (int32_t)((len(rows[k0]) + 7) / 8);  // the longest row of the level comes first
+        if (slabs > 0xffff) return fail(NSG_ERR_ARG, "a row with more than 2^19 entries");
+        const size_t q0 = slots.size(), groups = (size_t)(k1 - k0 + 3) / 4;
+        info[l] = make_int4((int)q0, slabs, 0, k0);
+        const int32_t pad = std::max(k0 - 1, 0);  // padding (factor 0) reads the last unknown of the previous level
+        slots.resize(q0 + groups * slabs * 32, make_int4(0, 0, k1 - pad <= TRI_W ? pad : ~pad, 0));
+        fsrc.resize(q0 + groups * slabs * 32, -1);
+        for (int32_t r = 0; r < k1 - k0; ++r) {
+          const int64_t i = rows[k0 + r];
+          const int64_t p0 = upper ? diag[i] + 1 : rowptr[i], m = len(i);
+          for (int64_t j = 0; j < m; ++j) {  // entry j: lane j mod 8 of the row, slab j / 8 of its group
+            const int32_t cp = pos[col[p0 + j]];  // a row of an earlier level: cp < k0
+            const size_t q = q0 + ((size_t)(r >> 2) * slabs + (size_t)(j >> 3)) * 32 + 8 * (r & 3) + (j & 7);
+            slots[q].z = k1 - cp <= TRI_W ? cp : ~cp;
+            fsrc[q] = p0 + j;
+          }
+          ra_src[k0 + r] = upper ? (*pos_fwd)[i] : (int32_t)i;
+        }
+      }
+      if (slots.size() >= (size_t)1 << 30) return fail(NSG_ERR_ARG, "the level-order layout of the triangular solve is too large");
+      info[nl] = make_int4((int)slots.size(), 0, 0, (int)n);
+      int32_t in_place = 0;
+      for (int32_t l = 0; l < nl; ++l) {  // levels l - TRI_DEPTH .. l share the rings while level l is staged
+        const int32_t f = std::max(l - TRI_DEPTH, 0);
+        info[l].z = (info[l + 1].x - info[f].x <= TRI_RQ && info[l + 1].w - info[f].w <= TRI_RK) ? 1 : 0;
+        in_place += info[l].z ? 0 : 1;
+      }
+      T.n_levels = nl, T.nq = (int64_t)slots.size();
+      // ~0.3 us per staged level, an L2 round trip more per level read in place, 16 bytes per slot through one SM
+      t_cta += 0.3e-6 * nl + 0.5e-6 * in_place + 16.0 * (double)slots.size() / 60e9;
+      slots.push_back(make_int4(0, 0, 0, 0)), fsrc.push_back(-1);
+      NSG_TRY(upload(c, &T.info, info.data(), nl + 1));
+      NSG_TRY(upload(c, &T.slots, slots.data(), (int64_t)slots.size()));
+      NSG_TRY(upload(c, &T.fsrc, fsrc.data(), (int64_t)fsrc.size()));
+      NSG_TRY(upload(c, &T.ra_src, ra_src.data(), n));
+      NSG_TRY(upload(c, &T.rowid, rows.data(), n));
+      NSG_TRY(dev_alloc(&T.rows, n + 1));
+      NSG_TRY(dev_alloc(&T.yg, n + 2));
+      NSG_CUDA(cudaMemsetAsync(T.rows, 0, sizeof(double2) * (size_t)(n + 1), c->stream));
+      NSG_CUDA(cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
+      return NSG_OK;
+    };
+    std::vector<int32_t> posL, posU;
+    NSG_TRY(layout(false, rowsL, B.h_level_ptr, nullptr, B.triL, posL));
+    NSG_TRY(layout(true, rowsU, B.h_ulevel_ptr, &posL, B.triU, posU));
+    NSG_CUDA(cudaFuncSetAttribute(k_ilu_solve_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_SMEM));
+    NSG_CUDA(cudaFuncSetAttribute(k_ilu_solve_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_SMEM));
+    B.tri_ok = true;
+    B.tri_pick = t_cta < 1.6e-6 * (nL + nU);  // stamped single launch: ~1.6 us per level (profiles/r02_summary.md)
+  }
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   return NSG_OK;
 }
@@ -284,6 +573,9 @@ static int build_blocks(nsg_ctx *c) {
 }
 
 static void free_block(CsrBlock &B) {
+  for (CsrBlock::Tri *T : {&B.triL, &B.triU})
+    dev_free(T->info), dev_free(T->rowid), dev_free(T->slots), dev_free(T->fsrc), dev_free(T->ra_src), dev_free(T->rows), dev_free(T->yg);
+  B.tri_ok = B.tri_pick = false;
   dev_free(B.rowptr), dev_free(B.col), dev_free(B.src), dev_free(B.diag), dev_free(B.level_rows), dev_free(B.ulevel_rows);
   dev_free(B.fval), dev_free(B.dinv);
   dev_free(B.done_l), dev_free(B.done_u), dev_free(B.ticket), dev_free(B.sf_error);
@@ -308,6 +600,15 @@ static int ilu_factor(nsg_ctx *c, CsrBlock &B, const double *parent_vals) {
                                                                      B.fval, B.dinv);
     NSG_LAUNCH_CHECK(c);
   }
+  if (B.tri_ok) {  // the same factors in the level-order layouts of the one-CTA solves
+    for (CsrBlock::Tri *T : {&B.triL, &B.triU})
+      if (T->nq > 0) {
+        k_gather_slot_factors<<<grid_for(T->nq, 256, 1 << 30), 256, 0, c->stream>>>(T->nq, T->fsrc, B.fval, reinterpret_cast<double *>(T->slots));
+        NSG_LAUNCH_CHECK(c);
+      }
+    k_gather_row_word<<<grid_for(B.n, 256, 1 << 30), 256, 0, c->stream>>>(B.n, B.triU.rowid, B.dinv, reinterpret_cast<double *>(B.triU.rows), 1);
+    NSG_LAUNCH_CHECK(c);
+  }
   return NSG_OK;
 }
 
@@ -323,7 +624,24 @@ static int precond_initialize(nsg_ctx *c) {
 
 // y = (LU)^-1 x on block-local vectors of length B.n
 static int ilu_apply(nsg_ctx *c, CsrBlock &B, double *y, const double *x) {
-  if (c->ilu_variant == 1 && B.n > 0) {
+  const int variant = c->ilu_variant >= 0 ? c->ilu_variant : (B.tri_pick ? 2 : 1);
+  if (variant == 2 && B.n > 0) {
+    if (!B.tri_ok) return fail(NSG_ERR_ARG, "the one-CTA triangular solve cannot take this block (2^28 entries or a level of more than 2 048 rows)");
+    const unsigned g = (unsigned)grid_for(B.n, 256, 1 << 30);
+    auto args = [&](const CsrBlock::Tri &T) { return TriArgs{T.n_levels, T.info, T.slots, T.rows, T.yg, (int32_t)B.n}; };
+    k_gather_row_word<<<g, 256, 0, c->stream>>>(B.n, B.triL.ra_src, x, reinterpret_cast<double *>(B.triL.rows), 0);
+    NSG_LAUNCH_CHECK(c);
+    k_ilu_solve_cta<false><<<1, TRI_THREADS, TRI_SMEM, c->stream>>>(args(B.triL));
+    NSG_LAUNCH_CHECK(c);
+    k_gather_row_word<<<g, 256, 0, c->stream>>>(B.n, B.triU.ra_src, B.triL.yg, reinterpret_cast<double *>(B.triU.rows), 0);
+    NSG_LAUNCH_CHECK(c);
+    k_ilu_solve_cta<true><<<1, TRI_THREADS, TRI_SMEM, c->stream>>>(args(B.triU));
+    NSG_LAUNCH_CHECK(c);
+    k_scatter_by_index<<<g, 256, 0, c->stream>>>(B.n, B.triU.rowid, B.triU.yg, y);
+    NSG_LAUNCH_CHECK(c);
+    return NSG_OK;
+  }
+  if (variant == 1 && B.n > 0) {
     ++B.epoch;  // 64-bit stamp: never wraps
     // rows in flight = 4 x CTAs; measured on a 51 842-row block (1 120 levels): 148 CTAs 3.55 ms, 296: 3.64, 592: 3.69,
     // 1 184: 3.93, one CTA per 4 rows: 6.0 (level-scheduled launches: 9.3)

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 pkg = importlib.import_module("navier-stokes-dealii_b200")
 from conftest import analytic_state, mesh_path
 levels = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-preconds = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2, 1]
+preconds = [int(x) for x in sys.argv[2].split(",") if x not in ("", "-")] if len(sys.argv) > 2 else [2, 1]   # "-" = time the ILU applies only
 m = pkg.Mesh.read_msh(mesh_path("square_h0.0125.msh"))
 if levels:
     m = m.refine(levels)
@@ -37,12 +37,27 @@ out["ilu_apply_A"] = {"ms": 1e3 * t_apply, "nnz": nnz_A, "algorithmic_bytes": 12
                       "GB_per_s": (12 * nnz_A + 24 * d.n_u) / t_apply / 1e9,
                       "note": "forward + backward triangular solve in natural (DoF) order as Ifpack does; one launch each, rows wait on the "
                               "completion stamps of the rows they depend on; bound by the length of the dependency chain, not by bytes"}
+out["ilu_apply_A_device_ms"] = {}
+for variant, label in ((0, "one launch per level"), (1, "stamped single launch, all SMs"), (2, "one CTA, shared-memory window"), (-1, "library's choice")):
+    dev.set_tuning(4, variant)
+    dev.time_kernel(6, 2)
+    out["ilu_apply_A_device_ms"][label] = dev.time_kernel(6, 20)
+out["ilu_apply_Mp_device_ms"] = {}
+for variant, label in ((1, "stamped single launch, all SMs"), (2, "one CTA, shared-memory window")):
+    dev.set_tuning(4, variant)
+    dev.time_kernel(7, 2)
+    out["ilu_apply_Mp_device_ms"][label] = dev.time_kernel(7, 20)
+dev.set_tuning(4, -1)
 for pc in preconds:
     dev.set_delta(np.zeros(d.n))
     t = time.perf_counter()
     its, res, rc = dev.solve(pc, 1e-6, 2000, 30, 0, check=False)
     out[{1: "block_diagonal", 2: "block_triangular"}[pc]] = {"outer_gmres_steps": int(its), "rc": int(rc), "last_residual": float(res),
                                                              "solve_s": time.perf_counter() - t, "device_ms": dev.phase_ms()["solve"]}
+if not preconds:
+    print(json.dumps(out), flush=True)
+    dev.close()
+    sys.exit(0)
 dev.set_delta(np.zeros(d.n))
 t = time.perf_counter()
 its, res, rc = dev.solve(0, 1e-6, 20000, 30, 0, check=False)

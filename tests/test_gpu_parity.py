@@ -453,17 +453,23 @@ def test_ilu0_parity(pkg, which):
     dev.close()
 
 
-def test_ilu_single_launch_solves_bitwise(pkg):
-    """Tuning key 4: the single-launch triangular solves (rows wait on completion stamps) sum each row in the same
-    order as the level-scheduled ones: identical bits, also when applied repeatedly (epoch stamps)."""
-    d, part, dev, o = _precond_system(pkg)
+@pytest.mark.parametrize("case", ["square", "cmy"])
+def test_ilu_single_launch_solves_bitwise(pkg, case):
+    """Tuning key 4: the single-launch triangular solves (1: rows wait on completion stamps; 2: one CTA walks the levels with the
+    unknowns in a shared-memory window; -1: the library's choice of the two) sum each row in the same order as the
+    level-scheduled ones: identical bits, also when applied repeatedly with changing right-hand sides (epoch stamps, reused
+    rings).  "cmy" (26 296 velocity rows, 204 levels of up to 838 rows) has columns outside the window and levels too large
+    for the rings: every path of variant 2 runs."""
+    d, part, dev, o = _precond_system(pkg, case)
     for which, n in ((0, d.n_u), (1, d.n_p)):
-        x = np.random.default_rng(7 + which).standard_normal(n)
+        xs = [np.random.default_rng(7 + which + 10 * r).standard_normal(n) for r in range(3)]
         dev.set_tuning(4, 0)
-        ref = dev.ilu_apply(which, x)
-        dev.set_tuning(4, 1)
-        for _ in range(3):
-            assert np.array_equal(dev.ilu_apply(which, x), ref)
+        refs = [dev.ilu_apply(which, x) for x in xs]
+        assert np.abs(refs[0] - o.ilu_apply(which, xs[0])).max() <= 1e-11 * np.abs(refs[0]).max()
+        for variant in (1, 2, -1):
+            dev.set_tuning(4, variant)
+            for x, ref in zip(xs, refs):
+                assert np.array_equal(dev.ilu_apply(which, x), ref), (which, variant)
     dev.close()
 
 
