@@ -207,9 +207,13 @@ k_ilu_solve_sf(const int32_t *__restrict__ rows, int64_t n, const int64_t *__res
 // and 8 inside the thread, 4, 2, 1 by shuffles): the result is bitwise the same.  Measured on the 51 842-row block
 // (1 120 + 1 120 levels), per apply: stamped solve 3.46 ms; a warp per row 3.67 ms, a thread per row 6.39 ms (one warp
 // crawling through ~1 000 dependent instructions per level), 8 lanes per row with per-group headers and cp.async
-// staging by 8 producer warps 2.0 ms (2 150 warp instructions per level on one SM).
+// staging by 8 producer warps 2.0 ms (2 150 warp instructions per level on one SM), this kernel 1.70 ms = 0.76 us per
+// level.  Tried on top of it and not kept (profiles/r02_summary.md): far unknowns prefetched into a shared-memory ring
+// by the producer warp (2.09 - 2.11 ms), the next level's records prepared before the barrier with 24 compute warps
+// (2.47 ms), rows and slots in one stream with a single bulk copy per level (3.04 ms).
 constexpr int TRI_W = 8192, TRI_RQ = 8192, TRI_RK = 1024;
-constexpr int TRI_CW = 12, TRI_THREADS = 32 * (TRI_CW + 1);  // compute warps + the producer warp
+constexpr int TRI_CW = 20, TRI_MAX_THREADS = 1024;  // compute warps (the launch adds the producer warp; NSG_TRI_CW overrides);
+                                                     // measured 6 / 8 / 12 / 16 / 20 / 24 / 31 warps: 2.33 / 2.12 / 1.87 / 1.87 / 1.70 / 1.73 / 1.75 ms
 constexpr int TRI_DEPTH = 4;                                 // levels the producer runs ahead (a power of two)
 constexpr int TRI_FLUSH = 512, TRI_MAX_LEVEL_ROWS = 2048;    // write-out granularity; widest level the window can take
 constexpr size_t TRI_SMEM = sizeof(double) * TRI_W + 16 * (size_t)(TRI_RQ + TRI_RK);
@@ -293,20 +297,22 @@ __device__ __forceinline__ void tri_group(const TriArgs &A, uint32_t sm_y, uint3
   }
 }
 template <bool UPPER, bool STAGED, int S>
-__device__ __forceinline__ void tri_level(const TriArgs &A, uint32_t sm_y, uint32_t sm_slots, uint32_t sm_rows, const int4 lv, int warp, int lane) {
+__device__ __forceinline__ void tri_level(const TriArgs &A, uint32_t sm_y, uint32_t sm_slots, uint32_t sm_rows, const int4 lv, int warp, int lane,
+                                          int n_warps) {
   const int n_slabs = lv.y & 0xffff, rows_in_level = lv.w - lv.z;
-  for (int gi = warp; 4 * gi < rows_in_level; gi += TRI_CW)
+  for (int gi = warp; 4 * gi < rows_in_level; gi += n_warps)
     tri_group<UPPER, STAGED, S>(A, sm_y, sm_slots, sm_rows, lv.x + gi * n_slabs * 32, n_slabs, lv.z + 4 * gi, min(4, rows_in_level - 4 * gi), lane);
 }
 template <bool UPPER>
-__global__ void __launch_bounds__(TRI_THREADS, 1) k_ilu_solve_cta(const TriArgs A) {
+__global__ void __launch_bounds__(TRI_MAX_THREADS, 1) k_ilu_solve_cta(const TriArgs A) {
   extern __shared__ __align__(16) unsigned char tri_smem[];
   __shared__ int4 s_info[2 * TRI_DEPTH];  // {first slot, slabs | staged << 16, first position, one past the last position}
   __shared__ __align__(8) unsigned long long s_full[TRI_DEPTH];  // mbarriers: the copies of a level have landed
   const uint32_t sm_y = smem_addr_u32(tri_smem), sm_slots = sm_y + 8u * TRI_W, sm_rows = sm_slots + 16u * TRI_RQ;
   double *s_y = reinterpret_cast<double *>(tri_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = tid == 32 * TRI_CW;  // lane 0 of the last warp
+  const int cw = (int)(blockDim.x >> 5) - 1;  // compute warps
+  const bool producer = tid == 32 * cw;       // lane 0 of the last warp
   if (producer) {
     for (int i = 0; i < TRI_DEPTH; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(s_full + i)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) k_ilu_solve_cta(const TriArgs 
       parities ^= 1u << st;
     }
     __syncthreads();  // ... and so have the unknowns of level l - 1; the rings of level l - 1 are free
-    if (warp == TRI_CW) {
+    if (warp == cw) {
       if (producer) {
         const int final_below = s_info[l & (2 * TRI_DEPTH - 1)].z & ~1;  // the levels before l are complete
         if (final_below - flushed >= TRI_FLUSH) flush(final_below);
@@ -369,8 +375,8 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) k_ilu_solve_cta(const TriArgs 
       const int S = min(lv.y & 0xffff, 5);
 #define NSG_TRI_CASE(n)                                                              \
   case n:                                                                            \
-    if (lv.y >> 16) tri_level<UPPER, true, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane); \
-    else tri_level<UPPER, false, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane);     \
+    if (lv.y >> 16) tri_level<UPPER, true, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane, cw); \
+    else tri_level<UPPER, false, n>(A, sm_y, sm_slots, sm_rows, lv, warp, lane, cw);     \
     break;
       switch (S) {
         NSG_TRI_CASE(0)
@@ -523,8 +529,10 @@ static int build_block(nsg_ctx *c, CsrBlock &B, const std::vector<int64_t> &rp, 
         in_place += info[l].z ? 0 : 1;
       }
       T.n_levels = nl, T.nq = (int64_t)slots.size();
-      // ~0.3 us per staged level, an L2 round trip more per level read in place, 16 bytes per slot through one SM
-      t_cta += 0.3e-6 * nl + 0.5e-6 * in_place + 16.0 * (double)slots.size() / 60e9;
+      // measured: ~0.35 us per staged level + ~0.4 us per pass of the compute warps over its groups (0.76 us per level on
+      // the 51 842-row block), L2 round trips more per level read in place, 16 bytes per slot through one SM
+      for (int32_t l = 0; l < nl; ++l) t_cta += 0.35e-6 + 0.4e-6 * ((ptr[l + 1] - ptr[l] + 4 * TRI_CW - 1) / (4 * TRI_CW));
+      t_cta += 1.5e-6 * in_place + 16.0 * (double)slots.size() / 60e9;
       slots.push_back(make_int4(0, 0, 0, 0)), fsrc.push_back(-1);
       NSG_TRY(upload(c, &T.info, info.data(), nl + 1));
       NSG_TRY(upload(c, &T.slots, slots.data(), (int64_t)slots.size()));
@@ -543,7 +551,7 @@ static int build_block(nsg_ctx *c, CsrBlock &B, const std::vector<int64_t> &rp, 
     NSG_CUDA(cudaFuncSetAttribute(k_ilu_solve_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_SMEM));
     NSG_CUDA(cudaFuncSetAttribute(k_ilu_solve_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_SMEM));
     B.tri_ok = true;
-    B.tri_pick = t_cta < 1.6e-6 * (nL + nU);  // stamped single launch: ~1.6 us per level (profiles/r02_summary.md)
+    B.tri_pick = t_cta < 1.55e-6 * (nL + nU);  // stamped single launch: ~1.55 us per level (profiles/r02_summary.md)
   }
   NSG_CUDA(cudaStreamSynchronize(c->stream));
   return NSG_OK;
@@ -628,14 +636,16 @@ static int ilu_apply(nsg_ctx *c, CsrBlock &B, double *y, const double *x) {
   if (variant == 2 && B.n > 0) {
     if (!B.tri_ok) return fail(NSG_ERR_ARG, "the one-CTA triangular solve cannot take this block (2^28 entries or a level of more than 2 048 rows)");
     const unsigned g = (unsigned)grid_for(B.n, 256, 1 << 30);
+    static const int tri_cw = std::getenv("NSG_TRI_CW") ? std::min(31, std::max(1, std::atoi(std::getenv("NSG_TRI_CW")))) : TRI_CW;
+    const unsigned tri_threads = 32u * (unsigned)(tri_cw + 1);
     auto args = [&](const CsrBlock::Tri &T) { return TriArgs{T.n_levels, T.info, T.slots, T.rows, T.yg, (int32_t)B.n}; };
     k_gather_row_word<<<g, 256, 0, c->stream>>>(B.n, B.triL.ra_src, x, reinterpret_cast<double *>(B.triL.rows), 0);
     NSG_LAUNCH_CHECK(c);
-    k_ilu_solve_cta<false><<<1, TRI_THREADS, TRI_SMEM, c->stream>>>(args(B.triL));
+    k_ilu_solve_cta<false><<<1, tri_threads, TRI_SMEM, c->stream>>>(args(B.triL));
     NSG_LAUNCH_CHECK(c);
     k_gather_row_word<<<g, 256, 0, c->stream>>>(B.n, B.triU.ra_src, B.triL.yg, reinterpret_cast<double *>(B.triU.rows), 0);
     NSG_LAUNCH_CHECK(c);
-    k_ilu_solve_cta<true><<<1, TRI_THREADS, TRI_SMEM, c->stream>>>(args(B.triU));
+    k_ilu_solve_cta<true><<<1, tri_threads, TRI_SMEM, c->stream>>>(args(B.triU));
     NSG_LAUNCH_CHECK(c);
     k_scatter_by_index<<<g, 256, 0, c->stream>>>(B.n, B.triU.rowid, B.triU.yg, y);
     NSG_LAUNCH_CHECK(c);
