@@ -4,6 +4,8 @@ uniformly refined cylinder mesh, N GPUs of one node (one process per GPU).
 
   python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference ...                      # the CPU oracle port on the host cores
+  python bench.py --precond block_diagonal                  # opt-in: the CONVERGED preconditioned solve of BASELINE.json configs[1]
+                                                            # (one GPU, ~80 s, its own JSON line; see run_precond)
 
 A "step" = zero-free owner-computes assembly of J, Mp, R (+ Neumann) + Dirichlet rows + ||R|| +
 GMRES(28, identity) capped at --gmres-its steps (the synthetic state does not converge with an
@@ -260,6 +262,80 @@ def workload_config(args, d):
     return cfg
 
 
+def run_precond(args):
+    """--precond: BASELINE.json configs[1] at its stated size - mesh-square-h0.012500.msh (12 800 cells, 58 403 DoFs), Stokes-initialised
+    steady Navier-Stokes through the reference's block preconditioners (hpp:520-639), the largest repo mesh on which the reference's
+    own inner-solver settings converge (profiles/r02_summary.md section 6).  One GPU.  Prints ONE JSON line of its own: the converged
+    "GMRES time per Newton step" VERDICT r1 asked for beside the capped identity figure of the default run, with the ILU(0) apply
+    (the kernel that bounds it) timed on the device for every triangular-solve variant and put against the HBM roofline."""
+    import importlib
+    import torch
+    pkg = importlib.import_module("navier-stokes-dealii_b200")
+    torch.cuda.set_device(0)
+    prm = pkg.Parameters(mesh_path=os.path.join(ROOT, "tests", "golden", "square_h0.0125.msh"), nu=0.05, H=1.0, inlet_time_mode="constant",
+                         neumann_id=1, inlet_id=0, wall_ids=(2, 3), clear_inlet_before_walls=True, use_mass=False,
+                         preconditioner=args.precond, p_out=0.0, increment_bc="consistent", newton_max_iters=8)
+    mesh = pkg.Mesh.read_msh(prm.mesh_path, prm.surface_entity)
+    s = pkg.NavierStokesSolver(2, 1, 1.0, 1.0, prm, verbose=False)
+    t0 = time.perf_counter()
+    s.setup(mesh)
+    setup_s = time.perf_counter() - t0
+    dev = s.dev
+    solves = []
+    plain_solve = dev.solve
+
+    def timed_solve(*a, **k):
+        t = time.perf_counter()
+        out = plain_solve(*a, **k)
+        solves.append({"outer_gmres_steps": int(out[0]), "inner_iterations": dev.last_inner_iterations(),
+                       "device_ms": dev.phase_ms()["solve"], "wall_ms": 1e3 * (time.perf_counter() - t)})
+        return out
+    dev.solve = timed_solve
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    error = None
+    try:
+        s.solve(stokes_init=True)
+    except Exception as e:  # noqa: BLE001  (e.g. the inner CG of the block-triangular preconditioner does not converge on this system)
+        error = f"{type(e).__name__}: {e}"
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    hbm, hbm_src = peaks()
+    d = s.dofs
+    rp, cl = dev.get_pattern()[:2]
+    n_u, n_p = int(d.n_u), int(d.n_p)
+    nnz_A = int((cl[: rp[n_u]] < n_u).sum())
+    ilu = {}
+    for variant, label in ((0, "one launch per level"), (1, "stamped single launch, all SMs"), (2, "one CTA, shared-memory window"),
+                           (-1, "library's choice")):
+        dev.set_tuning(4, variant)
+        dev.time_kernel(6, 2)
+        ilu[label] = {"A_ms": dev.time_kernel(6, 20), "Mp_ms": dev.time_kernel(7, 20)}
+    dev.set_tuning(4, -1)
+    a_ms = ilu["library's choice"]["A_ms"]
+    a_bytes = 12 * nnz_A + 24 * n_u   # factors + column indices once, right-hand side, unknowns
+    inner = sum(x["inner_iterations"] for x in solves)
+    line = {"metric": "preconditioned_newton_solve_s", "value": wall, "unit": "s", "n_gpus": 1, "higher_is_better": False, "dtype": "f64",
+            "data": "the reference's own mesh", "impl": "b200",
+            "error": error,
+            "config": {"workload": "BASELINE.json configs[1]: mesh-square-h0.012500.msh, Stokes-initialised steady Navier-Stokes, nu = 0.05, "
+                                   "reference tolerances (outer GMRES 1e-2, inner 1e-2, cpp:566, hpp:541-612)",
+                       "preconditioner": args.precond, "cells": int(mesh.n_cells), "dofs": int(d.n)},
+            "newton_history": [[int(a), int(b), float(c), None if e is None else int(e)] for a, b, c, e in s.history],
+            "solves": solves, "gmres_ms_per_newton_step": float(np.mean([x["device_ms"] for x in solves])) if solves else None,
+            "inner_iterations_total": inner, "ilu_applies_share_of_solve_time_upper_bound":
+                (inner * a_ms) / max(sum(x["device_ms"] for x in solves), 1e-9),
+            "ilu_apply_device_ms": ilu, "setup_s": setup_s, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_ilu_solve_cta<lower> + <upper> (ILU(0) apply of the velocity block)",
+                         "achieved": a_bytes / a_ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": a_bytes / a_ms / 1e6 / hbm, "traffic": None,
+                         "peak_source": hbm_src, "algorithmic_bytes_per_launch": a_bytes, "ms_per_launch": a_ms,
+                         "note": "a dependency chain of 1 120 + 1 120 levels of ~46 rows: bound by the latency of a level (0.76 us), not by "
+                                 "bytes - the HBM fraction is reported for completeness"}}
+    print(json.dumps(line), flush=True)
+    dev.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,7 +354,11 @@ def main():
     ap.add_argument("--time-step", dest="deltat", type=float, default=0.05, help="time step (reference main.cpp:13; configs[4]: small)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-patterns", action="store_true", help="build the sparsity patterns on the host (libnst) and upload them")
+    ap.add_argument("--precond", default=None, choices=["block_triangular", "block_diagonal"],
+                    help="instead of the default run: the converged preconditioned solve of BASELINE.json configs[1] (one GPU, own JSON line)")
     args = ap.parse_args()
+    if args.precond:
+        return run_precond(args)
     if args.cpu_level is None:
         args.cpu_level = {"cmy": 2, "mesh2d": 4}[args.mesh]
     if args.scaling == "weak":      # cells per GPU: 1x, 1/2x, 1x, 1/2x of the 1-GPU mesh at N = 1, 2, 4, 8

@@ -146,6 +146,9 @@ int64_t nsg_gmres_history(nsg_ctx *ctx, double *out, int64_t cap);
  * out4[2] = SpMV kernel variant used by the operator (tuning key 0; -1 for the cooperative kernel, which has its own);
  * out4[3] = Gram-Schmidt variant (tuning key 3). */
 int nsg_last_solve_info(nsg_ctx *ctx, int32_t *out4);
+/* Iterations the inner CG / GMRES solvers of a block preconditioner (hpp:541-551, 598-612) took during the last nsg_solve, summed
+ * over its applications (each inner iteration is one ILU(0) apply); 0 for the identity. Returns the count. */
+int64_t nsg_last_inner_iterations(nsg_ctx *ctx);
 
 /* solution_owned += delta_owned; solution = solution_owned (cpp:616-618). */
 int nsg_update_solution(nsg_ctx *ctx);

@@ -142,6 +142,7 @@ _NSG_SIGS = {
     "nsg_solve": (C.c_int, [vp, i32, C.c_double, i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_double)]),
     "nsg_gmres_history": (i64, [vp, _opt(f64p), i64]),
     "nsg_last_solve_info": (C.c_int, [vp, i32p]),
+    "nsg_last_inner_iterations": (i64, [vp]),
     "nsg_update_solution": (C.c_int, [vp]),
     "nsg_push_time_level": (C.c_int, [vp]),
     "nsg_set_solution": (C.c_int, [vp, f64p]),

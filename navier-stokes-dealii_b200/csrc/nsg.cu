@@ -1671,6 +1671,8 @@ int nsg_last_solve_info(nsg_ctx *c, int32_t *out4) {
   return NSG_OK;
 }
 
+int64_t nsg_last_inner_iterations(nsg_ctx *c) { return c ? c->inner_its : 0; }
+
 int64_t nsg_gmres_history(nsg_ctx *c, double *out, int64_t cap) {
   if (!c) return 0;
   const int64_t n = std::min<int64_t>(cap, (int64_t)c->h_hist.size());

@@ -132,6 +132,10 @@ class DeviceProblem:
         nsg_check(self._L.nsg_last_solve_info(self._h, out))
         return {"fused": bool(out[0]), "graph_replays": int(out[1]), "spmv_variant": int(out[2]), "orthogonalization": int(out[3])}
 
+    def last_inner_iterations(self):
+        """Inner CG / GMRES iterations (= ILU(0) applies) of the block preconditioner during the last solve()."""
+        return int(self._L.nsg_last_inner_iterations(self._h))
+
     def get_pattern(self):
         """(jac_rowptr, jac_col, pm_rowptr, pm_col) as the device holds them."""
         rp, prp = np.zeros(self.n_own + 1, np.int64), np.zeros(self.n_own + 1, np.int64)
