@@ -105,6 +105,7 @@ struct Ctx {
   // block-Jacobi extents for the ILU(0) preconditioners (one range per virtual rank)
   std::vector<int64_t> u_off{0}, p_off{0};
   std::vector<double> gmres_hist;  // residual estimate after every GMRES step of the last solve
+  int64_t last_inner_its = 0;      // inner CG / GMRES iterations of the block preconditioner during the last solve
 };
 
 inline int64_t find_col(const Ctx &c, const std::vector<int64_t> &rp, const std::vector<int32_t> &cl,
@@ -686,6 +687,7 @@ int orc_solve(void *h, int precond, double rel_tol, int max_it, int n_tmp, int t
   Csr Ab, Mb, Bb;
   Ilu0 ilu_a, ilu_m;
   bool inner_fail = false;
+  int64_t inner_its = 0;  // iterations of the inner solvers, summed over the applications of the preconditioner
   Op Pinv;
   if (precond == 0) {
     Pinv = [c](double *y, const double *x) { std::memcpy(y, x, sizeof(double) * c->N); };
@@ -701,20 +703,22 @@ int orc_solve(void *h, int precond, double rel_tol, int max_it, int n_tmp, int t
     Op Ia = [&ilu_a](double *y, const double *x) { ilu_a.apply(y, x); };
     Op Im = [&ilu_m](double *y, const double *x) { ilu_m.apply(y, x); };
     if (precond == 1)
-      Pinv = [=, &inner_fail](double *y, const double *x) {
+      Pinv = [=, &inner_fail, &inner_its](double *y, const double *x) {
         const Layout Lu{nu, nu}, Lp{np, np};
         SolveResult r0 = gmres(Lu, Aop, Ia, y, x, 1e-2 * norm(Lu, x), 1000, 30, nullptr);
         SolveResult r1 = gmres(Lp, Mop, Im, y + nu, x + nu, 1e-2 * norm(Lp, x + nu), 1000, 30, nullptr);
+        inner_its += r0.its + r1.its;
         if (!r0.ok || !r1.ok) inner_fail = true;
       };
     else
-      Pinv = [=, &Bb, &inner_fail](double *y, const double *x) {
+      Pinv = [=, &Bb, &inner_fail, &inner_its](double *y, const double *x) {
         const Layout Lu{nu, nu}, Lp{np, np};
         SolveResult r0 = cg(Lu, Aop, Ia, y, x, 1e-2 * norm(Lu, x), 2000);
         Vec tmp(np);
         Bb.vmult(tmp.data(), y);
         for (int64_t i = 0; i < np; ++i) tmp[i] = -tmp[i] + x[nu + i];  // tmp.sadd(-1, src1)
         SolveResult r1 = cg(Lp, Mop, Im, y + nu, tmp.data(), 1e-2 * norm(Lp, x + nu), 2000);
+        inner_its += r0.its + r1.its;
         if (!r0.ok || !r1.ok) inner_fail = true;
       };
   }
@@ -723,10 +727,12 @@ int orc_solve(void *h, int precond, double rel_tol, int max_it, int n_tmp, int t
   SolveResult r = gmres(L, A, Pinv, x.data(), c->R.data(), tol, max_it, n_tmp, &c->gmres_hist);
   if (its) *its = r.its;
   if (res) *res = r.res;
+  c->last_inner_its = inner_its;
   if (target) c->sol = c->sol_owned;  // cpp:556
   if (inner_fail) return 2;
   return r.ok ? 0 : 1;
 }
+int64_t orc_last_inner_iterations(void *h) { return ((Ctx *)h)->last_inner_its; }
 int64_t orc_gmres_history(void *h, double *out, int64_t cap) {
   Ctx *c = (Ctx *)h;
   const int64_t n = std::min<int64_t>(cap, (int64_t)c->gmres_hist.size());

@@ -33,6 +33,8 @@ def lib():
         L.orc_spmv.argtypes = [vp, f64p, f64p]
         L.orc_solve.restype = C.c_int
         L.orc_solve.argtypes = [vp, C.c_int, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(dbl)]
+        L.orc_last_inner_iterations.restype = i64
+        L.orc_last_inner_iterations.argtypes = [vp]
         L.orc_gmres_history.restype = i64
         L.orc_gmres_history.argtypes = [vp, f64p, i64]
         for n in ("orc_update_solution", "orc_push_time_level"):
@@ -97,6 +99,9 @@ class Oracle:
         its, res = C.c_int(), C.c_double()
         rc = self._L.orc_solve(self._h, precond, rel_tol, max_it, n_tmp, target, C.byref(its), C.byref(res))
         return its.value, res.value, rc
+
+    def last_inner_iterations(self):
+        return int(self._L.orc_last_inner_iterations(self._h))
 
     def gmres_history(self):
         n = self._L.orc_gmres_history(self._h, np.zeros(1), 0)

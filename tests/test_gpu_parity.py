@@ -482,6 +482,9 @@ def test_block_preconditioned_gmres_parity(pkg, precond):
     rd = dev.solve(precond, 1e-6, 2000, 30, 0)
     ro = o.solve(precond, 1e-6, 2000, 30, 0)
     assert rd[2] == ro[2] == 0 and rd[0] == ro[0], (rd, ro)
+    # the inner solvers (hpp:541-551, 598-612) take the same number of iterations = ILU(0) applies, summed over the solve
+    ni_d, ni_o = dev.last_inner_iterations(), o.last_inner_iterations()
+    assert ni_d > rd[0] and abs(ni_d - ni_o) <= max(2, ni_o // 200), (ni_d, ni_o)
     h1, h2 = dev.gmres_history(), o.gmres_history()
     assert np.abs(h1 / h2 - 1).max() <= 1e-6
     xd, xo = dev.get_delta(), o.get_delta()
