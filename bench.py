@@ -35,10 +35,20 @@ MESHES = {  # name -> (file, surface entity, geometric tags?, Dirichlet calls, n
 
 
 def analytic_state(xy, n_u):
+    """Synthetic iterate u = (sin(pi x) cos(pi y), -cos(pi x) sin(pi y)), p = x y at the support points (85 M of them at the default
+    size: evaluated with torch's multi-threaded CPU kernels when torch is there, numpy otherwise)."""
     sol = np.zeros(len(xy))
-    sol[0:n_u:2] = np.sin(np.pi * xy[0:n_u:2, 0]) * np.cos(np.pi * xy[0:n_u:2, 1])
-    sol[1:n_u:2] = -np.cos(np.pi * xy[1:n_u:2, 0]) * np.sin(np.pi * xy[1:n_u:2, 1])
-    sol[n_u:] = xy[n_u:, 0] * xy[n_u:, 1]
+    torch = sys.modules.get("torch")  # only if the caller has it loaded already (the CPU-baseline workers do not)
+    if torch is not None:
+        t, out = torch.from_numpy(xy), torch.from_numpy(sol)
+        x0, y0, x1, y1 = t[0:n_u:2, 0], t[0:n_u:2, 1], t[1:n_u:2, 0], t[1:n_u:2, 1]
+        out[0:n_u:2] = torch.sin(np.pi * x0) * torch.cos(np.pi * y0)
+        out[1:n_u:2] = -torch.cos(np.pi * x1) * torch.sin(np.pi * y1)
+        out[n_u:] = t[n_u:, 0] * t[n_u:, 1]
+    else:
+        sol[0:n_u:2] = np.sin(np.pi * xy[0:n_u:2, 0]) * np.cos(np.pi * xy[0:n_u:2, 1])
+        sol[1:n_u:2] = -np.cos(np.pi * xy[1:n_u:2, 0]) * np.sin(np.pi * xy[1:n_u:2, 1])
+        sol[n_u:] = xy[n_u:, 0] * xy[n_u:, 1]
     return sol
 
 
