@@ -147,9 +147,9 @@ const int32_t *nst_part_cell_dofs(const nst_part *p);    /* [15 n_cells] local d
 const int32_t *nst_part_cell_vertices(const nst_part *p);/* [3 n_cells] local vertex ids */
 const double *nst_part_xy(const nst_part *p);            /* [2 n_vertices] */
 const uint8_t *nst_part_cell_owned(const nst_part *p);   /* [n_cells] 1 if the cell is owned by rank */
-const int64_t *nst_part_jac_rowptr(const nst_part *p);   /* [n_own+1] */
+const int64_t *nst_part_jac_rowptr(const nst_part *p);   /* [n_own+1]; NULL for a part built with NST_PART_NO_PATTERNS */
 const int32_t *nst_part_jac_col(const nst_part *p);      /* local column ids, ascending */
-const int64_t *nst_part_pm_rowptr(const nst_part *p);    /* [n_own+1], rows < n_own_u empty */
+const int64_t *nst_part_pm_rowptr(const nst_part *p);    /* [n_own+1], rows < n_own_u empty; NULL with NST_PART_NO_PATTERNS */
 const int32_t *nst_part_pm_col(const nst_part *p);
 /* halo plan: neighbours in ascending rank; send_idx are local owned indices to pack for
  * neighbour k in [send_ptr[k],send_ptr[k+1]); recv for neighbour k lands contiguously at

@@ -51,18 +51,6 @@ struct nst_mesh {
   int64_t n_inverted = 0, n_boundary = 0;
 };
 
-struct nst_dofs {
-  int64_t n_u = 0, n_p = 0;
-  int n_parts = 1;
-  std::vector<int32_t> cell_dofs;    // [15T]
-  std::vector<int32_t> vertex_node;  // [V]
-  std::vector<int32_t> edge_node;    // [E]
-  std::vector<int32_t> vertex_p;     // [V]
-  std::vector<int32_t> vertex_owner, edge_owner;
-  std::vector<int64_t> part_n_u, part_n_p;  // owned counts
-  std::vector<int64_t> u_off, p_off;        // prefix sums (n_parts+1)
-};
-
 // vector whose resize() leaves new elements uninitialised: the column arrays of the patterns (hundreds of millions of
 // entries) are filled by the OpenMP loop right after; value-initialising them first was a serial 0.7 s per 160 M entries
 template <class T>
@@ -82,10 +70,23 @@ struct DefaultInitAlloc : std::allocator<T> {
 };
 using ColVec = std::vector<int32_t, DefaultInitAlloc<int32_t>>;
 
+struct nst_dofs {
+  int64_t n_u = 0, n_p = 0;
+  int n_parts = 1;
+  ColVec cell_dofs;                  // [15T] (1.1 GB at the bench size: first touched by the parallel loop that fills it)
+  std::vector<int32_t> vertex_node;  // [V]
+  std::vector<int32_t> edge_node;    // [E]
+  std::vector<int32_t> vertex_p;     // [V]
+  std::vector<int32_t> vertex_owner, edge_owner;
+  std::vector<int64_t> part_n_u, part_n_p;  // owned counts
+  std::vector<int64_t> u_off, p_off;        // prefix sums (n_parts+1)
+};
+
 struct nst_part {
   nst_part_info info{};
-  std::vector<int64_t> l2g;
-  std::vector<int32_t> cell_ids, cell_dofs, cell_vertices;
+  std::vector<int64_t, DefaultInitAlloc<int64_t>> l2g;
+  std::vector<int32_t> cell_ids;
+  ColVec cell_dofs, cell_vertices;
   std::vector<double> xy;
   std::vector<uint8_t> cell_owned;
   std::vector<int64_t> jac_rowptr, pm_rowptr;
@@ -114,14 +115,127 @@ inline int64_t find_slot(const std::vector<int64_t> &off, const std::vector<int3
   return p - his.data();
 }
 
+// ---- "number by first appearance", in parallel ------------------------------------------------------------------
+// deal.II numbers lines, vertices and DoFs in the order a cell loop first meets them.  A serial loop does that in one
+// pass; with 57 M (cell, line) slots per mesh level it was most of the set-up time.  The same numbers without the loop:
+// every entity records the SMALLEST slot position that refers to it (atomic min); a slot is a first appearance iff it is
+// that position; the entity's number is the count of first appearances before its slot (one scan).
+inline void atomic_min(int64_t *addr, int64_t v) {
+  int64_t cur = __atomic_load_n(addr, __ATOMIC_RELAXED);
+  while (v < cur && !__atomic_compare_exchange_n(addr, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+}
+inline void atomic_min32(int32_t *addr, int32_t v) {
+  int32_t cur = __atomic_load_n(addr, __ATOMIC_RELAXED);
+  while (v < cur && !__atomic_compare_exchange_n(addr, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+}
+struct Tracer {  // NST_TRACE=1: wall time of the stages of the big set-up functions on stderr
+  const char *fn;
+  double t;
+  bool on;
+  explicit Tracer(const char *f) : fn(f), t(0), on(std::getenv("NST_TRACE") != nullptr) {
+#ifdef _OPENMP
+    t = omp_get_wtime();
+#endif
+  }
+  void mark(const char *what) {
+#ifdef _OPENMP
+    if (on) {
+      const double now = omp_get_wtime();
+      std::fprintf(stderr, "[nst trace] %s: %s %.3f s\n", fn, what, now - t);
+      t = now;
+    }
+#endif
+  }
+};
+inline int n_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+// Calls visit(pos, rank) for every position pos in [p0, p1) with is_first(pos), in ascending order of pos inside a chunk,
+// where rank = rank0 + number of first positions in [p0, pos).  Returns rank0 + their total number.
+template <class IsFirst, class Visit>
+int64_t rank_first_positions(int64_t p0, int64_t p1, int64_t rank0, IsFirst is_first, Visit visit) {
+  const int nt = n_threads();
+  const int64_t n = p1 - p0, chunk = (n + nt - 1) / std::max(nt, 1);
+  std::vector<int64_t> cnt(nt + 1, 0);
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < nt; ++t) {
+    int64_t k = 0;
+    for (int64_t p = p0 + t * chunk, e = std::min(p1, p + chunk); p < e; ++p) k += is_first(p) ? 1 : 0;
+    cnt[t + 1] = k;
+  }
+  for (int t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < nt; ++t) {
+    int64_t r = rank0 + cnt[t];
+    for (int64_t p = p0 + t * chunk, e = std::min(p1, p + chunk); p < e; ++p)
+      if (is_first(p)) visit(p, r++);
+  }
+  return rank0 + cnt[nt];
+}
+
+// Numbers the E unique edges ("slots") of m->cells by first appearance in (cell, local line) order and fills cell_edges,
+// edge_v (orientation of the first cell that sees the edge) and edge_nc.  slot_of[3c + l] = slot of line l of cell c.
+int number_edges(nst_mesh *m, const std::vector<int32_t> &slot_of, std::vector<int32_t> &slot_id) {
+  const int64_t T = m->T, E = m->E;
+  std::vector<int32_t> n_cells_of(E, 0);
+  std::vector<int64_t> first_pos(E, INT64_MAX);
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < 3 * T; ++p) {
+    const int32_t s = slot_of[p];
+    atomic_min(&first_pos[s], p);
+#pragma omp atomic
+    n_cells_of[s]++;
+  }
+  int64_t too_many = 0;
+#pragma omp parallel for reduction(+ : too_many) schedule(static)
+  for (int64_t s = 0; s < E; ++s) too_many += n_cells_of[s] > 2 ? 1 : 0;
+  if (too_many) {  // report the edge the cell loop would have stumbled over first
+    std::vector<uint8_t> seen(E, 0);
+    for (int64_t p = 0; p < 3 * T; ++p)
+      if (++seen[slot_of[p]] == 3) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "edge (%d,%d) is shared by more than two cells (overlapping surface entities?)",
+                 m->cells[p], m->cells[3 * (p / 3) + (p % 3 + 1) % 3]);
+        return fail(NST_ERR_TOPOLOGY, buf);
+      }
+  }
+  slot_id.assign(E, -1);
+  m->cell_edges.resize(3 * T);
+  m->edge_v.resize(2 * E);
+  m->edge_nc.assign(E, 0);
+  rank_first_positions(
+      0, 3 * T, 0, [&](int64_t p) { return first_pos[slot_of[p]] == p; },
+      [&](int64_t p, int64_t id) {
+        const int64_t c = p / 3;
+        const int l = (int)(p % 3);
+        slot_id[slot_of[p]] = (int32_t)id;
+        m->edge_v[2 * id] = m->cells[3 * c + l];  // orientation of the first cell that sees the edge
+        m->edge_v[2 * id + 1] = m->cells[3 * c + (l + 1) % 3];
+        m->edge_nc[id] = (uint8_t)n_cells_of[slot_of[p]];
+      });
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < 3 * T; ++p) m->cell_edges[p] = slot_id[slot_of[p]];
+  return NST_OK;
+}
+
 int build_mesh(int64_t V, const double *xy, int64_t T, const int32_t *cells, int64_t n_lines,
                const Line *lines, nst_mesh *m) {
+  Tracer tr("build_mesh");
+  auto mark = [&](const char *w) { tr.mark(w); };
   m->V = V;
   m->T = T;
   m->xy.assign(xy, xy + 2 * V);
   m->cells.assign(cells, cells + 3 * T);
-  for (int64_t i = 0; i < 3 * T; ++i)
-    if (cells[i] < 0 || cells[i] >= V) return fail(NST_ERR_ARG, "cell vertex index out of range");
+  int64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+  for (int64_t i = 0; i < 3 * T; ++i) bad += (cells[i] < 0 || cells[i] >= V) ? 1 : 0;
+  if (bad) return fail(NST_ERR_ARG, "cell vertex index out of range");
   // Negative-measure cells are inverted by swapping vertices 1 and 2.
   int64_t ninv = 0;
 #pragma omp parallel for reduction(+ : ninv) schedule(static)
@@ -135,26 +249,37 @@ int build_mesh(int64_t V, const double *xy, int64_t T, const int32_t *cells, int
     }
   }
   m->n_inverted = ninv;
+  mark("copy+orient");
 
   // unique edges: bucket half-edges by their lower vertex, dedupe per vertex, then number
   // by first appearance in (cell, local line) order: line 0=(v0,v1) 1=(v1,v2) 2=(v2,v0).
   std::vector<int64_t> off(V + 1, 0);
+#pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < T; ++c) {
     const int32_t *v = &m->cells[3 * c];
-    for (int l = 0; l < 3; ++l) off[std::min(v[l], v[(l + 1) % 3]) + 1]++;
+    for (int l = 0; l < 3; ++l) {
+#pragma omp atomic
+      off[std::min(v[l], v[(l + 1) % 3]) + 1]++;
+    }
   }
   for (int64_t i = 0; i < V; ++i) off[i + 1] += off[i];
+  mark("histogram");
   std::vector<int32_t> his(off[V]);
   {
     std::vector<int64_t> pos(off.begin(), off.end() - 1);
+#pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < T; ++c) {
       const int32_t *v = &m->cells[3 * c];
       for (int l = 0; l < 3; ++l) {
         const int32_t a = v[l], b = v[(l + 1) % 3];
-        his[pos[std::min(a, b)]++] = std::max(a, b);
+        int64_t at;
+#pragma omp atomic capture
+        at = pos[std::min(a, b)]++;
+        his[at] = std::max(a, b);  // the order inside a bucket does not matter: sorted below
       }
     }
   }
+  mark("fill");
   // sort + unique per vertex (compacting in place)
   std::vector<int64_t> uoff(V + 1, 0);
 #pragma omp parallel for schedule(dynamic, 4096)
@@ -170,38 +295,29 @@ int build_mesh(int64_t V, const double *xy, int64_t T, const int32_t *cells, int
     std::copy(his.data() + off[i], his.data() + off[i] + (uoff[i + 1] - uoff[i]), uhis.data() + uoff[i]);
   his.clear();
   his.shrink_to_fit();
+  mark("sort+unique+copy");
   const int64_t E = uoff[V];
+  if (E > (int64_t)INT32_MAX) return fail(NST_ERR_ARG, "more than 2^31-1 edges");
   m->E = E;
-  std::vector<int32_t> slot_id(E, -1);
-  m->cell_edges.resize(3 * T);
-  m->edge_v.resize(2 * E);
-  m->edge_nc.assign(E, 0);
-  int32_t next = 0;
+  // slot of every (cell, line) position
+  std::vector<int32_t> slot_of(3 * (size_t)T);
+#pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < T; ++c) {
     const int32_t *v = &m->cells[3 * c];
     for (int l = 0; l < 3; ++l) {
       const int32_t a = v[l], b = v[(l + 1) % 3];
-      const int64_t s = find_slot(uoff, uhis, std::min(a, b), std::max(a, b));
-      if (slot_id[s] < 0) {
-        slot_id[s] = next;
-        m->edge_v[2 * next] = a;
-        m->edge_v[2 * next + 1] = b;
-        ++next;
-      }
-      const int32_t e = slot_id[s];
-      m->cell_edges[3 * c + l] = e;
-      if (m->edge_nc[e] == 2) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "edge (%d,%d) is shared by more than two cells (overlapping surface entities?)",
-                 a, b);
-        return fail(NST_ERR_TOPOLOGY, buf);
-      }
-      m->edge_nc[e]++;
+      slot_of[3 * c + l] = (int32_t)find_slot(uoff, uhis, std::min(a, b), std::max(a, b));
     }
   }
+  mark("slots");
+  std::vector<int32_t> slot_id;
+  const int rc = number_edges(m, slot_of, slot_id);
+  if (rc != NST_OK) return rc;
+  mark("numbering");
   // boundary ids: boundary edges default to 0 (deal.II's default boundary_id), interior -1
   m->edge_tag.assign(E, -1);
   int64_t nb = 0;
+#pragma omp parallel for reduction(+ : nb) schedule(static)
   for (int64_t e = 0; e < E; ++e)
     if (m->edge_nc[e] == 1) {
       m->edge_tag[e] = 0;
@@ -216,7 +332,79 @@ int build_mesh(int64_t V, const double *xy, int64_t T, const int32_t *cells, int
     const int32_t e = slot_id[s];
     if (m->edge_nc[e] == 1) m->edge_tag[e] = L.tag;
   }
+  mark("tags");
   return NST_OK;
+}
+
+// One level of red refinement WITHOUT rediscovering the edges: a child line is either half of a parent edge (slot 2e + which
+// end) or one of the 3 interior lines of the parent cell (slot 2E + 3c + j), so its slot is a formula; the numbering by
+// first appearance is then the same as build_mesh's.  Returns nullptr (and leaves *rc untouched) if a child cell came out
+// with negative measure - build_mesh would swap its vertices, so the caller takes the general path.
+nst_mesh *refine_direct(const nst_mesh *cur, int snap_id, double cx, double cy, double r, int *rc) {
+  const int64_t V = cur->V, T = cur->T, E = cur->E;
+  if (2 * E + 3 * T > (int64_t)INT32_MAX) return nullptr;
+  auto *m = new nst_mesh;
+  m->V = V + E, m->T = 4 * T, m->E = 2 * E + 3 * T;
+  m->xy.resize(2 * (size_t)(V + E));
+  std::copy(cur->xy.begin(), cur->xy.end(), m->xy.begin());
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < E; ++e) {
+    const int32_t a = cur->edge_v[2 * e], b = cur->edge_v[2 * e + 1];
+    double x = 0.5 * (cur->xy[2 * a] + cur->xy[2 * b]), y = 0.5 * (cur->xy[2 * a + 1] + cur->xy[2 * b + 1]);
+    if (snap_id >= 0 && cur->edge_tag[e] == snap_id) {
+      const double dx = x - cx, dy = y - cy, d = std::sqrt(dx * dx + dy * dy);
+      if (d > 0) {
+        x = cx + dx * r / d;
+        y = cy + dy * r / d;
+      }
+    }
+    m->xy[2 * (V + e)] = x;
+    m->xy[2 * (V + e) + 1] = y;
+  }
+  m->cells.resize(12 * (size_t)T);
+  std::vector<int32_t> slot_of(12 * (size_t)T);
+  int64_t inverted = 0;
+#pragma omp parallel for reduction(+ : inverted) schedule(static)
+  for (int64_t c = 0; c < T; ++c) {
+    const int32_t *v = &cur->cells[3 * c];
+    const int32_t *ce = &cur->cell_edges[3 * c];
+    const int32_t m01 = (int32_t)(V + ce[0]), m12 = (int32_t)(V + ce[1]), m20 = (int32_t)(V + ce[2]);
+    int32_t *o = &m->cells[12 * c];
+    o[0] = v[0], o[1] = m01, o[2] = m20;
+    o[3] = m01, o[4] = v[1], o[5] = m12;
+    o[6] = m20, o[7] = m12, o[8] = v[2];
+    o[9] = m01, o[10] = m12, o[11] = m20;
+    for (int q = 0; q < 4; ++q) {
+      const double *p0 = &m->xy[2 * o[3 * q]], *p1 = &m->xy[2 * o[3 * q + 1]], *p2 = &m->xy[2 * o[3 * q + 2]];
+      inverted += (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (p1[1] - p0[1]) < 0 ? 1 : 0;
+    }
+    // half of parent edge ce[k] at the end that is vertex w; interior line j of the parent
+    auto half = [&](int k, int32_t w) { return 2 * ce[k] + (cur->edge_v[2 * ce[k]] == w ? 0 : 1); };
+    const int32_t i0 = (int32_t)(2 * E + 3 * c), i1 = i0 + 1, i2 = i0 + 2;  // (m01,m20), (m01,m12), (m12,m20)
+    int32_t *s = &slot_of[12 * c];
+    s[0] = half(0, v[0]), s[1] = i0, s[2] = half(2, v[0]);   // child 0: (v0,m01) (m01,m20) (m20,v0)
+    s[3] = half(0, v[1]), s[4] = half(1, v[1]), s[5] = i1;   // child 1: (m01,v1) (v1,m12) (m12,m01)
+    s[6] = i2, s[7] = half(1, v[2]), s[8] = half(2, v[2]);   // child 2: (m20,m12) (m12,v2) (v2,m20)
+    s[9] = i1, s[10] = i2, s[11] = i0;                       // child 3: (m01,m12) (m12,m20) (m20,m01)
+  }
+  if (inverted) {
+    delete m;
+    return nullptr;
+  }
+  m->n_inverted = 0;
+  std::vector<int32_t> slot_id;
+  *rc = number_edges(m, slot_of, slot_id);
+  if (*rc != NST_OK) {
+    delete m;
+    return nullptr;
+  }
+  // the halves of a boundary edge inherit its id (the two "lines" the general path would have been given); the rest is interior
+  m->edge_tag.assign(m->E, -1);
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < E; ++e)
+    if (cur->edge_nc[e] == 1) m->edge_tag[slot_id[2 * e]] = m->edge_tag[slot_id[2 * e + 1]] = cur->edge_tag[e];
+  m->n_boundary = 2 * cur->n_boundary;
+  return m;
 }
 
 // Drops vertices no triangle references, keeping file order (GridTools::delete_unused_vertices).
@@ -447,6 +635,20 @@ int nst_mesh_refine(const nst_mesh *in, int levels, int snap_id, double cx, doub
       delete owned;
       return fail(NST_ERR_ARG, "refined mesh would exceed the 32-bit index range");
     }
+    {
+      int drc = NST_OK;
+      nst_mesh *direct = refine_direct(cur, snap_id, cx, cy, r, &drc);
+      if (drc != NST_OK) {
+        delete owned;
+        return drc;
+      }
+      if (direct) {
+        delete owned;
+        owned = direct;
+        cur = direct;
+        continue;
+      }
+    }
     std::vector<double> xy(2 * (size_t)(V + E));
     std::copy(cur->xy.begin(), cur->xy.end(), xy.begin());
 #pragma omp parallel for schedule(static)
@@ -599,6 +801,7 @@ int nst_dofs_distribute(const nst_mesh *m, int n_parts, const int32_t *cell_part
   if (!m || !out || n_parts < 1) return fail(NST_ERR_ARG, "bad argument");
   if (n_parts > 1 && !cell_part) return fail(NST_ERR_ARG, "cell_part required for n_parts > 1");
   auto *d = new nst_dofs;
+  Tracer tr("dofs");
   d->n_parts = n_parts;
   const int64_t V = m->V, E = m->E, T = m->T;
   d->vertex_node.assign(V, -1);
@@ -607,48 +810,91 @@ int nst_dofs_distribute(const nst_mesh *m, int n_parts, const int32_t *cell_part
   d->vertex_owner.assign(V, 0);
   d->edge_owner.assign(E, 0);
   std::vector<int64_t> order(T);  // cells grouped by part, file order inside a part
+  std::vector<int64_t> part_begin;  // [n_parts+1] where the cells of a part start in `order`
   if (n_parts > 1) {
     std::fill(d->vertex_owner.begin(), d->vertex_owner.end(), INT32_MAX);
     std::fill(d->edge_owner.begin(), d->edge_owner.end(), INT32_MAX);
     std::vector<int64_t> cnt(n_parts + 1, 0);
+    int64_t out_of_range = 0;
+#pragma omp parallel for reduction(+ : out_of_range) schedule(static)
     for (int64_t c = 0; c < T; ++c) {
       const int32_t p = cell_part[c];
       if (p < 0 || p >= n_parts) {
-        delete d;
-        return fail(NST_ERR_ARG, "cell_part entry out of range");
+        ++out_of_range;
+        continue;
       }
-      cnt[p + 1]++;
-      for (int k = 0; k < 3; ++k) {
-        int32_t &vo = d->vertex_owner[m->cells[3 * c + k]];
-        vo = std::min(vo, p);
-        int32_t &eo = d->edge_owner[m->cell_edges[3 * c + k]];
-        eo = std::min(eo, p);
+      for (int k = 0; k < 3; ++k) {  // an entity belongs to the lowest part among its cells
+        atomic_min32(&d->vertex_owner[m->cells[3 * c + k]], p);
+        atomic_min32(&d->edge_owner[m->cell_edges[3 * c + k]], p);
       }
     }
+    if (out_of_range) {
+      delete d;
+      return fail(NST_ERR_ARG, "cell_part entry out of range");
+    }
+    for (int64_t c = 0; c < T; ++c) cnt[cell_part[c] + 1]++;
     for (int p = 0; p < n_parts; ++p) cnt[p + 1] += cnt[p];
+    part_begin.assign(cnt.begin(), cnt.end());
     for (int64_t c = 0; c < T; ++c) order[cnt[cell_part[c]]++] = c;
   } else {
     std::iota(order.begin(), order.end(), 0);
+    part_begin = {0, T};
   }
+  tr.mark("owners + order");
   d->part_n_u.assign(n_parts, 0);
   d->part_n_p.assign(n_parts, 0);
-  // pass 1: per-part first-visit ranks (node rank and pressure rank local to the part)
+  // pass 1: per-part first-visit ranks (node rank and pressure rank local to the part).  The cell loop of a part visits, per
+  // cell, its 3 vertices and then its 3 lines: position 6 i + k of the i-th cell in `order`; an entity is numbered at the first
+  // position that refers to it among the cells of its owner part (see rank_first_positions).
   std::vector<int64_t> nn(n_parts, 0), np(n_parts, 0);
-  for (int64_t i = 0; i < T; ++i) {
-    const int64_t c = order[i];
-    const int32_t p = n_parts > 1 ? cell_part[c] : 0;
-    for (int k = 0; k < 3; ++k) {
-      const int32_t v = m->cells[3 * c + k];
-      if (d->vertex_owner[v] == p && d->vertex_node[v] < 0) {
-        d->vertex_node[v] = (int32_t)nn[p]++;
-        d->vertex_p[v] = (int32_t)np[p]++;
+  {
+    std::vector<int64_t> first_v(V, INT64_MAX), first_e(E, INT64_MAX);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < T; ++i) {
+      const int64_t c = order[i];
+      const int32_t p = n_parts > 1 ? cell_part[c] : 0;
+      for (int k = 0; k < 3; ++k) {
+        const int32_t v = m->cells[3 * c + k], e = m->cell_edges[3 * c + k];
+        if (d->vertex_owner[v] == p) atomic_min(&first_v[v], 6 * i + k);
+        if (d->edge_owner[e] == p) atomic_min(&first_e[e], 6 * i + 3 + k);
       }
     }
-    for (int k = 0; k < 3; ++k) {
-      const int32_t e = m->cell_edges[3 * c + k];
-      if (d->edge_owner[e] == p && d->edge_node[e] < 0) d->edge_node[e] = (int32_t)nn[p]++;
+    auto is_first = [&](int64_t pos) {
+      const int64_t c = order[pos / 6];
+      const int k = (int)(pos % 6);
+      return k < 3 ? first_v[m->cells[3 * c + k]] == pos : first_e[m->cell_edges[3 * c + k - 3]] == pos;
+    };
+    const int nt = n_threads();
+    for (int p = 0; p < n_parts; ++p) {  // both ranks (node, pressure vertex) in one counting and one numbering pass
+      const int64_t b = 6 * part_begin[p], e = 6 * part_begin[p + 1], chunk = (e - b + nt - 1) / std::max(nt, 1);
+      std::vector<int64_t> cn(nt + 1, 0), cp(nt + 1, 0);
+#pragma omp parallel for schedule(static, 1)
+      for (int t = 0; t < nt; ++t) {
+        int64_t kn = 0, kp = 0;
+        for (int64_t pos = std::min(e, b + t * chunk), pe = std::min(e, pos + chunk); pos < pe; ++pos)
+          if (is_first(pos)) ++kn, kp += pos % 6 < 3 ? 1 : 0;
+        cn[t + 1] = kn, cp[t + 1] = kp;
+      }
+      for (int t = 0; t < nt; ++t) cn[t + 1] += cn[t], cp[t + 1] += cp[t];
+#pragma omp parallel for schedule(static, 1)
+      for (int t = 0; t < nt; ++t) {
+        int64_t rn = cn[t], rp = cp[t];
+        for (int64_t pos = std::min(e, b + t * chunk), pe = std::min(e, pos + chunk); pos < pe; ++pos)
+          if (is_first(pos)) {
+            const int64_t c = order[pos / 6];
+            const int k = (int)(pos % 6);
+            if (k < 3) {
+              d->vertex_node[m->cells[3 * c + k]] = (int32_t)rn++;
+              d->vertex_p[m->cells[3 * c + k]] = (int32_t)rp++;
+            } else {
+              d->edge_node[m->cell_edges[3 * c + k - 3]] = (int32_t)rn++;
+            }
+          }
+      }
+      nn[p] = cn[nt], np[p] = cp[nt];
     }
   }
+  tr.mark("first-visit numbering");
   d->u_off.assign(n_parts + 1, 0);
   d->p_off.assign(n_parts + 1, 0);
   std::vector<int64_t> node_off(n_parts + 1, 0);
@@ -674,6 +920,7 @@ int nst_dofs_distribute(const nst_mesh *m, int n_parts, const int32_t *cell_part
     }
     for (int64_t e = 0; e < E; ++e) d->edge_node[e] += (int32_t)node_off[d->edge_owner[e]];
   }
+  tr.mark("offsets");
   d->cell_dofs.resize(15 * (size_t)T);
   const int32_t nu = (int32_t)d->n_u;
 #pragma omp parallel for schedule(static)
@@ -689,6 +936,7 @@ int nst_dofs_distribute(const nst_mesh *m, int n_parts, const int32_t *cell_part
       o[9 + 2 * k + 1] = 2 * d->edge_node[e] + 1;
     }
   }
+  tr.mark("cell_dofs");
   *out = d;
   return NST_OK;
 }
@@ -823,6 +1071,7 @@ int nst_sparsity(const nst_mesh *m, const nst_dofs *d, int kind, int64_t *nnz, i
 int nst_dofs_support_points(const nst_mesh *m, const nst_dofs *d, double *xy) {
   if (!m || !d || !xy) return fail(NST_ERR_ARG, "null argument");
   const int64_t nu = d->n_u;
+#pragma omp parallel for schedule(static)
   for (int64_t v = 0; v < m->V; ++v) {
     const double x = m->xy[2 * v], y = m->xy[2 * v + 1];
     const int64_t n = d->vertex_node[v];
@@ -834,6 +1083,7 @@ int nst_dofs_support_points(const nst_mesh *m, const nst_dofs *d, double *xy) {
     xy[2 * p] = x;
     xy[2 * p + 1] = y;
   }
+#pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < m->E; ++e) {
     const int32_t a = m->edge_v[2 * e], b = m->edge_v[2 * e + 1];
     const double x = 0.5 * (m->xy[2 * a] + m->xy[2 * b]), y = 0.5 * (m->xy[2 * a + 1] + m->xy[2 * b + 1]);
@@ -857,11 +1107,24 @@ int nst_dirichlet_values(const nst_mesh *m, const nst_dofs *d, int n_calls, cons
     const double yy = y - inlet->y0;
     return 4. * inlet->u_m * yy * (inlet->H - yy) * inlet->time_factor / (inlet->H * inlet->H);
   };
+  // the boundary faces in (cell, face) order: one parallel pass over the cells instead of one serial pass per call
+  std::vector<int64_t> bfaces;  // 3 c + f
+  {
+    const int nt = n_threads();
+    const int64_t ch = (m->T + nt - 1) / std::max(nt, 1);
+    std::vector<std::vector<int64_t>> found(nt);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; ++t)
+      for (int64_t c = std::min(m->T, t * ch), ce = std::min(m->T, c + ch); c < ce; ++c)
+        for (int f = 0; f < 3; ++f)
+          if (m->edge_nc[m->cell_edges[3 * c + f]] == 1) found[t].push_back(3 * c + f);
+    for (int t = 0; t < nt; ++t) bfaces.insert(bfaces.end(), found[t].begin(), found[t].end());
+  }
   for (int call = 0; call < n_calls; ++call) {
-    for (int64_t c = 0; c < m->T; ++c)
-      for (int f = 0; f < 3; ++f) {
+    for (const int64_t cf : bfaces) {
+        const int64_t c = cf / 3;
+        const int f = (int)(cf % 3);
         const int32_t e = m->cell_edges[3 * c + f];
-        if (m->edge_nc[e] != 1) continue;
         int hit = -1;
         for (int32_t q = call_ptr[call]; q < call_ptr[call + 1]; ++q)
           if (ids[q] == m->edge_tag[e]) hit = q;
@@ -903,6 +1166,7 @@ int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const i
     return fail(NST_ERR_ARG, "bad argument (n_parts must match nst_dofs_distribute)");
   if (n_parts > 1 && !cell_part) return fail(NST_ERR_ARG, "cell_part required");
   auto *P = new nst_part;
+  Tracer tr("part");
   const int64_t T = m->T, nu = d->n_u;
   const int64_t u0 = d->u_off[rank], u1 = d->u_off[rank + 1], p0 = d->p_off[rank], p1 = d->p_off[rank + 1];
   const int64_t n_own_u = u1 - u0, n_own_p = p1 - p0, n_own = n_own_u + n_own_p;
@@ -912,31 +1176,60 @@ int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const i
     const int64_t x = g < nu ? g : g - nu;
     return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;
   };
+  // Order-preserving parallel filter: calls emit(thread_local_sink, i) for i in [0, n) in chunks and concatenates the chunks in
+  // order, so the result equals the serial loop's.
+  const int nt = n_threads();
+  auto chunk_of = [nt](int64_t n, int t, int64_t &b, int64_t &e) {
+    const int64_t ch = (n + nt - 1) / std::max(nt, 1);
+    b = std::min(n, t * ch), e = std::min(n, b + ch);
+  };
   // local cells: every cell touching an owned DoF, in global order
-  for (int64_t c = 0; c < T; ++c) {
-    const int32_t *cd = &d->cell_dofs[15 * c];
-    bool any = false;
-    for (int k = 0; k < 15 && !any; ++k) any = owned_g(cd[k]);
-    if (any) P->cell_ids.push_back((int32_t)c);
+  {
+    std::vector<std::vector<int32_t>> found(nt);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; ++t) {
+      int64_t b, e;
+      chunk_of(T, t, b, e);
+      for (int64_t c = b; c < e; ++c) {
+        const int32_t *cd = &d->cell_dofs[15 * c];
+        bool any = false;
+        for (int k = 0; k < 15 && !any; ++k) any = owned_g(cd[k]);
+        if (any) found[t].push_back((int32_t)c);
+      }
+    }
+    for (int t = 0; t < nt; ++t) P->cell_ids.insert(P->cell_ids.end(), found[t].begin(), found[t].end());
   }
   const int64_t nc = (int64_t)P->cell_ids.size();
+  tr.mark("cell ids");
   // ghosts
   std::vector<int32_t> gu, gp;
-  for (int64_t i = 0; i < nc; ++i) {
-    const int32_t *cd = &d->cell_dofs[15 * (int64_t)P->cell_ids[i]];
-    for (int k = 0; k < 15; ++k)
-      if (!owned_g(cd[k])) (cd[k] < nu ? gu : gp).push_back(cd[k]);
-  }
   auto uniq = [](std::vector<int32_t> &v) {
     std::sort(v.begin(), v.end());
     v.erase(std::unique(v.begin(), v.end()), v.end());
   };
+  if (n_parts > 1) {
+    std::vector<std::vector<int32_t>> tu(nt), tp(nt);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; ++t) {
+      int64_t b, e;
+      chunk_of(nc, t, b, e);
+      for (int64_t i = b; i < e; ++i) {
+        const int32_t *cd = &d->cell_dofs[15 * (int64_t)P->cell_ids[i]];
+        for (int k = 0; k < 15; ++k)
+          if (!owned_g(cd[k])) (cd[k] < nu ? tu[t] : tp[t]).push_back(cd[k]);
+      }
+      uniq(tu[t]), uniq(tp[t]);
+    }
+    for (int t = 0; t < nt; ++t) gu.insert(gu.end(), tu[t].begin(), tu[t].end()), gp.insert(gp.end(), tp[t].begin(), tp[t].end());
+  }
   uniq(gu);
   uniq(gp);
   const int64_t n_gu = (int64_t)gu.size(), n_gp = (int64_t)gp.size();
   const int64_t n_loc = n_own + n_gu + n_gp;
   P->l2g.resize(n_loc);
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n_own_u; ++i) P->l2g[i] = u0 + i;
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n_own_p; ++i) P->l2g[n_own_u + i] = nu + p0 + i;
   for (int64_t i = 0; i < n_gu; ++i) P->l2g[n_own + i] = gu[i];
   for (int64_t i = 0; i < n_gp; ++i) P->l2g[n_own + n_gu + i] = gp[i];
@@ -948,67 +1241,97 @@ int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const i
     if (g - nu >= p0 && g - nu < p1) return (int32_t)(n_own_u + (g - nu - p0));
     return (int32_t)(n_own + n_gu + (std::lower_bound(gp.begin(), gp.end(), g) - gp.begin()));
   };
-  // local cells, vertices, dofs
+  tr.mark("ghosts + l2g");
+  // local cells, vertices, dofs; local vertices are numbered by first appearance in the local cell loop
   P->cell_dofs.resize(15 * (size_t)nc);
   P->cell_vertices.resize(3 * (size_t)nc);
   P->cell_owned.resize(nc);
   std::vector<int32_t> vloc(m->V, -1);
   int32_t nv = 0;
-  for (int64_t i = 0; i < nc; ++i) {
-    const int64_t c = P->cell_ids[i];
-    for (int k = 0; k < 15; ++k) P->cell_dofs[15 * i + k] = g2l(d->cell_dofs[15 * c + k]);
-    for (int k = 0; k < 3; ++k) {
-      const int32_t v = m->cells[3 * c + k];
-      if (vloc[v] < 0) {
-        vloc[v] = nv++;
-        P->xy.push_back(m->xy[2 * v]);
-        P->xy.push_back(m->xy[2 * v + 1]);
-      }
-      P->cell_vertices[3 * i + k] = vloc[v];
+  {
+    std::vector<int64_t> first_v(m->V, INT64_MAX);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nc; ++i) {
+      const int64_t c = P->cell_ids[i];
+      for (int k = 0; k < 15; ++k) P->cell_dofs[15 * i + k] = g2l(d->cell_dofs[15 * c + k]);
+      for (int k = 0; k < 3; ++k) atomic_min(&first_v[m->cells[3 * c + k]], 3 * i + k);
+      P->cell_owned[i] = (n_parts == 1 || cell_part[c] == rank) ? 1 : 0;
     }
-    P->cell_owned[i] = (n_parts == 1 || cell_part[c] == rank) ? 1 : 0;
-    for (int f = 0; f < 3; ++f) {
-      const int32_t e = m->cell_edges[3 * c + f];
-      if (m->edge_nc[e] == 1) {
-        P->bface_cell.push_back((int32_t)i);
-        P->bface_face.push_back(f);
-        P->bface_tag.push_back(m->edge_tag[e]);
-      }
+    auto vertex_at = [&](int64_t pos) { return m->cells[3 * (int64_t)P->cell_ids[pos / 3] + pos % 3]; };
+    nv = (int32_t)rank_first_positions(
+        0, 3 * nc, 0, [&](int64_t pos) { return first_v[vertex_at(pos)] == pos; },
+        [&](int64_t pos, int64_t rank) { vloc[vertex_at(pos)] = (int32_t)rank; });
+    P->xy.resize(2 * (size_t)nv);
+#pragma omp parallel for schedule(static)
+    for (int64_t pos = 0; pos < 3 * nc; ++pos) {
+      const int32_t v = vertex_at(pos), l = vloc[v];
+      P->cell_vertices[pos] = l;
+      if (first_v[v] == pos) P->xy[2 * l] = m->xy[2 * v], P->xy[2 * l + 1] = m->xy[2 * v + 1];
     }
   }
+  tr.mark("local cells + vertices");
+  {  // boundary faces in local cell order
+    std::vector<std::vector<int32_t>> fc(nt), ff(nt), ft(nt);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; ++t) {
+      int64_t b, e;
+      chunk_of(nc, t, b, e);
+      for (int64_t i = b; i < e; ++i) {
+        const int64_t c = P->cell_ids[i];
+        for (int f = 0; f < 3; ++f) {
+          const int32_t ed = m->cell_edges[3 * c + f];
+          if (m->edge_nc[ed] == 1) fc[t].push_back((int32_t)i), ff[t].push_back(f), ft[t].push_back(m->edge_tag[ed]);
+        }
+      }
+    }
+    for (int t = 0; t < nt; ++t) {
+      P->bface_cell.insert(P->bface_cell.end(), fc[t].begin(), fc[t].end());
+      P->bface_face.insert(P->bface_face.end(), ff[t].begin(), ff[t].end());
+      P->bface_tag.insert(P->bface_tag.end(), ft[t].begin(), ft[t].end());
+    }
+  }
+  tr.mark("boundary faces");
   // local patterns of the owned rows (columns ascending in local ids: owned first, then ghosts)
   const int32_t a0 = (int32_t)n_own_u, a1 = (int32_t)n_own, a2 = (int32_t)(n_own + n_gu);
   auto is_p = [a0, a1, a2](int32_t l) { return (l >= a0 && l < a1) || l >= a2; };
-  if (flags & NST_PART_NO_PATTERNS) {  // the device builds them from cell_dofs (nsg_set_pattern_from_cells)
-    P->jac_rowptr.assign((size_t)n_own + 1, 0);
-    P->pm_rowptr.assign((size_t)n_own + 1, 0);
+  if (flags & NST_PART_NO_PATTERNS) {  // the device builds them from cell_dofs (nsg_set_pattern_from_cells): the row pointers stay empty
   } else {
     DofCells dc;  // shared by the two patterns
     dof_to_cells(n_own, nc, P->cell_dofs.data(), dc);
     build_pattern(n_own, nc, P->cell_dofs.data(), 0, is_p, P->jac_rowptr, &P->jac_col, &dc);
     build_pattern(n_own, nc, P->cell_dofs.data(), 2, is_p, P->pm_rowptr, &P->pm_col, &dc);
   }
+  tr.mark("patterns");
   // halo plan
   std::vector<std::vector<int32_t>> recv(n_parts), send(n_parts);
   for (int64_t i = 0; i < n_gu; ++i) recv[owner_of(gu[i])].push_back((int32_t)(n_own + i));
   for (int64_t i = 0; i < n_gp; ++i) recv[owner_of(gp[i])].push_back((int32_t)(n_own + n_gu + i));
   if (n_parts > 1) {
-    for (int64_t i = 0; i < nc; ++i) {
-      const int32_t *cd = &d->cell_dofs[15 * (int64_t)P->cell_ids[i]];
-      int owners[15], no = 0;
-      for (int k = 0; k < 15; ++k) {
-        const int o = owner_of(cd[k]);
-        bool seen = false;
-        for (int q = 0; q < no; ++q) seen |= owners[q] == o;
-        if (!seen) owners[no++] = o;
+    std::vector<std::vector<std::vector<int32_t>>> tsend(nt, std::vector<std::vector<int32_t>>(n_parts));
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; ++t) {
+      int64_t b, e;
+      chunk_of(nc, t, b, e);
+      for (int64_t i = b; i < e; ++i) {
+        const int32_t *cd = &d->cell_dofs[15 * (int64_t)P->cell_ids[i]];
+        int owners[15], no = 0;
+        for (int k = 0; k < 15; ++k) {
+          const int o = owner_of(cd[k]);
+          bool seen = false;
+          for (int q = 0; q < no; ++q) seen |= owners[q] == o;
+          if (!seen) owners[no++] = o;
+        }
+        if (no == 1) continue;
+        for (int q = 0; q < no; ++q) {
+          if (owners[q] == rank) continue;
+          for (int k = 0; k < 15; ++k)
+            if (owned_g(cd[k])) tsend[t][owners[q]].push_back(g2l(cd[k]));
+        }
       }
-      if (no == 1) continue;
-      for (int q = 0; q < no; ++q) {
-        if (owners[q] == rank) continue;
-        for (int k = 0; k < 15; ++k)
-          if (owned_g(cd[k])) send[owners[q]].push_back(g2l(cd[k]));
-      }
+      for (auto &v : tsend[t]) uniq(v);
     }
+    for (int t = 0; t < nt; ++t)
+      for (int k = 0; k < n_parts; ++k) send[k].insert(send[k].end(), tsend[t][k].begin(), tsend[t][k].end());
     for (auto &s : send) uniq(s);  // local owned ids ascend with global ids inside [u | p]
   }
   P->send_ptr.push_back(0);
@@ -1030,11 +1353,12 @@ int nst_part_build_ex(const nst_mesh *m, const nst_dofs *d, int n_parts, const i
   I.n_owned_cells = 0;
   for (uint8_t o : P->cell_owned) I.n_owned_cells += o;
   I.n_vertices = nv;
-  I.nnz_jac = P->jac_rowptr[n_own];
-  I.nnz_pm = P->pm_rowptr[n_own];
+  I.nnz_jac = P->jac_rowptr.empty() ? 0 : P->jac_rowptr[n_own];
+  I.nnz_pm = P->pm_rowptr.empty() ? 0 : P->pm_rowptr[n_own];
   I.n_neighbors = (int32_t)P->neighbors.size();
   I.n_send = (int64_t)P->send_idx.size();
   I.n_recv = (int64_t)P->recv_idx.size();
+  tr.mark("halo plan");
   *out = P;
   return NST_OK;
 }
@@ -1051,9 +1375,9 @@ const int32_t *nst_part_cell_dofs(const nst_part *p) { return p->cell_dofs.data(
 const int32_t *nst_part_cell_vertices(const nst_part *p) { return p->cell_vertices.data(); }
 const double *nst_part_xy(const nst_part *p) { return p->xy.data(); }
 const uint8_t *nst_part_cell_owned(const nst_part *p) { return p->cell_owned.data(); }
-const int64_t *nst_part_jac_rowptr(const nst_part *p) { return p->jac_rowptr.data(); }
+const int64_t *nst_part_jac_rowptr(const nst_part *p) { return p->jac_rowptr.empty() ? nullptr : p->jac_rowptr.data(); }
 const int32_t *nst_part_jac_col(const nst_part *p) { return p->jac_col.data(); }
-const int64_t *nst_part_pm_rowptr(const nst_part *p) { return p->pm_rowptr.data(); }
+const int64_t *nst_part_pm_rowptr(const nst_part *p) { return p->pm_rowptr.empty() ? nullptr : p->pm_rowptr.data(); }
 const int32_t *nst_part_pm_col(const nst_part *p) { return p->pm_col.data(); }
 const int32_t *nst_part_neighbors(const nst_part *p) { return p->neighbors.data(); }
 const int64_t *nst_part_send_ptr(const nst_part *p) { return p->send_ptr.data(); }

@@ -129,7 +129,7 @@ class Dofs:
         return rowptr, col[: nnz.value]
 
     def support_points(self):
-        xy = np.zeros(2 * self.n, np.float64)
+        xy = np.empty(2 * self.n, np.float64)   # every entry is written
         nst_check(nst().nst_dofs_support_points(self.mesh._h, self._h, xy))
         return xy.reshape(-1, 2)
 
@@ -232,9 +232,12 @@ class Part:
         self.cell_vertices = view(L.nst_part_cell_vertices(h), 3 * self.n_cells, np.int32)
         self.xy = view(L.nst_part_xy(h), 2 * self.n_vertices, np.float64)
         self.cell_owned = view(L.nst_part_cell_owned(h), self.n_cells, np.uint8)
-        self.jac_rowptr = view(L.nst_part_jac_rowptr(h), self.n_own + 1, np.int64)
+        if self.has_patterns:
+            self.jac_rowptr = view(L.nst_part_jac_rowptr(h), self.n_own + 1, np.int64)
+            self.pm_rowptr = view(L.nst_part_pm_rowptr(h), self.n_own + 1, np.int64)
+        else:   # the library keeps no row pointers in this mode; all-zero ones (lazily allocated pages) keep the attribute
+            self.jac_rowptr, self.pm_rowptr = np.zeros(self.n_own + 1, np.int64), np.zeros(self.n_own + 1, np.int64)
         self.jac_col = view(L.nst_part_jac_col(h), self.nnz_jac, np.int32)
-        self.pm_rowptr = view(L.nst_part_pm_rowptr(h), self.n_own + 1, np.int64)
         self.pm_col = view(L.nst_part_pm_col(h), self.nnz_pm, np.int32)
         self.neighbors = as_array(L.nst_part_neighbors(h), self.n_neighbors, np.int32)
         self.send_ptr = as_array(L.nst_part_send_ptr(h), self.n_neighbors + 1, np.int64)

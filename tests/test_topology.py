@@ -247,3 +247,30 @@ def test_part_views_outlive_the_part(pkg):
     junk = [np.zeros(1 << 16) for _ in range(8)]      # churn the allocator
     assert np.array_equal(keep, want) and keep._owner is not None
     del junk
+
+
+@pytest.mark.parametrize("threads", ["1", "all"])
+def test_topology_outputs_are_pinned(threads):
+    """Everything libnst.so produces (numbering by first appearance of lines, vertices and DoFs, red refinement incl. snapping, partitions,
+    ghost layers, local patterns, halo plans, Dirichlet lists) equals the committed digests - which were generated with the serial
+    round-1 library - for one OpenMP thread and for all of them: the parallel min/scan numbering is deterministic and unchanged."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "golden", "make_topology_hashes.py")
+    env = dict(os.environ)
+    if threads == "1":
+        env["OMP_NUM_THREADS"] = "1"
+    else:
+        env.pop("OMP_NUM_THREADS", None)
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"topology_hashes_{os.getpid()}_{threads}.json")
+    try:
+        subprocess.run([sys.executable, script, out], check=True, env=env, timeout=600)
+        got, want = json.load(open(out)), json.load(open(os.path.join(root, "tests", "golden", "topology_hashes.json")))
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+    assert got.keys() == want.keys()
+    assert [k for k in want if got[k] != want[k]] == []
