@@ -11,6 +11,7 @@
 #pragma once
 #include "nsg_common.cuh"
 #include "nsg_krylov.cuh"
+#include "nsg_tri_layout.h"
 
 namespace nsg {
 
@@ -207,14 +208,15 @@ k_ilu_solve_sf(const int32_t *__restrict__ rows, int64_t n, const int64_t *__res
 // and 8 inside the thread, 4, 2, 1 by shuffles): the result is bitwise the same.  Measured on the 51 842-row block
 // (1 120 + 1 120 levels), per apply: stamped solve 3.46 ms; a warp per row 3.67 ms, a thread per row 6.39 ms (one warp
 // crawling through ~1 000 dependent instructions per level), 8 lanes per row with per-group headers and cp.async
-// staging by 8 producer warps 2.0 ms (2 150 warp instructions per level on one SM), this kernel 1.70 ms = 0.76 us per
+// staging by 8 producer warps 2.0 ms (2 150 warp instructions per level on one SM), this kernel 1.67 ms = 0.75 us per
 // level.  Tried on top of it and not kept (profiles/r02_summary.md): far unknowns prefetched into a shared-memory ring
 // by the producer warp (2.09 - 2.11 ms), the next level's records prepared before the barrier with 24 compute warps
 // (2.47 ms), rows and slots in one stream with a single bulk copy per level (3.04 ms).
 constexpr int TRI_W = 8192, TRI_RQ = 8192, TRI_RK = 1024;
 constexpr int TRI_CW = 20, TRI_MAX_THREADS = 1024;  // compute warps (the launch adds the producer warp; NSG_TRI_CW overrides);
                                                      // measured 6 / 8 / 12 / 16 / 20 / 24 / 31 warps: 2.33 / 2.12 / 1.87 / 1.87 / 1.70 / 1.73 / 1.75 ms
-constexpr int TRI_DEPTH = 4;                                 // levels the producer runs ahead (a power of two)
+constexpr int TRI_DEPTH = 2;                                 // levels the producer runs ahead (a power of two). With 4, 407 of the 2 240
+                                                             // levels of the 51 842-row block no longer fit the rings (tests/test_tri_layout.py)
 constexpr int TRI_FLUSH = 512, TRI_MAX_LEVEL_ROWS = 2048;    // write-out granularity; widest level the window can take
 constexpr size_t TRI_SMEM = sizeof(double) * TRI_W + 16 * (size_t)(TRI_RQ + TRI_RK);
 struct TriArgs {
@@ -485,60 +487,25 @@ static int build_block(nsg_ctx *c, CsrBlock &B, const std::vector<int64_t> &rp, 
   for (int32_t l = 0; l < nU; ++l) widest = std::max(widest, B.h_ulevel_ptr[l + 1] - B.h_ulevel_ptr[l]);
   if (n > 0 && B.nnz < (int64_t)1 << 28 && widest <= TRI_MAX_LEVEL_ROWS) {
     double t_cta = 0.0;
+    static_assert(sizeof(TriRec) == sizeof(int4), "TriRec is uploaded as int4");
+    const TriLimits lim{TRI_W, TRI_RQ, TRI_RK, TRI_DEPTH};
     auto layout = [&](bool upper, const std::vector<int32_t> &rows_by_level, const std::vector<int32_t> &ptr,
                       const std::vector<int32_t> *pos_fwd, CsrBlock::Tri &T, std::vector<int32_t> &pos) -> int {
-      const int32_t nl = (int32_t)ptr.size() - 1;
-      auto len = [&](int64_t i) { return upper ? rowptr[i + 1] - diag[i] - 1 : diag[i] - rowptr[i]; };
-      // positions: level by level, inside a level by falling row length
-      std::vector<int32_t> rows(rows_by_level);
-      for (int32_t l = 0; l < nl; ++l)
-        std::stable_sort(rows.begin() + ptr[l], rows.begin() + ptr[l + 1], [&](int32_t x, int32_t y) { return len(x) > len(y); });
-      pos.resize(n);
-      for (int64_t k = 0; k < n; ++k) pos[rows[k]] = (int32_t)k;
-      std::vector<int4> info(nl + 1), slots;
-      std::vector<int32_t> ra_src(n);
-      std::vector<int64_t> fsrc;  // -1: padding (factor 0)
-      slots.reserve(2 * B.nnz), fsrc.reserve(2 * B.nnz);
-      for (int32_t l = 0; l < nl; ++l) {
-        const int32_t k0 = ptr[l], k1 = ptr[l + 1];
-        const int32_t slabs = (int32_t)((len(rows[k0]) + 7) / 8);  // the longest row of the level comes first
-        if (slabs > 0xffff) return fail(NSG_ERR_ARG, "a row with more than 2^19 entries");
-        const size_t q0 = slots.size(), groups = (size_t)(k1 - k0 + 3) / 4;
-        info[l] = make_int4((int)q0, slabs, 0, k0);
-        const int32_t pad = std::max(k0 - 1, 0);  // padding (factor 0) reads the last unknown of the previous level
-        slots.resize(q0 + groups * slabs * 32, make_int4(0, 0, k1 - pad <= TRI_W ? pad : ~pad, 0));
-        fsrc.resize(q0 + groups * slabs * 32, -1);
-        for (int32_t r = 0; r < k1 - k0; ++r) {
-          const int64_t i = rows[k0 + r];
-          const int64_t p0 = upper ? diag[i] + 1 : rowptr[i], m = len(i);
-          for (int64_t j = 0; j < m; ++j) {  // entry j: lane j mod 8 of the row, slab j / 8 of its group
-            const int32_t cp = pos[col[p0 + j]];  // a row of an earlier level: cp < k0
-            const size_t q = q0 + ((size_t)(r >> 2) * slabs + (size_t)(j >> 3)) * 32 + 8 * (r & 3) + (j & 7);
-            slots[q].z = k1 - cp <= TRI_W ? cp : ~cp;
-            fsrc[q] = p0 + j;
-          }
-          ra_src[k0 + r] = upper ? (*pos_fwd)[i] : (int32_t)i;
-        }
-      }
-      if (slots.size() >= (size_t)1 << 30) return fail(NSG_ERR_ARG, "the level-order layout of the triangular solve is too large");
-      info[nl] = make_int4((int)slots.size(), 0, 0, (int)n);
-      int32_t in_place = 0;
-      for (int32_t l = 0; l < nl; ++l) {  // levels l - TRI_DEPTH .. l share the rings while level l is staged
-        const int32_t f = std::max(l - TRI_DEPTH, 0);
-        info[l].z = (info[l + 1].x - info[f].x <= TRI_RQ && info[l + 1].w - info[f].w <= TRI_RK) ? 1 : 0;
-        in_place += info[l].z ? 0 : 1;
-      }
-      T.n_levels = nl, T.nq = (int64_t)slots.size();
+      TriLayout lay;  // nsg_tri_layout.h
+      const int lrc = tri_layout(upper, n, rowptr.data(), col.data(), diag.data(), rows_by_level, ptr, pos_fwd, lim, lay);
+      if (lrc) return fail(NSG_ERR_ARG, lrc == 1 ? "a row with more than 2^19 entries" : "the level-order layout of the triangular solve is too large");
+      pos.swap(lay.pos);
+      const int32_t nl = lay.n_levels;
+      T.n_levels = nl, T.nq = lay.nq;
       // measured: ~0.35 us per staged level + ~0.4 us per pass of the compute warps over its groups (0.76 us per level on
       // the 51 842-row block), L2 round trips more per level read in place, 16 bytes per slot through one SM
       for (int32_t l = 0; l < nl; ++l) t_cta += 0.35e-6 + 0.4e-6 * ((ptr[l + 1] - ptr[l] + 4 * TRI_CW - 1) / (4 * TRI_CW));
-      t_cta += 1.5e-6 * in_place + 16.0 * (double)slots.size() / 60e9;
-      slots.push_back(make_int4(0, 0, 0, 0)), fsrc.push_back(-1);
-      NSG_TRY(upload(c, &T.info, info.data(), nl + 1));
-      NSG_TRY(upload(c, &T.slots, slots.data(), (int64_t)slots.size()));
-      NSG_TRY(upload(c, &T.fsrc, fsrc.data(), (int64_t)fsrc.size()));
-      NSG_TRY(upload(c, &T.ra_src, ra_src.data(), n));
-      NSG_TRY(upload(c, &T.rowid, rows.data(), n));
+      t_cta += 1.5e-6 * lay.in_place + 16.0 * (double)lay.nq / 60e9;
+      NSG_TRY(upload(c, &T.info, reinterpret_cast<const int4 *>(lay.info.data()), nl + 1));
+      NSG_TRY(upload(c, &T.slots, reinterpret_cast<const int4 *>(lay.slots.data()), (int64_t)lay.slots.size()));
+      NSG_TRY(upload(c, &T.fsrc, lay.fsrc.data(), (int64_t)lay.fsrc.size()));
+      NSG_TRY(upload(c, &T.ra_src, lay.ra_src.data(), n));
+      NSG_TRY(upload(c, &T.rowid, lay.rows.data(), n));
       NSG_TRY(dev_alloc(&T.rows, n + 1));
       NSG_TRY(dev_alloc(&T.yg, n + 2));
       NSG_CUDA(cudaMemsetAsync(T.rows, 0, sizeof(double2) * (size_t)(n + 1), c->stream));
