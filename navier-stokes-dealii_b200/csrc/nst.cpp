@@ -757,20 +757,18 @@ int nst_mesh_boundary_faces(const nst_mesh *m, int32_t *out_cell, int32_t *out_f
 // ---------------------------------------------------------------------------------------
 // partition: recursive coordinate bisection of cell centroids
 // ---------------------------------------------------------------------------------------
-static void rcb(const nst_mesh *m, std::vector<int32_t> &ids, int64_t lo, int64_t hi, int p0, int np,
-                int32_t *part) {
+// Recursive coordinate bisection of the cell centroids.  The part of a cell depends only on the SETS the bisections produce
+// (the `mid - lo` smallest cells under the total order (coordinate, cell id)), so the two halves can run as OpenMP tasks and
+// the result does not depend on the thread count.
+static void rcb(const double *cen, std::vector<int32_t> &ids, int64_t lo, int64_t hi, int p0, int np, int32_t *part) {
   if (np == 1) {
     for (int64_t i = lo; i < hi; ++i) part[ids[i]] = p0;
     return;
   }
   double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
-  auto cen = [&](int32_t c, int d) {
-    const int32_t *v = &m->cells[3 * (int64_t)c];
-    return (m->xy[2 * v[0] + d] + m->xy[2 * v[1] + d] + m->xy[2 * v[2] + d]) / 3.0;
-  };
   for (int64_t i = lo; i < hi; ++i)
     for (int d = 0; d < 2; ++d) {
-      const double x = cen(ids[i], d);
+      const double x = cen[2 * (int64_t)ids[i] + d];
       mn[d] = std::min(mn[d], x);
       mx[d] = std::max(mx[d], x);
     }
@@ -778,18 +776,29 @@ static void rcb(const nst_mesh *m, std::vector<int32_t> &ids, int64_t lo, int64_
   const int npl = np / 2;
   const int64_t mid = lo + (hi - lo) * npl / np;
   std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int32_t a, int32_t b) {
-    const double xa = cen(a, d), xb = cen(b, d);
+    const double xa = cen[2 * (int64_t)a + d], xb = cen[2 * (int64_t)b + d];
     return xa < xb || (xa == xb && a < b);
   });
-  rcb(m, ids, lo, mid, p0, npl, part);
-  rcb(m, ids, mid, hi, p0 + npl, np - npl, part);
+#pragma omp task shared(ids) if (hi - lo > 100000)
+  rcb(cen, ids, lo, mid, p0, npl, part);
+#pragma omp task shared(ids) if (hi - lo > 100000)
+  rcb(cen, ids, mid, hi, p0 + npl, np - npl, part);
+#pragma omp taskwait
 }
 
 int nst_partition_rcb(const nst_mesh *m, int n_parts, int32_t *cell_part) {
   if (!m || !cell_part || n_parts < 1) return fail(NST_ERR_ARG, "bad argument");
   std::vector<int32_t> ids(m->T);
   std::iota(ids.begin(), ids.end(), 0);
-  rcb(m, ids, 0, m->T, 0, n_parts, cell_part);
+  std::vector<double> cen(2 * (size_t)m->T);  // centroids once: the comparator of nth_element reads them many times
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < m->T; ++c) {
+    const int32_t *v = &m->cells[3 * c];
+    for (int d = 0; d < 2; ++d) cen[2 * c + d] = (m->xy[2 * v[0] + d] + m->xy[2 * v[1] + d] + m->xy[2 * v[2] + d]) / 3.0;
+  }
+#pragma omp parallel
+#pragma omp single
+  rcb(cen.data(), ids, 0, m->T, 0, n_parts, cell_part);
   return NST_OK;
 }
 
